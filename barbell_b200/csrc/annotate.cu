@@ -1,0 +1,594 @@
+// Host engine + C ABI of the annotate hot path (see include/barbell_b200.h).
+// One Engine = one CUDA stream with its own device buffers; a bb_ctx owns BB_MAX_INFLIGHT engines so that the
+// host->device copy of one batch overlaps the kernels of the previous one (bb_submit / bb_collect).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <condition_variable>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_select.cuh>
+#include <deque>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "kernels.cuh"
+
+namespace bb {
+
+#define BB_CUDA(call)                                                                              \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return BB_ERR_CUDA;                                                                    \
+        }                                                                                          \
+    } while (0)
+
+struct DBuf {   // growable device buffer
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return static_cast<T*>(p); }
+};
+
+// ---------------- host-side tables (same alphabet policy S7 as the oracle) ----------------
+struct Alphabet {
+    uint8_t code[256];
+    uint8_t rcchar[256];
+    Alphabet() {
+        std::memset(code, 0, sizeof code);
+        const char* L = "ACGTURYSWKMBDHVN";
+        const uint8_t V[] = {1, 2, 4, 8, 8, 5, 10, 6, 9, 12, 3, 14, 13, 11, 7, 15};
+        for (int i = 0; L[i]; i++) { code[static_cast<uint8_t>(L[i])] = V[i]; code[static_cast<uint8_t>(L[i] | 0x20)] = V[i]; }
+        for (int i = 0; i < 256; i++) rcchar[i] = static_cast<uint8_t>(i);
+        const char *a = "ACTGRYSWKMBDHVNX", *b = "TGACYRSWMKVHDBNX";   // reference barcodes.rs:398-441
+        for (int i = 0; a[i]; i++) {
+            rcchar[static_cast<uint8_t>(a[i])] = static_cast<uint8_t>(b[i]);
+            rcchar[static_cast<uint8_t>(a[i] | 0x20)] = static_cast<uint8_t>(b[i] | 0x20);
+        }
+    }
+    static uint8_t comp(uint8_t c) { return static_cast<uint8_t>(((c & 1) << 3) | ((c & 2) << 1) | ((c & 4) >> 1) | ((c & 8) >> 3)); }
+};
+static const Alphabet kAlpha;
+
+static double lodhi_all_match(int l) {   // reference searcher.rs:229-239 with the recurrence of orc_lodhi / k_barcode
+    volatile double a1 = 0.0, a2 = 0.0, s = 0.0;
+    for (int p = 0; p < l; p++) { s = s + 0.5 * a2; a2 = 0.5 * (a2 + a1); a1 = 0.5 * (a1 + 1.0); }
+    return s;
+}
+
+struct GroupTables {          // device copies for all groups of a ctx (shared by its engines)
+    std::vector<DevGroup> host;
+    DBuf d_groups, d_blob, d_code;
+    int n = 0, max_trace_cols = 0, max_nw = 1;
+    void release() { d_groups.release(); d_blob.release(); d_code.release(); host.clear(); n = 0; }
+};
+
+struct Engine {
+    int device = 0;
+    cudaStream_t stream = nullptr;       // owned stream for bb_annotate / bb_submit
+    const GroupTables* gt = nullptr;
+    Params prm{};
+    std::string err;
+    uint64_t launches = 0;
+    // device buffers
+    DBuf d_bases, d_offsets, d_entries, d_sorted, d_cub, d_flags, d_hitkeys, d_hits, d_hist, d_rows, d_valid, d_rows_out, d_hits6;
+    DBuf d_counters;                     // [0] n_entries (u32) [2] n_selected (u32) [4..5] kept reads (u64)
+    uint32_t entries_cap = 0;
+    uint32_t* h_counters = nullptr;      // pinned, 8 x u32
+    bb_row* h_rows = nullptr; size_t h_rows_cap = 0;   // pinned
+    cudaEvent_t ev[6] = {};
+    float stage_ms[5] = {0, 0, 0, 0, 0};
+    uint32_t last_hits = 0;
+    uint64_t last_rows = 0, last_reads = 0, last_kept = 0;
+
+    void set_error(const char* fmt, ...) {
+        char buf[512];
+        va_list ap; va_start(ap, fmt); std::vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+        err = buf;
+    }
+    int init(int dev) {
+        device = dev;
+        BB_CUDA(cudaSetDevice(device));
+        BB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        BB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&h_counters), 64));
+        BB_CUDA(d_counters.ensure(64));
+        for (auto& e : ev) BB_CUDA(cudaEventCreate(&e));
+        return BB_OK;
+    }
+    void destroy() {
+        cudaSetDevice(device);
+        for (DBuf* b : {&d_bases, &d_offsets, &d_entries, &d_sorted, &d_cub, &d_flags, &d_hitkeys, &d_hits, &d_hist, &d_rows,
+                        &d_valid, &d_rows_out, &d_hits6, &d_counters})
+            b->release();
+        if (h_counters) cudaFreeHost(h_counters);
+        if (h_rows) cudaFreeHost(h_rows);
+        for (auto& e : ev) if (e) cudaEventDestroy(e);
+        if (stream) cudaStreamDestroy(stream);
+    }
+    int ensure_host_rows(size_t n) {
+        if (n <= h_rows_cap) return BB_OK;
+        if (h_rows) cudaFreeHost(h_rows);
+        h_rows = nullptr; h_rows_cap = 0;
+        size_t want = n + n / 2 + 1024;
+        BB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&h_rows), want * sizeof(bb_row)));
+        h_rows_cap = want;
+        return BB_OK;
+    }
+
+    // The whole device pipeline on stream `st`; inputs resident on the device.
+    int run(const uint8_t* bases, const uint64_t* offsets, uint32_t n_reads, uint64_t total, cudaStream_t st, uint64_t* n_rows) {
+        if (!gt || gt->n == 0) { set_error("bb_set_groups has not been called"); return BB_ERR_INVALID; }
+        if (n_reads > kMaxBatchReads) { set_error("batch of %u reads exceeds the limit of %u", n_reads, kMaxBatchReads); return BB_ERR_INVALID; }
+        if ((reinterpret_cast<uintptr_t>(bases) & 15) != 0) { set_error("bases must be 16-byte aligned"); return BB_ERR_INVALID; }
+        BB_CUDA(cudaSetDevice(device));
+        last_reads = n_reads; last_rows = 0; last_hits = 0; last_kept = 0;
+        *n_rows = 0;
+        for (float& f : stage_ms) f = 0.f;
+        if (n_reads == 0 || total == 0) return BB_OK;
+        const uint64_t total16 = (total + 15) & ~15ull;
+        uint32_t* d_cnt = d_counters.as<uint32_t>();
+        BB_CUDA(cudaEventRecord(ev[0], st));
+
+        // ---- K1: flank scan, one launch per group ----
+        uint32_t n_entries = 0;
+        for (int attempt = 0; attempt < 4; attempt++) {
+            if (entries_cap == 0) {
+                uint64_t want = std::max<uint64_t>(1u << 20, static_cast<uint64_t>(n_reads) * 32);
+                entries_cap = static_cast<uint32_t>(std::min<uint64_t>(want, 1u << 28));
+            }
+            BB_CUDA(d_entries.ensure(static_cast<size_t>(entries_cap) * 8));
+            BB_CUDA(cudaMemsetAsync(d_cnt, 0, 64, st));
+            for (int g = 0; g < gt->n; g++) {
+                const DevGroup& G = gt->host[g];
+                ScanArgs A{};
+                A.bases = bases; A.offsets = offsets; A.n_reads = n_reads; A.total = total; A.total16 = total16;
+                A.group = g; A.chunk = 336;
+                A.entries = d_entries.as<uint64_t>(); A.n_entries = d_cnt; A.cap = entries_cap;
+                const uint64_t tile = static_cast<uint64_t>(kScanThreads) * A.chunk;
+                const unsigned grid = static_cast<unsigned>((total + tile - 1) / tile);
+                const size_t smem = 128 + 2 * 256 * G.nw * sizeof(uint64_t) + 2 * static_cast<size_t>(G.halo) + tile;
+                if (G.nw == 1) {
+                    BB_CUDA(cudaFuncSetAttribute(k_flank_scan<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+                    k_flank_scan<1><<<grid, kScanThreads, smem, st>>>(A, G);
+                } else {
+                    BB_CUDA(cudaFuncSetAttribute(k_flank_scan<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+                    k_flank_scan<2><<<grid, kScanThreads, smem, st>>>(A, G);
+                }
+                launches++;
+                BB_CUDA(cudaGetLastError());
+            }
+            BB_CUDA(cudaMemcpyAsync(h_counters, d_cnt, 4, cudaMemcpyDeviceToHost, st));
+            BB_CUDA(cudaStreamSynchronize(st));
+            n_entries = h_counters[0];
+            if (n_entries <= entries_cap) break;
+            if (attempt == 3 || n_entries > (1u << 28)) { set_error("flank scan produced %u sub-threshold positions; batch too dense", n_entries); return BB_ERR_INVALID; }
+            entries_cap = static_cast<uint32_t>(std::min<uint64_t>(static_cast<uint64_t>(n_entries) + n_entries / 4, 1u << 28));
+        }
+        BB_CUDA(cudaEventRecord(ev[1], st));
+        if (n_entries == 0) { return finish_timing(st, 1); }
+
+        // ---- sort entries by (read, group, strand, position) and apply the local-minimum rule ----
+        BB_CUDA(d_sorted.ensure(static_cast<size_t>(n_entries) * 8));
+        {
+            size_t tmp = 0;
+            int end_bit = kKeyReadShift;
+            while (end_bit < 64 && (static_cast<uint64_t>(n_reads) >> (end_bit - kKeyReadShift)) != 0) end_bit++;
+            cub::DeviceRadixSort::SortKeys(nullptr, tmp, d_entries.as<uint64_t>(), d_sorted.as<uint64_t>(), static_cast<int>(n_entries), kKeyPosShift, end_bit, st);
+            BB_CUDA(d_cub.ensure(tmp));
+            BB_CUDA(cub::DeviceRadixSort::SortKeys(d_cub.p, tmp, d_entries.as<uint64_t>(), d_sorted.as<uint64_t>(), static_cast<int>(n_entries), kKeyPosShift, end_bit, st));
+        }
+        BB_CUDA(d_flags.ensure(n_entries));
+        k_resolve<<<(n_entries + 255) / 256, 256, 0, st>>>(d_sorted.as<uint64_t>(), n_entries, offsets, d_groups(), d_flags.as<uint8_t>());
+        launches++;
+        BB_CUDA(cudaGetLastError());
+        BB_CUDA(d_hitkeys.ensure(static_cast<size_t>(n_entries) * 8));
+        {
+            size_t tmp = 0;
+            cub::DeviceSelect::Flagged(nullptr, tmp, d_sorted.as<uint64_t>(), d_flags.as<uint8_t>(), d_hitkeys.as<uint64_t>(), d_cnt + 2, static_cast<int>(n_entries), st);
+            BB_CUDA(d_cub.ensure(tmp));
+            BB_CUDA(cub::DeviceSelect::Flagged(d_cub.p, tmp, d_sorted.as<uint64_t>(), d_flags.as<uint8_t>(), d_hitkeys.as<uint64_t>(), d_cnt + 2, static_cast<int>(n_entries), st));
+        }
+        BB_CUDA(cudaMemcpyAsync(h_counters + 2, d_cnt + 2, 4, cudaMemcpyDeviceToHost, st));
+        BB_CUDA(cudaStreamSynchronize(st));
+        const uint32_t n_hits = h_counters[2];
+        last_hits = n_hits;
+        BB_CUDA(cudaEventRecord(ev[2], st));
+        if (n_hits == 0) { return finish_timing(st, 2); }
+
+        // ---- K2b: traceback of the flank matches ----
+        BB_CUDA(d_hits.ensure(static_cast<size_t>(n_hits) * sizeof(Hit)));
+        {
+            TraceArgs T{};
+            const unsigned blocks = std::min<unsigned>((n_hits + 63) / 64, 148 * 4);
+            T.n_slots = blocks * 64;
+            BB_CUDA(d_hist.ensure(static_cast<size_t>(gt->max_trace_cols + 2) * 2 * gt->max_nw * 8 * T.n_slots));
+            T.bases = bases; T.offsets = offsets; T.hit_keys = d_hitkeys.as<uint64_t>(); T.n_hits = n_hits;
+            T.groups = d_groups(); T.hist = d_hist.as<uint64_t>(); T.hits = d_hits.as<Hit>();
+            k_trace<<<blocks, 64, 0, st>>>(T);
+            launches++;
+            BB_CUDA(cudaGetLastError());
+        }
+        BB_CUDA(cudaEventRecord(ev[3], st));
+
+        // ---- K3: barcode stage ----
+        BB_CUDA(d_rows.ensure(static_cast<size_t>(n_hits) * sizeof(bb_row)));
+        BB_CUDA(d_valid.ensure(n_hits));
+        {
+            BarArgs B{};
+            B.bases = bases; B.offsets = offsets; B.hits = d_hits.as<Hit>(); B.n_hits = n_hits; B.groups = d_groups();
+            B.code = gt->d_code.as<uint8_t>(); B.prm = prm; B.rows = d_rows.as<bb_row>(); B.row_valid = d_valid.as<uint8_t>();
+            const unsigned blocks = std::min<unsigned>((n_hits + kBarWarps - 1) / kBarWarps, 148 * 8);
+            k_barcode<<<blocks, kBarWarps * 32, 0, st>>>(B);
+            launches++;
+            BB_CUDA(cudaGetLastError());
+        }
+        BB_CUDA(cudaEventRecord(ev[4], st));
+
+        // ---- K4: collapse + ordered compaction ----
+        unsigned long long* d_kept = reinterpret_cast<unsigned long long*>(d_cnt + 4);
+        k_collapse<<<(n_hits + 127) / 128, 128, 0, st>>>(d_hits.as<Hit>(), n_hits, d_rows.as<bb_row>(), d_valid.as<uint8_t>(), d_kept);
+        launches++;
+        BB_CUDA(cudaGetLastError());
+        BB_CUDA(d_rows_out.ensure(static_cast<size_t>(n_hits) * sizeof(bb_row)));
+        {
+            size_t tmp = 0;
+            cub::DeviceSelect::Flagged(nullptr, tmp, d_rows.as<bb_row>(), d_valid.as<uint8_t>(), d_rows_out.as<bb_row>(), d_cnt + 3, static_cast<int>(n_hits), st);
+            BB_CUDA(d_cub.ensure(tmp));
+            BB_CUDA(cub::DeviceSelect::Flagged(d_cub.p, tmp, d_rows.as<bb_row>(), d_valid.as<uint8_t>(), d_rows_out.as<bb_row>(), d_cnt + 3, static_cast<int>(n_hits), st));
+        }
+        BB_CUDA(cudaMemcpyAsync(h_counters + 3, d_cnt + 3, 12, cudaMemcpyDeviceToHost, st));
+        int rc = finish_timing(st, 5);
+        if (rc != BB_OK) return rc;
+        last_rows = h_counters[3];
+        std::memcpy(&last_kept, h_counters + 4, 8);
+        *n_rows = last_rows;
+        return BB_OK;
+    }
+    const DevGroup* d_groups() const { return gt->d_groups.as<DevGroup>(); }
+    int finish_timing(cudaStream_t st, int n_stages) {
+        BB_CUDA(cudaEventRecord(ev[5], st));
+        BB_CUDA(cudaStreamSynchronize(st));
+        for (int s = 0; s < n_stages && s < 5; s++) {
+            cudaEvent_t b = ev[s], e = (s + 1 < n_stages) ? ev[s + 1] : ev[5];
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, b, e) == cudaSuccess) stage_ms[s] = ms;
+        }
+        return BB_OK;
+    }
+
+    // host-buffer form: copy in, run, copy rows to pinned memory
+    int run_host(const uint8_t* bases, const uint64_t* offsets, uint32_t n_reads, uint64_t* n_rows) {
+        BB_CUDA(cudaSetDevice(device));
+        *n_rows = 0;
+        if (n_reads == 0) { last_reads = 0; last_rows = 0; last_kept = 0; return BB_OK; }
+        const uint64_t total = offsets[n_reads] - offsets[0];
+        if (offsets[0] != 0) { set_error("offsets[0] must be 0"); return BB_ERR_INVALID; }
+        BB_CUDA(d_bases.ensure(((total + 15) & ~15ull) + 16));
+        BB_CUDA(d_offsets.ensure(static_cast<size_t>(n_reads + 1) * 8));
+        BB_CUDA(cudaMemcpyAsync(d_bases.p, bases, total, cudaMemcpyHostToDevice, stream));
+        BB_CUDA(cudaMemcpyAsync(d_offsets.p, offsets, static_cast<size_t>(n_reads + 1) * 8, cudaMemcpyHostToDevice, stream));
+        int rc = run(d_bases.as<uint8_t>(), d_offsets.as<uint64_t>(), n_reads, total, stream, n_rows);
+        if (rc != BB_OK) return rc;
+        if (*n_rows) {
+            rc = ensure_host_rows(*n_rows);
+            if (rc != BB_OK) return rc;
+            BB_CUDA(cudaMemcpyAsync(h_rows, d_rows_out.p, *n_rows * sizeof(bb_row), cudaMemcpyDeviceToHost, stream));
+            BB_CUDA(cudaStreamSynchronize(stream));
+        }
+        return BB_OK;
+    }
+};
+
+}  // namespace bb
+
+// ---------------------------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------------------------
+struct bb_job {
+    const uint8_t* bases; const uint64_t* offsets; uint32_t n_reads; uint64_t tag; int engine;
+    int rc = 0; uint64_t n_rows = 0; bool done = false;
+};
+
+struct bb_ctx {
+    bb_opts opts{};
+    bb::GroupTables gt;
+    bb::Engine eng[BB_MAX_INFLIGHT];
+    std::string err;
+    uint64_t total_reads = 0, kept_reads = 0;
+    // pipelined mode: one worker thread per engine
+    std::thread workers[BB_MAX_INFLIGHT];
+    std::mutex mu;
+    std::condition_variable cv;
+    std::deque<bb_job*> queue[BB_MAX_INFLIGHT];   // per engine FIFO
+    std::deque<bb_job*> order;                     // submission order
+    bool stop = false, workers_started = false;
+    uint64_t submitted = 0;
+    int last_engine = 0;
+};
+
+static void ctx_error(bb_ctx* c, const std::string& s) { c->err = s; }
+
+static void worker_main(bb_ctx* c, int idx) {
+    for (;;) {
+        bb_job* job = nullptr;
+        {
+            std::unique_lock<std::mutex> lk(c->mu);
+            c->cv.wait(lk, [&] { return c->stop || !c->queue[idx].empty(); });
+            if (c->queue[idx].empty()) return;
+            job = c->queue[idx].front();
+        }
+        uint64_t n_rows = 0;
+        const int rc = c->eng[idx].run_host(job->bases, job->offsets, job->n_reads, &n_rows);
+        {
+            std::lock_guard<std::mutex> lk(c->mu);
+            job->rc = rc; job->n_rows = n_rows; job->done = true;
+            c->queue[idx].pop_front();
+        }
+        c->cv.notify_all();
+    }
+}
+
+extern "C" {
+
+int bb_create(const bb_opts* opts, bb_ctx** out, char* err, size_t errlen) {
+    auto fail = [&](int code, const std::string& msg) { if (err && errlen) std::snprintf(err, errlen, "%s", msg.c_str()); return code; };
+    if (!opts || !out) return fail(BB_ERR_INVALID, "null argument");
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev == 0)
+        return fail(BB_ERR_NO_DEVICE, std::string("no CUDA device available (") + cudaGetErrorString(e) + "); barbell_b200 has no CPU path");
+    if (opts->device < 0 || opts->device >= n_dev) return fail(BB_ERR_INVALID, "device ordinal out of range");
+    if (!(opts->alpha > 0.0f) || !(opts->alpha <= 1.0f)) return fail(BB_ERR_INVALID, "alpha must be in (0, 1]");
+    cudaDeviceProp prop{};
+    cudaGetDeviceProperties(&prop, opts->device);
+    if (prop.major < 10) return fail(BB_ERR_NO_DEVICE, "barbell_b200 is built for sm_100a (B200) only");
+    auto* c = new bb_ctx();
+    c->opts = *opts;
+    for (int i = 0; i < BB_MAX_INFLIGHT; i++) {
+        int rc = c->eng[i].init(opts->device);
+        if (rc != BB_OK) { std::string m = c->eng[i].err; for (int j = 0; j <= i; j++) c->eng[j].destroy(); delete c; return fail(rc, m); }
+        c->eng[i].gt = &c->gt;
+        c->eng[i].prm.min_score = opts->min_score; c->eng[i].prm.min_score_diff = opts->min_score_diff;
+    }
+    *out = c;
+    return BB_OK;
+}
+
+void bb_destroy(bb_ctx* c) {
+    if (!c) return;
+    if (c->workers_started) {
+        { std::lock_guard<std::mutex> lk(c->mu); c->stop = true; }
+        c->cv.notify_all();
+        for (auto& w : c->workers) if (w.joinable()) w.join();
+        for (auto* j : c->order) delete j;
+    }
+    cudaSetDevice(c->opts.device);
+    for (auto& e : c->eng) e.destroy();
+    c->gt.release();
+    delete c;
+}
+
+const char* bb_last_error(const bb_ctx* c) { return c ? c->err.c_str() : "null ctx"; }
+
+int bb_set_groups(bb_ctx* c, const bb_group* groups, int32_t n_groups) {
+    using namespace bb;
+    if (!c || !groups || n_groups <= 0) return BB_ERR_INVALID;
+    auto bad = [&](const std::string& m) { ctx_error(c, m); return BB_ERR_INVALID; };
+    if (n_groups > kMaxGroups) return bad("at most 8 query groups are supported");
+    if (cudaSetDevice(c->opts.device) != cudaSuccess) return bad("cudaSetDevice failed");
+    const float alpha = c->opts.alpha;
+    // blob layout per group: eq[2][256][nw] u64 | bar_eq[2][nb][16] u64 | ov[m+1] i32 (padded to 8)
+    std::vector<uint64_t> blob;
+    std::vector<size_t> off_eq(n_groups), off_bar(n_groups), off_ov(n_groups);
+    std::vector<DevGroup> hg(n_groups);
+    int max_trace = 0, max_nw = 1;
+    for (int g = 0; g < n_groups; g++) {
+        const bb_group& S = groups[g];
+        DevGroup& D = hg[g];
+        std::memset(&D, 0, sizeof D);
+        const int m = S.flank_len;
+        if (m < 1 || m > 64 * kMaxFlankWords) return bad("flank length must be 1..128");
+        if (S.bar_len < 1 || S.bar_len > kMaxBarLen) return bad("padded barcode length must be 1..64");
+        if (S.n_barcodes < 1 || S.n_barcodes > 32 * kMaxBarRounds) return bad("1..512 barcodes per group");
+        if (S.k_flank < 0 || S.k_flank > 120) return bad("flank threshold must be 0..120");
+        const int ov_m = static_cast<int>(std::floor(static_cast<float>(m) * alpha));
+        if (S.k_flank >= ov_m - 1) return bad("flank threshold too large for the overhang cost: need k < floor(alpha*len)-1");
+        if (S.bar1 - S.bar0 + 1 + S.k_flank + 2 * kPadding > kRegionMax) return bad("barcode region (mask + k + 20) exceeds 160 characters");
+        if (S.bar0 < 0 || S.bar1 < S.bar0 || S.bar1 >= m || S.pad0 < 0 || S.pad0 > S.bar0) return bad("inconsistent bar/pad regions");
+        D.m = m; D.nw = (m + 63) / 64; D.last_bit = (m - 1) & 63; D.k = S.k_flank;
+        D.bar0 = S.bar0; D.bar1 = S.bar1; D.pad0 = S.pad0; D.pad1 = S.pad1;
+        D.bar_len = S.bar_len; D.n_barcodes = S.n_barcodes; D.match_type = S.match_type;
+        D.k_bar = static_cast<int>(static_cast<float>(S.bar_len) * 0.4f);
+        D.pbar0 = S.bar0 - S.pad0; D.pbar1 = S.bar1 - S.pad0;
+        D.ov_m = ov_m; D.halo = ((m + S.k_flank) + 15) & ~15;
+        D.trace_cols = m + 2 * std::min(S.k_flank, m) + 8;
+        D.perfect = lodhi_all_match(S.pad1 - S.pad0);
+        max_trace = std::max(max_trace, D.trace_cols); max_nw = std::max(max_nw, D.nw);
+        std::vector<uint8_t> pc(m);
+        for (int i = 0; i < m; i++) pc[i] = kAlpha.code[static_cast<uint8_t>(S.flank[i])];
+        std::vector<int> ov(m + 1);
+        for (int t = 0; t <= m; t++) ov[t] = static_cast<int>(std::floor(static_cast<float>(t) * alpha));
+        for (int i = 0; i < m; i++) {
+            D.pv_plain[i >> 6] |= 1ull << (i & 63);
+            if (ov[i + 1] - ov[i]) D.pv_over[i >> 6] |= 1ull << (i & 63);
+        }
+        off_eq[g] = blob.size();
+        blob.resize(blob.size() + 2 * 256 * D.nw, 0);
+        for (int s = 0; s < 2; s++)
+            for (int ch = 0; ch < 256; ch++) {
+                uint8_t code = kAlpha.code[ch];
+                if (s == 1) code = Alphabet::comp(code);
+                for (int i = 0; i < m; i++)
+                    if (pc[i] & code) blob[off_eq[g] + (static_cast<size_t>(s) * 256 + ch) * D.nw + (i >> 6)] |= 1ull << (i & 63);
+            }
+        off_bar[g] = blob.size();
+        blob.resize(blob.size() + static_cast<size_t>(2) * S.n_barcodes * 16, 0);
+        for (int b = 0; b < S.n_barcodes; b++)
+            for (int i = 0; i < S.bar_len; i++) {
+                const uint8_t ch = static_cast<uint8_t>(S.barcodes[static_cast<size_t>(b) * S.bar_len + i]);
+                const uint8_t cf = kAlpha.code[ch], cr = kAlpha.code[kAlpha.rcchar[ch]];
+                const int ir = S.bar_len - 1 - i;
+                for (int code = 0; code < 16; code++) {
+                    if (cf & code) blob[off_bar[g] + (static_cast<size_t>(0) * S.n_barcodes + b) * 16 + code] |= 1ull << i;
+                    if (cr & code) blob[off_bar[g] + (static_cast<size_t>(1) * S.n_barcodes + b) * 16 + code] |= 1ull << ir;
+                }
+            }
+        off_ov[g] = blob.size();
+        blob.resize(blob.size() + (m + 2) / 2 + 1, 0);
+        std::memcpy(reinterpret_cast<int*>(blob.data() + off_ov[g]), ov.data(), sizeof(int) * (m + 1));
+    }
+    bb::GroupTables& T = c->gt;
+    for (auto& e : c->eng) cudaStreamSynchronize(e.stream);
+    if (T.d_blob.ensure(blob.size() * 8) != cudaSuccess || T.d_groups.ensure(sizeof(DevGroup) * n_groups) != cudaSuccess ||
+        T.d_code.ensure(256) != cudaSuccess)
+        return (ctx_error(c, "cudaMalloc failed for the pattern tables"), BB_ERR_CUDA);
+    const uint64_t* base = T.d_blob.as<uint64_t>();
+    for (int g = 0; g < n_groups; g++) {
+        hg[g].eq = base + off_eq[g];
+        hg[g].bar_eq = base + off_bar[g];
+        hg[g].ov = reinterpret_cast<const int*>(base + off_ov[g]);
+    }
+    cudaError_t e1 = cudaMemcpy(T.d_blob.p, blob.data(), blob.size() * 8, cudaMemcpyHostToDevice);
+    cudaError_t e2 = cudaMemcpy(T.d_groups.p, hg.data(), sizeof(DevGroup) * n_groups, cudaMemcpyHostToDevice);
+    cudaError_t e3 = cudaMemcpy(T.d_code.p, kAlpha.code, 256, cudaMemcpyHostToDevice);
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) return (ctx_error(c, "cudaMemcpy of the pattern tables failed"), BB_ERR_CUDA);
+    T.host = hg; T.n = n_groups; T.max_trace_cols = max_trace; T.max_nw = max_nw;
+    return BB_OK;
+}
+
+static int validate_offsets(bb_ctx* c, const uint64_t* offsets, uint32_t n_reads) {
+    for (uint32_t r = 0; r < n_reads; r++) {
+        if (offsets[r + 1] < offsets[r]) { ctx_error(c, "offsets must be non-decreasing"); return BB_ERR_INVALID; }
+        if (offsets[r + 1] - offsets[r] > bb::kMaxReadLen) { ctx_error(c, "read longer than 2^28 bases"); return BB_ERR_INVALID; }
+    }
+    return BB_OK;
+}
+
+int bb_annotate(bb_ctx* c, const uint8_t* bases, const uint64_t* offsets, uint32_t n_reads, bb_row* rows, uint64_t rows_cap, uint64_t* n_rows) {
+    if (!c || !offsets || !n_rows || (n_reads && !bases)) return BB_ERR_INVALID;
+    int rc = validate_offsets(c, offsets, n_reads);
+    if (rc != BB_OK) return rc;
+    bb::Engine& E = c->eng[0];
+    rc = E.run_host(bases, offsets, n_reads, n_rows);
+    c->last_engine = 0;
+    if (rc != BB_OK) { c->err = E.err; return rc; }
+    c->total_reads += n_reads; c->kept_reads += E.last_kept;
+    if (*n_rows > rows_cap) { ctx_error(c, "row buffer too small"); return BB_ERR_OVERFLOW; }
+    if (*n_rows) std::memcpy(rows, E.h_rows, *n_rows * sizeof(bb_row));
+    return BB_OK;
+}
+
+int bb_annotate_device(bb_ctx* c, const void* d_bases, const void* d_offsets, uint32_t n_reads, uint64_t total_bytes, void* stream, uint64_t* n_rows) {
+    if (!c || !n_rows) return BB_ERR_INVALID;
+    bb::Engine& E = c->eng[0];
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : E.stream;
+    int rc = E.run(static_cast<const uint8_t*>(d_bases), static_cast<const uint64_t*>(d_offsets), n_reads, total_bytes, st, n_rows);
+    c->last_engine = 0;
+    if (rc != BB_OK) { c->err = E.err; return rc; }
+    c->total_reads += n_reads; c->kept_reads += E.last_kept;
+    return BB_OK;
+}
+
+int bb_fetch_rows(bb_ctx* c, bb_row* rows, uint64_t rows_cap, uint64_t* n_rows) {
+    if (!c || !n_rows) return BB_ERR_INVALID;
+    bb::Engine& E = c->eng[c->last_engine];
+    *n_rows = E.last_rows;
+    if (E.last_rows > rows_cap) { ctx_error(c, "row buffer too small"); return BB_ERR_OVERFLOW; }
+    if (E.last_rows) {
+        cudaSetDevice(E.device);
+        cudaError_t e = cudaMemcpy(rows, E.d_rows_out.p, E.last_rows * sizeof(bb_row), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) { ctx_error(c, std::string("cudaMemcpy failed: ") + cudaGetErrorString(e)); return BB_ERR_CUDA; }
+    }
+    return BB_OK;
+}
+
+int bb_submit(bb_ctx* c, const uint8_t* bases, const uint64_t* offsets, uint32_t n_reads, uint64_t batch_tag) {
+    if (!c || !offsets || (n_reads && !bases)) return BB_ERR_INVALID;
+    int rc = validate_offsets(c, offsets, n_reads);
+    if (rc != BB_OK) return rc;
+    std::unique_lock<std::mutex> lk(c->mu);
+    if (!c->workers_started) {
+        for (int i = 0; i < BB_MAX_INFLIGHT; i++) c->workers[i] = std::thread(worker_main, c, i);
+        c->workers_started = true;
+    }
+    if (c->order.size() >= BB_MAX_INFLIGHT) { ctx_error(c, "too many batches in flight: call bb_collect first"); return BB_ERR_INVALID; }
+    const int idx = static_cast<int>(c->submitted % BB_MAX_INFLIGHT);
+    auto* job = new bb_job{bases, offsets, n_reads, batch_tag, idx};
+    c->queue[idx].push_back(job);
+    c->order.push_back(job);
+    c->submitted++;
+    lk.unlock();
+    c->cv.notify_all();
+    return BB_OK;
+}
+
+int bb_collect(bb_ctx* c, uint64_t* batch_tag, const bb_row** rows, uint64_t* n_rows) {
+    if (!c || !rows || !n_rows) return BB_ERR_INVALID;
+    std::unique_lock<std::mutex> lk(c->mu);
+    if (c->order.empty()) { ctx_error(c, "nothing in flight"); return BB_ERR_INVALID; }
+    bb_job* job = c->order.front();
+    c->cv.wait(lk, [&] { return job->done; });
+    c->order.pop_front();
+    const int idx = job->engine, rc = job->rc;
+    if (batch_tag) *batch_tag = job->tag;
+    *n_rows = job->n_rows;
+    *rows = c->eng[idx].h_rows;      // valid until the next bb_submit / bb_collect on this ctx
+    if (rc == BB_OK) { c->total_reads += job->n_reads; c->kept_reads += c->eng[idx].last_kept; c->last_engine = idx; }
+    else c->err = c->eng[idx].err;
+    delete job;
+    return rc;
+}
+
+int bb_counters(const bb_ctx* c, uint64_t out[3]) {
+    if (!c || !out) return BB_ERR_INVALID;
+    out[0] = c->total_reads; out[1] = c->kept_reads; out[2] = c->total_reads - c->kept_reads;
+    return BB_OK;
+}
+
+int bb_last_stage_ms(bb_ctx* c, float out[5]) {
+    if (!c || !out) return BB_ERR_INVALID;
+    for (int i = 0; i < 5; i++) out[i] = c->eng[c->last_engine].stage_ms[i];
+    return BB_OK;
+}
+
+uint64_t bb_kernel_launches(const bb_ctx* c) {
+    uint64_t n = 0;
+    if (c) for (const auto& e : c->eng) n += e.launches;
+    return n;
+}
+
+int bb_fetch_flank_hits(bb_ctx* c, int32_t* out6, uint64_t cap, uint64_t* n_hits) {
+    if (!c || !n_hits) return BB_ERR_INVALID;
+    bb::Engine& E = c->eng[c->last_engine];
+    *n_hits = E.last_hits;
+    if (E.last_hits > cap) { ctx_error(c, "hit buffer too small"); return BB_ERR_OVERFLOW; }
+    if (E.last_hits == 0) return BB_OK;
+    cudaSetDevice(E.device);
+    if (E.d_hits6.ensure(static_cast<size_t>(E.last_hits) * 24) != cudaSuccess) { ctx_error(c, "cudaMalloc failed"); return BB_ERR_CUDA; }
+    bb::k_export_hits<<<(E.last_hits + 255) / 256, 256, 0, E.stream>>>(E.d_hits.as<bb::Hit>(), E.last_hits, E.d_hits6.as<int32_t>());
+    E.launches++;
+    cudaError_t e = cudaMemcpyAsync(out6, E.d_hits6.p, static_cast<size_t>(E.last_hits) * 24, cudaMemcpyDeviceToHost, E.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(E.stream);
+    if (e != cudaSuccess) { ctx_error(c, std::string("export failed: ") + cudaGetErrorString(e)); return BB_ERR_CUDA; }
+    return BB_OK;
+}
+
+}  // extern "C"

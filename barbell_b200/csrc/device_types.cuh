@@ -1,0 +1,48 @@
+// Device-side view of the pattern sets and the intermediate records that flow between the kernels.
+#pragma once
+#include <cstdint>
+
+namespace bb {
+
+constexpr int kMaxGroups = 8;        // 3 key bits
+constexpr int kMaxFlankWords = 2;    // flank patterns up to 128 characters
+constexpr int kMaxBarLen = 64;       // padded barcode patterns fit one 64-bit word
+constexpr int kRegionMax = 160;      // longest barcode text region (mask + k_flank + 2*PADDING)
+constexpr int kPadding = 10;         // reference src/lib.rs:10
+
+// sort key of one sub-threshold end position produced by the flank scan
+//   [63:40] read (24 bit) | [39:37] group | [36] strand | [35:8] end position in the strand's frame | [7:0] cost
+constexpr int kKeyReadShift = 40, kKeyGroupShift = 37, kKeyStrandShift = 36, kKeyPosShift = 8;
+constexpr uint32_t kMaxBatchReads = 1u << 24;
+constexpr uint32_t kMaxReadLen = (1u << 28) - 512;
+
+struct DevGroup {
+    int m, nw, last_bit, k;              // flank length, 64-bit words, bit of the last row in the last word, k_flank
+    int bar0, bar1, pad0, pad1;          // reference barcodes.rs:160-192
+    int bar_len, n_barcodes, match_type, k_bar;   // k_bar = (int)(bar_len * 0.4f)   searcher.rs:460
+    int pbar0, pbar1;                    // bar0 - pad0, bar1 - pad0                   searcher.rs:379-382
+    int ov_m, halo;                      // floor(m*alpha); m + k rounded up to 16
+    int trace_cols, pad_;                // m + 2k + 8 (+1 columns of history)
+    double perfect;                      // Lodhi of pad1-pad0 matches                 searcher.rs:229-239
+    uint64_t pv_plain[kMaxFlankWords];   // first column D[i] = i
+    uint64_t pv_over[kMaxFlankWords];    // first column D[i] = floor(i*alpha)
+    const uint64_t* eq;                  // [2 strands][256 bytes][nw]  flank match masks indexed by the raw text byte
+    const int* ov;                       // [m+1] floor(t*alpha)
+    const uint64_t* bar_eq;              // [2 strands][n_barcodes][16 codes]
+};
+
+struct Params {
+    double min_score, min_score_diff;
+    int n_groups;
+};
+
+// one reported flank match (sassy Match of the overhang searcher) + the barcode text region
+struct Hit {
+    uint32_t read;
+    int32_t group, strand;
+    int32_t text_start, text_end, cost;  // forward text coordinates
+    int32_t rs, re;                      // padded barcode region [rs, re) in forward text coordinates
+    int32_t has_region;                  // get_matching_region returned Some
+};
+
+}  // namespace bb

@@ -1,0 +1,137 @@
+/*
+ * barbell_b200.h -- C ABI of the B200-native `annotate` hot path (libbarbell_b200.so).
+ *
+ * This is the drop-in boundary a Rust host (rickbeeloo/barbell @ 9a2b814) binds with `extern "C"`; see
+ * INTEGRATION.md for the binding.  No strings, no torch types, no C++ types cross it: plain pointers and sizes.
+ * Every entry point cites the reference interface it replaces (paths relative to the reference root).
+ *
+ * Threading: a bb_ctx belongs to one host thread and one GPU (the reference keeps one Demuxer per worker thread,
+ * src/annotate/annotator.rs:88-101).  Errors: every call returns 0 on success or a negative bb_status; the message is
+ * available through bb_last_error().  There is NO CPU fallback: without a CUDA device bb_create fails.
+ */
+#ifndef BARBELL_B200_H
+#define BARBELL_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BB_ABI_VERSION 1
+
+typedef enum {
+    BB_OK = 0,
+    BB_ERR_INVALID = -1,      /* bad argument / unsupported geometry (message says which) */
+    BB_ERR_CUDA = -2,         /* CUDA runtime error (sticky on the ctx) */
+    BB_ERR_OVERFLOW = -3,     /* caller's row buffer too small (n_rows tells how many were produced) */
+    BB_ERR_NO_DEVICE = -4,    /* no CUDA device: the product has no CPU path */
+    BB_ERR_KIT = -5,          /* unknown kit / malformed query set (the reference panics: kits.rs:704, barcodes.rs:113-143) */
+    BB_ERR_IO = -6
+} bb_status;
+
+/* BarcodeType, src/annotate/barcodes.rs:8-14 */
+enum { BB_FTAG = 0, BB_RTAG = 1, BB_FFLANK = 2, BB_RFLANK = 3 };
+/* sassy::Strand as serialised in annotation.tsv, src/annotate/searcher.rs:100-142 */
+enum { BB_FWD = 0, BB_RC = 1 };
+
+/* One BarcodeGroup (src/annotate/barcodes.rs:57-71) in flat form. */
+typedef struct {
+    const char *flank;      /* prefix + 'N'*mask + suffix                        barcodes.rs:145-154 */
+    int32_t flank_len;
+    int32_t k_flank;        /* k_cutoff after set_flank_threshold                annotator.rs:216-229 */
+    int32_t bar0, bar1;     /* bar_region, INCLUSIVE end                         barcodes.rs:192 */
+    int32_t pad0, pad1;     /* pad_region, pad1 not clamped to the sequence      barcodes.rs:160-163 */
+    int32_t match_type;     /* BB_FTAG / BB_RTAG */
+    int32_t n_barcodes;
+    int32_t bar_len;        /* length of every padded barcode pattern            barcodes.rs:165-173 */
+    const char *barcodes;   /* n_barcodes * bar_len bytes, forward orientation */
+} bb_group;
+
+/* One annotation.tsv row (BarbellMatch, src/annotate/searcher.rs:31-64) without its strings:
+   read_id is the caller's (read_idx), label is bb_groupset_label(group_idx, label_idx) or "flank" when -1. */
+typedef struct {
+    uint32_t read_idx;      /* index of the read inside the submitted batch */
+    uint32_t read_len;
+    int64_t  rel_dist_to_end;
+    int64_t  read_start_bar, read_end_bar;
+    int64_t  read_start_flank, read_end_flank;
+    int64_t  bar_start, bar_end;
+    int32_t  flank_cost, barcode_cost;
+    int32_t  label_idx;
+    int32_t  group_idx;
+    uint8_t  match_type;
+    uint8_t  strand;
+    uint8_t  pad_[6];
+} bb_row;
+
+/* AnnotateConfig (src/config.rs:3-12) fields the search needs + device selection. */
+typedef struct {
+    int32_t device;             /* CUDA device ordinal */
+    float   alpha;              /* --alpha, bin/main.rs:110-111 (default 0.4) */
+    double  min_score;          /* --min-score, bin/main.rs:98-101 (default 0.2) */
+    double  min_score_diff;     /* --min-score-diff, bin/main.rs:102-105 (default 0.1) */
+    uint64_t max_batch_bytes;   /* capacity of the staging buffers for bb_annotate (0 = 256 MiB) */
+    uint32_t max_batch_reads;   /* (0 = 4 Mi reads) */
+    uint32_t flags;             /* reserved, 0 */
+} bb_opts;
+
+typedef struct bb_ctx bb_ctx;
+typedef struct bb_groupset bb_groupset;
+
+/* ---- pattern-set construction (host side; replaces BarcodeGroup::new_from_kit / new_from_fasta / new,
+ *      src/annotate/barcodes.rs:106-197, 251-315, and get_kit_info, src/kits/kits.rs:635-708) ---- */
+int  bb_groups_from_kit(const char *kit, int use_extended, bb_groupset **out, char *err, size_t errlen);
+/* one FASTA per group; types[i] = BB_FTAG / BB_RTAG (bin/main.rs:78-96) */
+int  bb_groups_from_fasta(const char *const *paths, const int32_t *types, int32_t n, bb_groupset **out, char *err,
+                          size_t errlen);
+/* one group from in-memory sequences (BarcodeGroup::new); appends to *out if it is non-NULL */
+int  bb_groups_add(bb_groupset **out, const char *const *seqs, const char *const *labels, int32_t n, int32_t type,
+                   char *err, size_t errlen);
+/* annotate_with_groups, annotator.rs:216-229: max_flank_errors < 0 selects get_edit_cut_off(prefix+suffix) */
+int  bb_groups_set_flank_threshold(bb_groupset *gs, int32_t max_flank_errors);
+int32_t bb_groups_count(const bb_groupset *gs);
+const bb_group *bb_groups_data(const bb_groupset *gs);
+const char *bb_groups_label(const bb_groupset *gs, int32_t group_idx, int32_t label_idx);
+void bb_groups_free(bb_groupset *gs);
+/* get_edit_cut_off, src/annotate/edit_model.rs:2-11 */
+int32_t bb_edit_cut_off(int32_t effective_len);
+
+/* ---- the operator (replaces Demuxer::{new,add_query_group,demux}, src/annotate/searcher.rs:202-227, 430-490) ---- */
+int  bb_create(const bb_opts *opts, bb_ctx **out, char *err, size_t errlen);
+void bb_destroy(bb_ctx *ctx);
+const char *bb_last_error(const bb_ctx *ctx);
+int  bb_set_groups(bb_ctx *ctx, const bb_group *groups, int32_t n_groups);
+
+/* Batch form of DemuxProcessor::process_record (annotator.rs:122-135) with HOST buffers: `bases` holds the reads'
+   raw sequence bytes back to back, offsets[n_reads+1] their byte offsets.  Rows come back grouped by read in input
+   order, within a read in collapse_overlapping_matches order (interval.rs:4-28).  Reads without a hit emit no row. */
+int  bb_annotate(bb_ctx *ctx, const uint8_t *bases, const uint64_t *offsets, uint32_t n_reads, bb_row *rows,
+                 uint64_t rows_cap, uint64_t *n_rows);
+/* Same with DEVICE-resident inputs (d_bases 16-byte aligned, d_offsets = uint64[n_reads+1] on the device), enqueued on
+   `stream` (a cudaStream_t, may be NULL); rows stay on the device until bb_fetch_rows. */
+int  bb_annotate_device(bb_ctx *ctx, const void *d_bases, const void *d_offsets, uint32_t n_reads, uint64_t total_bytes,
+                        void *stream, uint64_t *n_rows);
+int  bb_fetch_rows(bb_ctx *ctx, bb_row *rows, uint64_t rows_cap, uint64_t *n_rows);
+
+/* Pipelined form: up to BB_MAX_INFLIGHT batches may be submitted before the first collect.  The caller's buffers may be
+   reused as soon as bb_submit returns (they are copied into pinned staging memory). */
+#define BB_MAX_INFLIGHT 2
+int  bb_submit(bb_ctx *ctx, const uint8_t *bases, const uint64_t *offsets, uint32_t n_reads, uint64_t batch_tag);
+int  bb_collect(bb_ctx *ctx, uint64_t *batch_tag, const bb_row **rows, uint64_t *n_rows);
+
+/* ProgressTracker counters (annotator.rs:109-113): out = {total reads, reads with >=1 row, reads with none} */
+int  bb_counters(const bb_ctx *ctx, uint64_t out[3]);
+/* Stage timings of the last bb_annotate_device call, milliseconds on the device: {scan, sort+resolve, trace, barcode, collapse} */
+int  bb_last_stage_ms(bb_ctx *ctx, float out[5]);
+/* number of kernels this library launched since bb_create */
+uint64_t bb_kernel_launches(const bb_ctx *ctx);
+/* debugging / parity of the flank stage alone: the hit list after the flank search of the last bb_annotate_device call,
+   6 int32 per hit {read_idx, group, strand, text_start, text_end, cost} in (read, group, Fwd-before-Rc, end) order */
+int  bb_fetch_flank_hits(bb_ctx *ctx, int32_t *out6, uint64_t cap, uint64_t *n_hits);
+
+int  bb_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
