@@ -33,7 +33,8 @@ class _Opts(C.Structure):
 
 
 EXPORTS = ["bb_groups_from_kit", "bb_groups_from_fasta", "bb_groups_add", "bb_groups_set_flank_threshold",
-           "bb_groups_count", "bb_groups_data", "bb_groups_label", "bb_groups_free", "bb_edit_cut_off", "bb_create",
+           "bb_groups_count", "bb_groups_data", "bb_groups_label", "bb_groups_free", "bb_edit_cut_off", "bb_label_range",
+           "bb_lookup_barcode_seq", "bb_create",
            "bb_destroy", "bb_last_error", "bb_set_groups", "bb_annotate", "bb_annotate_device", "bb_fetch_rows",
            "bb_submit", "bb_collect", "bb_counters", "bb_last_stage_ms", "bb_kernel_launches", "bb_fetch_flank_hits",
            "bb_abi_version"]
@@ -65,6 +66,8 @@ def lib():
     L.bb_groups_label.argtypes = [vp, i32, i32]; L.bb_groups_label.restype = C.c_char_p
     L.bb_groups_free.argtypes = [vp]; L.bb_groups_free.restype = None
     L.bb_edit_cut_off.argtypes = [i32]; L.bb_edit_cut_off.restype = i32
+    L.bb_label_range.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_char_p, C.c_size_t]
+    L.bb_lookup_barcode_seq.argtypes = [C.c_char_p]; L.bb_lookup_barcode_seq.restype = C.c_char_p
     L.bb_create.argtypes = [C.POINTER(_Opts), C.POINTER(vp), C.c_char_p, C.c_size_t]
     L.bb_destroy.argtypes = [vp]; L.bb_destroy.restype = None
     L.bb_last_error.argtypes = [vp]; L.bb_last_error.restype = C.c_char_p
@@ -86,6 +89,21 @@ def lib():
 def edit_cut_off(effective_len: int) -> int:
     """reference src/annotate/edit_model.rs:2-11"""
     return lib().bb_edit_cut_off(effective_len)
+
+
+def label_range(from_label: str, to_label: str, use_12a: bool = False):
+    """reference src/kits/kits.rs:741-816 (get_barcodes)"""
+    buf = C.create_string_buffer(4096)
+    n = lib().bb_label_range(from_label.encode(), to_label.encode(), int(use_12a), buf, 4096)
+    if n < 0:
+        raise BarbellError(buf.value.decode())
+    return buf.value.decode().split(",") if n else []
+
+
+def lookup_barcode_seq(label: str):
+    """reference src/kits/kits.rs:1074-1103"""
+    s = lib().bb_lookup_barcode_seq(label.encode())
+    return s.decode() if s is not None else None
 
 
 class GroupSet:

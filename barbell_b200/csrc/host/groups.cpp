@@ -269,5 +269,16 @@ const char* bb_groups_label(const bb_groupset* gs, int32_t g, int32_t idx) {
 }
 void bb_groups_free(bb_groupset* gs) { delete gs; }
 int32_t bb_edit_cut_off(int32_t l) { return bb::edit_cut_off(l); }
+int bb_label_range(const char* from, const char* to, int use_12a, char* out, size_t outlen) {
+    if (!from || !to || !out || !outlen) return BB_ERR_INVALID;
+    std::vector<std::string> labels; std::string e;
+    if (!bb::label_range(from, to, use_12a != 0, labels, e)) { std::snprintf(out, outlen, "%s", e.c_str()); return BB_ERR_KIT; }
+    std::string joined;
+    for (size_t i = 0; i < labels.size(); i++) { if (i) joined += ','; joined += labels[i]; }
+    if (joined.size() + 1 > outlen) return BB_ERR_OVERFLOW;
+    std::snprintf(out, outlen, "%s", joined.c_str());
+    return static_cast<int>(labels.size());
+}
+const char* bb_lookup_barcode_seq(const char* label) { return label ? bb::barcode_seq(label) : nullptr; }
 int bb_abi_version(void) { return BB_ABI_VERSION; }
 }

@@ -95,6 +95,10 @@ const char *bb_groups_label(const bb_groupset *gs, int32_t group_idx, int32_t la
 void bb_groups_free(bb_groupset *gs);
 /* get_edit_cut_off, src/annotate/edit_model.rs:2-11 */
 int32_t bb_edit_cut_off(int32_t effective_len);
+/* get_barcodes, src/kits/kits.rs:741-816: comma-joined labels into `out`; returns their count or a negative status */
+int  bb_label_range(const char *from_label, const char *to_label, int use_12a, char *out, size_t outlen);
+/* lookup_barcode_seq, src/kits/kits.rs:1074-1103: NULL when unknown */
+const char *bb_lookup_barcode_seq(const char *label);
 
 /* ---- the operator (replaces Demuxer::{new,add_query_group,demux}, src/annotate/searcher.rs:202-227, 430-490) ---- */
 int  bb_create(const bb_opts *opts, bb_ctx **out, char *err, size_t errlen);
@@ -113,8 +117,10 @@ int  bb_annotate_device(bb_ctx *ctx, const void *d_bases, const void *d_offsets,
                         void *stream, uint64_t *n_rows);
 int  bb_fetch_rows(bb_ctx *ctx, bb_row *rows, uint64_t rows_cap, uint64_t *n_rows);
 
-/* Pipelined form: up to BB_MAX_INFLIGHT batches may be submitted before the first collect.  The caller's buffers may be
-   reused as soon as bb_submit returns (they are copied into pinned staging memory). */
+/* Pipelined form: up to BB_MAX_INFLIGHT batches may be submitted before the first collect; batches alternate between
+   two CUDA streams so the host->device copy of one overlaps the kernels of the other.  The caller owns `bases` and
+   `offsets` until bb_collect has returned that batch_tag (they are read by the DMA engine in place: use pinned memory
+   for full PCIe speed).  `rows` returned by bb_collect stay valid until the next bb_submit / bb_collect on the ctx. */
 #define BB_MAX_INFLIGHT 2
 int  bb_submit(bb_ctx *ctx, const uint8_t *bases, const uint64_t *offsets, uint32_t n_reads, uint64_t batch_tag);
 int  bb_collect(bb_ctx *ctx, uint64_t *batch_tag, const bb_row **rows, uint64_t *n_rows);

@@ -1,0 +1,60 @@
+"""The C-ABI library loads and exports every symbol include/barbell_b200.h declares (no compute without a GPU)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+import barbell_b200 as bb
+from barbell_b200 import api
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "barbell_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(bb_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_exported():
+    L = bb.lib()
+    syms = declared_symbols()
+    assert len(syms) >= 24
+    for s in syms:
+        assert hasattr(L, s), f"{s} declared in include/barbell_b200.h but not exported"
+    assert set(api.EXPORTS) == set(syms)
+    assert L.bb_abi_version() == 1
+
+
+def test_row_layout_matches_oracle_and_header():
+    import oracle_lib as O
+    assert bb.ROW_DTYPE == O.ROW_DTYPE and bb.ROW_DTYPE.itemsize == 88
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device bb_create must fail loudly (the product path never routes through the oracle)."""
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if has_gpu:
+        pytest.skip("GPU present")
+    gs = bb.GroupSet.from_kit("SQK-NBD114-96")
+    with pytest.raises(bb.BarbellError, match="no CUDA device|CPU"):
+        bb.Annotator(gs)
+
+
+def test_product_does_not_reference_oracle():
+    """No file of the product tree mentions the oracle library or imports tests/oracle_lib."""
+    bad = []
+    for dp, _, fns in os.walk(os.path.join(ROOT, "barbell_b200")):
+        for fn in fns:
+            if fn.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")):
+                txt = open(os.path.join(dp, fn), errors="ignore").read()
+                if "oracle_lib" in txt or "libbarbell_oracle" in txt or "barbell_oracle.h" in txt:
+                    bad.append(fn)
+    assert not bad, bad
+    out = os.popen(f"ldd {bb.lib_path()}").read()
+    assert "oracle" not in out

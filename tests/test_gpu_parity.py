@@ -1,0 +1,186 @@
+"""Parity tests proper: the CUDA path, called through the C ABI, against the oracle and the golden fixtures.
+Bit-exact: every field of every annotation row (integer work; the f64 Lodhi score only decides thresholds)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import barbell_b200 as bb
+from barbell_b200 import api, synth
+import cases
+import oracle_lib as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _annotator(gs, **kw):
+    return bb.Annotator(gs, device=0, **kw)
+
+
+def _check(gs, bases, offsets, **kw):
+    an = _annotator(gs, **kw)
+    try:
+        rows = an.annotate(bases, offsets)
+        hits = an.flank_hits()
+    finally:
+        an.close()
+    G = gs.as_dicts()
+    want = O.demux_batch(G, bases, offsets, alpha=kw.get("alpha", 0.4), min_score=kw.get("min_score", 0.2),
+                         min_score_diff=kw.get("min_score_diff", 0.1))
+    want_h = O.flank_hits_batch(G, bases, offsets, alpha=kw.get("alpha", 0.4))
+    assert hits.shape == want_h.shape and (hits == want_h).all(), "flank hit list differs"
+    assert rows.tobytes() == want.tobytes(), "annotation rows differ"
+    return rows
+
+
+@pytest.mark.parametrize("name", sorted(cases.META["cases"]))
+def test_golden_cases(name):
+    """configs[0] (nbd_1k) and the kit/panel variants: GPU == golden == oracle."""
+    gs, bases, offsets, rows, hits = cases.load_case(name)
+    got = _check(gs, bases, offsets)
+    assert got.tobytes() == rows.tobytes()
+    if name == "nbd_1k":
+        ids = [f"read_{i}" for i in range(len(offsets) - 1)]
+        assert bb.rows_to_tsv(got, gs, ids) == open(cases.GOLD + "/nbd_1k.annotation.tsv").read()
+
+
+def test_10kb_reads():
+    gs = bb.GroupSet.from_kit("SQK-NBD114-96")
+    b, o, _ = synth.make_reads(gs.as_dicts(), 500, 10000, seed=21)
+    _check(gs, b, o)
+
+
+def test_ragged_tiny_and_empty_reads():
+    gs = bb.GroupSet.from_kit("SQK-NBD114-96")
+    b, o, _ = synth.make_reads(gs.as_dicts(), 600, (0, 130), seed=22)
+    assert (np.diff(o.astype(np.int64)) == 0).any()
+    _check(gs, b, o)
+    # a batch of only empty reads, and an empty batch
+    an = _annotator(gs)
+    assert len(an.annotate(np.zeros(0, np.uint8), np.zeros(5, np.uint64))) == 0
+    assert len(an.annotate(np.zeros(0, np.uint8), np.zeros(1, np.uint64))) == 0
+    an.close()
+
+
+def test_unaligned_read_boundaries_and_long_read():
+    gs = bb.GroupSet.from_kit("SQK-NBD114-96")
+    b1, o1, _ = synth.make_reads(gs.as_dicts(), 64, (1, 700), seed=23)
+    b2, o2, _ = synth.make_reads(gs.as_dicts(), 3, 300001, seed=24)      # spans several CTA tiles
+    bases = np.concatenate([b1, b2])
+    offsets = np.concatenate([o1, o2[1:] + o1[-1]])
+    _check(gs, bases, offsets)
+
+
+def test_adversarial_text():
+    """poly-N (matches everything), homopolymers, lower case, non-IUPAC bytes, tags cut by the read ends."""
+    gs = bb.GroupSet.from_kit("SQK-NBD114-96")
+    tag = synth.full_tags(gs.as_dicts()[0])[7].tobytes()
+    rnd = np.random.default_rng(3)
+    body = bytes(rnd.choice(np.frombuffer(b"ACGT", np.uint8), 500))
+    reads = [b"N" * 200, b"A" * 300, b"T" * 97, tag, tag[5:], tag[:-9], tag.lower() + body.lower(), body + synth.revcomp(np.frombuffer(tag, np.uint8)).tobytes()[:30],
+             b"ACGT-*.@" * 20 + tag, tag[20:] + body + tag[:25], b"N" * 30 + tag[30:] + body, b"ATTGCTAAGGTTAA" * 10, b"CAGCACCT" * 20,
+             tag + b"N" * 10 + tag + tag, b"G", b"", tag[:23], b"NNNNACGT" * 40]
+    bases = np.frombuffer(b"".join(reads), np.uint8)
+    offsets = np.concatenate([[0], np.cumsum([len(r) for r in reads])]).astype(np.uint64)
+    _check(gs, bases, offsets)
+
+
+def test_rbk_auto_threshold_two_word_patterns():
+    gs = bb.GroupSet.from_kit("SQK-RBK114-96")          # flank 90 chars, k = 20
+    b, o, _ = synth.make_reads(gs.as_dicts(), 400, (200, 3000), seed=25)
+    _check(gs, b, o)
+
+
+def test_custom_dual_end_384_panel():
+    """configs[3] style: 384 random 24-mers in the ald_left / ald_right flanks, Ftag + Rtag."""
+    rnd = np.random.default_rng(26)
+    gl, gr = bb.GroupSet.from_fasta([cases.GOLD + "/ald_left.fasta", cases.GOLD + "/ald_right.fasta"], [0, 1]).as_dicts()
+    def panel(g, n):
+        pre, suf = g["flank"][:g["bar_region"][0]], g["flank"][g["bar_region"][1] + 1:]
+        seqs = []
+        for i in range(n):
+            core = bytes(rnd.choice(np.frombuffer(b"ACGT", np.uint8), 24))
+            core = b"ACGT"[i % 4:i % 4 + 1] + core[1:-1] + b"ACGT"[(i // 4) % 4:(i // 4) % 4 + 1]
+            seqs.append(pre + core + suf)
+        return seqs
+    gs = bb.GroupSet.from_seqs([(panel(gl, 384), [f"L{i}" for i in range(384)], api.FTAG),
+                                (panel(gr, 384), [f"R{i}" for i in range(384)], api.RTAG)])
+    b, o, _ = synth.make_reads(gs.as_dicts(), 150, (400, 2500), seed=27)
+    rows = _check(gs, b, o)
+    assert (rows["match_type"] < 2).sum() > 50
+
+
+def test_thresholds_and_alpha_variants():
+    gs = bb.GroupSet.from_kit("SQK-NBD114-96", max_flank_errors=8)
+    b, o, _ = synth.make_reads(gs.as_dicts(), 300, (100, 1500), seed=28, p_mut=0.12)
+    _check(gs, b, o, alpha=0.5, min_score=0.5, min_score_diff=0.3)
+    _check(gs, b, o, alpha=0.4, min_score=0.0, min_score_diff=0.0)
+
+
+def test_device_api_and_pipeline_equal_host_api():
+    import torch
+    gs = bb.GroupSet.from_kit("SQK-NBD114-96")
+    b, o, _ = synth.make_reads(gs.as_dicts(), 2000, (500, 3000), seed=29)
+    an = _annotator(gs)
+    want = an.annotate(b, o)
+    # device-resident inputs
+    tb = torch.from_numpy(b).cuda()
+    to = torch.from_numpy(o.astype(np.int64)).cuda()
+    n = an.annotate_device(tb.data_ptr(), to.data_ptr(), len(o) - 1, len(b), torch.cuda.current_stream().cuda_stream)
+    assert an.fetch_rows(n).tobytes() == want.tobytes()
+    # pipelined submit/collect over 5 sub-batches on two streams
+    cuts = np.linspace(0, len(o) - 1, 6).astype(int)
+    parts = []
+    subs = []
+    for i in range(5):
+        lo, hi = cuts[i], cuts[i + 1]
+        sb = np.ascontiguousarray(b[int(o[lo]):int(o[hi])]); so = (o[lo:hi + 1] - o[lo]).astype(np.uint64)
+        subs.append((sb, so, lo))
+    inflight = 0
+    nxt = 0
+    while nxt < 5 or inflight:
+        while nxt < 5 and inflight < 2:
+            sb, so, lo = subs[nxt]
+            an.submit(sb.ctypes.data, so.ctypes.data, len(so) - 1, tag=nxt)
+            nxt += 1; inflight += 1
+        tag, rows = an.collect()
+        rows["read_idx"] += subs[tag][2]
+        parts.append((tag, rows)); inflight -= 1
+    assert [t for t, _ in parts] == [0, 1, 2, 3, 4]
+    assert np.concatenate([r for _, r in parts]).tobytes() == want.tobytes()
+    c = an.counters()
+    assert c["total"] == 3 * (len(o) - 1) and c["kept"] + c["dropped"] == c["total"]
+    assert c["kept"] == 3 * len(np.unique(want["read_idx"]))
+    assert an.kernel_launches() > 0
+    an.close()
+
+
+def test_full_size_properties():
+    """At bench size the oracle is too slow; check size-independent properties instead: the result of a batch equals the
+    concatenation of the results of its halves (reads are independent), and a sample of reads agrees with the oracle."""
+    gs = bb.GroupSet.from_kit("SQK-NBD114-96")
+    n = 20000
+    b, o, _ = synth.make_reads(gs.as_dicts(), n, 10000, seed=30)
+    an = _annotator(gs)
+    whole = an.annotate(b, o)
+    h = n // 2
+    a1 = an.annotate(b[:int(o[h])], o[:h + 1])
+    a2 = an.annotate(b[int(o[h]):], (o[h:] - o[h]).astype(np.uint64))
+    a2["read_idx"] += h
+    assert np.concatenate([a1, a2]).tobytes() == whole.tobytes()
+    assert (np.diff(whole["read_idx"].astype(np.int64)) >= 0).all()            # grouped by read, input order
+    idx = np.arange(0, n, 97)
+    sb = np.concatenate([b[int(o[i]):int(o[i + 1])] for i in idx])
+    so = np.concatenate([[0], np.cumsum([int(o[i + 1] - o[i]) for i in idx])]).astype(np.uint64)
+    want = O.demux_batch(gs.as_dicts(), sb, so)
+    sel = whole[np.isin(whole["read_idx"], idx)].copy()
+    remap = {int(v): k for k, v in enumerate(idx)}
+    sel["read_idx"] = [remap[int(v)] for v in sel["read_idx"]]
+    assert sel.tobytes() == want.tobytes()
+    an.close()
+
+
+def test_set_groups_rejects_unsupported_geometry():
+    gs = bb.GroupSet.from_kit("SQK-NBD114-96", max_flank_errors=30)     # k >= floor(0.4*46)-1
+    with pytest.raises(bb.BarbellError):
+        _annotator(gs)
