@@ -179,7 +179,23 @@ static int frame_costs(const pattern_t *pt, const uint8_t *tc, int n, int32_t *c
         memcpy(pv, P->has_over ? P->pv_over : P->pv_plain, sizeof pv);
         int score = P->ov[m];
         c[0] = score;
-        for (int j = 0; j < n; j++) { score += col_step(P, pv, mv, tc[j]); c[j + 1] = score; }
+        if (P->nw == 1) {            /* single-word fast path (same arithmetic as col_step) */
+            uint64_t Pv = pv[0], Mv = 0;
+            const int lb = P->last_bit;
+            for (int j = 0; j < n; j++) {
+                const uint64_t eq = P->eq[tc[j]][0];
+                const uint64_t xv = eq | Mv;
+                const uint64_t xh = (((eq & Pv) + Pv) ^ Pv) | eq;
+                uint64_t ph = Mv | ~(xh | Pv), mh = Pv & xh;
+                score += (int)((ph >> lb) & 1) - (int)((mh >> lb) & 1);
+                ph <<= 1; mh <<= 1;
+                Pv = mh | ~(xv | ph); Mv = ph & xv;
+                c[j + 1] = score;
+            }
+            pv[0] = Pv; mv[0] = Mv;
+        } else {
+            for (int j = 0; j < n; j++) { score += col_step(P, pv, mv, tc[j]); c[j + 1] = score; }
+        }
         if (P->has_over) for (int t = 1; t <= m; t++) c[n + t] = col_val(pv, mv, m - t) + P->ov[t];
     } else {
         int32_t *mat = (int32_t *)malloc(sizeof(int32_t) * (size_t)(n + 1) * (m + 1));
