@@ -217,8 +217,10 @@ class Annotator:
         cap = rows_cap if rows_cap is not None else max(64, 4 * n_reads)
         rows = np.zeros(cap, dtype=ROW_DTYPE)
         n = C.c_uint64()
-        self._check(lib().bb_annotate(self._ctx, bases.ctypes.data, offsets.ctypes.data, n_reads, rows.ctypes.data, cap,
-                                      C.byref(n)))
+        rc = lib().bb_annotate(self._ctx, bases.ctypes.data, offsets.ctypes.data, n_reads, rows.ctypes.data, cap, C.byref(n))
+        if rc == -3 and rows_cap is None:        # BB_ERR_OVERFLOW reports the needed size: fetch the rows still on the device
+            return self.fetch_rows(n.value)
+        self._check(rc)
         return rows[:n.value].copy()
 
     def annotate_ptr(self, bases_ptr, offsets_ptr, n_reads, rows_ptr, rows_cap) -> int:

@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstring>
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 #include <cub/device/device_select.cuh>
 #include <deque>
 #include <memory>
@@ -77,7 +78,7 @@ static double lodhi_all_match(int l) {   // reference searcher.rs:229-239 with t
 struct GroupTables {          // device copies for all groups of a ctx (shared by its engines)
     std::vector<DevGroup> host;
     DBuf d_groups, d_blob, d_code;
-    int n = 0, max_trace_cols = 0, max_nw = 1;
+    int n = 0, max_trace_cols = 0, max_nw = 1, max_region = 0;
     void release() { d_groups.release(); d_blob.release(); d_code.release(); host.clear(); n = 0; }
 };
 
@@ -89,7 +90,7 @@ struct Engine {
     std::string err;
     uint64_t launches = 0;
     // device buffers
-    DBuf d_bases, d_offsets, d_entries, d_sorted, d_cub, d_flags, d_hitkeys, d_hits, d_hist, d_rows, d_valid, d_rows_out, d_hits6;
+    DBuf d_bases, d_offsets, d_nch, d_chunk_base, d_tile_first, d_entries, d_sorted, d_cub, d_flags, d_hitkeys, d_hits, d_hist, d_rows, d_valid, d_rows_out, d_hits6;
     DBuf d_counters;                     // [0] n_entries (u32) [2] n_selected (u32) [4..5] kept reads (u64)
     uint32_t entries_cap = 0;
     uint32_t* h_counters = nullptr;      // pinned, 8 x u32
@@ -115,7 +116,7 @@ struct Engine {
     }
     void destroy() {
         cudaSetDevice(device);
-        for (DBuf* b : {&d_bases, &d_offsets, &d_entries, &d_sorted, &d_cub, &d_flags, &d_hitkeys, &d_hits, &d_hist, &d_rows,
+        for (DBuf* b : {&d_bases, &d_offsets, &d_nch, &d_chunk_base, &d_tile_first, &d_entries, &d_sorted, &d_cub, &d_flags, &d_hitkeys, &d_hits, &d_hist, &d_rows,
                         &d_valid, &d_rows_out, &d_hits6, &d_counters})
             b->release();
         if (h_counters) cudaFreeHost(h_counters);
@@ -147,6 +148,24 @@ struct Engine {
         uint32_t* d_cnt = d_counters.as<uint32_t>();
         BB_CUDA(cudaEventRecord(ev[0], st));
 
+        // ---- chunk index: reads -> chunks of kChunk bases (a chunk never straddles two reads) ----
+        const uint64_t max_chunks = total / kChunk + n_reads;
+        const unsigned n_tiles = static_cast<unsigned>((max_chunks + kScanThreads - 1) / kScanThreads);
+        BB_CUDA(d_nch.ensure(static_cast<size_t>(n_reads + 1) * 4));
+        BB_CUDA(d_chunk_base.ensure(static_cast<size_t>(n_reads + 1) * 4));
+        BB_CUDA(d_tile_first.ensure(static_cast<size_t>(n_tiles) * 4));
+        k_chunk_count<<<(n_reads + 1 + 255) / 256, 256, 0, st>>>(offsets, n_reads, d_nch.as<uint32_t>());
+        launches++;
+        {
+            size_t tmp = 0;
+            cub::DeviceScan::ExclusiveSum(nullptr, tmp, d_nch.as<uint32_t>(), d_chunk_base.as<uint32_t>(), static_cast<int>(n_reads + 1), st);
+            BB_CUDA(d_cub.ensure(tmp));
+            BB_CUDA(cub::DeviceScan::ExclusiveSum(d_cub.p, tmp, d_nch.as<uint32_t>(), d_chunk_base.as<uint32_t>(), static_cast<int>(n_reads + 1), st));
+        }
+        k_tile_index<<<(n_tiles + 255) / 256, 256, 0, st>>>(d_chunk_base.as<uint32_t>(), n_reads, n_tiles, d_tile_first.as<uint32_t>());
+        launches++;
+        BB_CUDA(cudaGetLastError());
+
         // ---- K1: flank scan, one launch per group ----
         uint32_t n_entries = 0;
         for (int attempt = 0; attempt < 4; attempt++) {
@@ -159,18 +178,17 @@ struct Engine {
             for (int g = 0; g < gt->n; g++) {
                 const DevGroup& G = gt->host[g];
                 ScanArgs A{};
-                A.bases = bases; A.offsets = offsets; A.n_reads = n_reads; A.total = total; A.total16 = total16;
-                A.group = g; A.chunk = 336;
+                A.bases = bases; A.offsets = offsets; A.n_reads = n_reads; A.total16 = total16;
+                A.chunk_base = d_chunk_base.as<uint32_t>(); A.tile_first = d_tile_first.as<uint32_t>();
+                A.group = g;
                 A.entries = d_entries.as<uint64_t>(); A.n_entries = d_cnt; A.cap = entries_cap;
-                const uint64_t tile = static_cast<uint64_t>(kScanThreads) * A.chunk;
-                const unsigned grid = static_cast<unsigned>((total + tile - 1) / tile);
-                const size_t smem = 128 + 2 * 256 * G.nw * sizeof(uint64_t) + 2 * static_cast<size_t>(G.halo) + tile;
+                const size_t smem = 128 + 2 * 256 * G.nw * sizeof(uint64_t) + static_cast<size_t>(kScanThreads) * kChunk + 2 * static_cast<size_t>(G.warm) + 48;
                 if (G.nw == 1) {
                     BB_CUDA(cudaFuncSetAttribute(k_flank_scan<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-                    k_flank_scan<1><<<grid, kScanThreads, smem, st>>>(A, G);
+                    k_flank_scan<1><<<n_tiles, kScanThreads, smem, st>>>(A, G);
                 } else {
                     BB_CUDA(cudaFuncSetAttribute(k_flank_scan<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-                    k_flank_scan<2><<<grid, kScanThreads, smem, st>>>(A, G);
+                    k_flank_scan<2><<<n_tiles, kScanThreads, smem, st>>>(A, G);
                 }
                 launches++;
                 BB_CUDA(cudaGetLastError());
@@ -235,8 +253,11 @@ struct Engine {
             BarArgs B{};
             B.bases = bases; B.offsets = offsets; B.hits = d_hits.as<Hit>(); B.n_hits = n_hits; B.groups = d_groups();
             B.code = gt->d_code.as<uint8_t>(); B.prm = prm; B.rows = d_rows.as<bb_row>(); B.row_valid = d_valid.as<uint8_t>();
-            const unsigned blocks = std::min<unsigned>((n_hits + kBarWarps - 1) / kBarWarps, 148 * 8);
-            k_barcode<<<blocks, kBarWarps * 32, 0, st>>>(B);
+            B.hist_cols = gt->max_region + 1;
+            const size_t smem = barcode_smem_bytes(B.hist_cols);
+            BB_CUDA(cudaFuncSetAttribute(k_barcode, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+            const unsigned blocks = std::min<unsigned>((n_hits + kBarWarps - 1) / kBarWarps, 148 * 16);
+            k_barcode<<<blocks, kBarWarps * 32, smem, st>>>(B);
             launches++;
             BB_CUDA(cudaGetLastError());
         }
@@ -397,9 +418,9 @@ int bb_set_groups(bb_ctx* c, const bb_group* groups, int32_t n_groups) {
     const float alpha = c->opts.alpha;
     // blob layout per group: eq[2][256][nw] u64 | bar_eq[2][nb][16] u64 | ov[m+1] i32 (padded to 8)
     std::vector<uint64_t> blob;
-    std::vector<size_t> off_eq(n_groups), off_bar(n_groups), off_ov(n_groups);
+    std::vector<size_t> off_eq(n_groups), off_eqt(n_groups), off_bar(n_groups), off_ov(n_groups);
     std::vector<DevGroup> hg(n_groups);
-    int max_trace = 0, max_nw = 1;
+    int max_trace = 0, max_nw = 1, max_region = 0;
     for (int g = 0; g < n_groups; g++) {
         const bb_group& S = groups[g];
         DevGroup& D = hg[g];
@@ -418,10 +439,13 @@ int bb_set_groups(bb_ctx* c, const bb_group* groups, int32_t n_groups) {
         D.bar_len = S.bar_len; D.n_barcodes = S.n_barcodes; D.match_type = S.match_type;
         D.k_bar = static_cast<int>(static_cast<float>(S.bar_len) * 0.4f);
         D.pbar0 = S.bar0 - S.pad0; D.pbar1 = S.bar1 - S.pad0;
-        D.ov_m = ov_m; D.halo = ((m + S.k_flank) + 15) & ~15;
+        D.ov_m = ov_m;
+        D.warm = ((m + S.k_flank + kGroup - 1) / kGroup) * kGroup;
+        D.halo = (D.warm + 15) & ~15;
         D.trace_cols = m + 2 * std::min(S.k_flank, m) + 8;
         D.perfect = lodhi_all_match(S.pad1 - S.pad0);
         max_trace = std::max(max_trace, D.trace_cols); max_nw = std::max(max_nw, D.nw);
+        max_region = std::max(max_region, S.bar1 - S.bar0 + 1 + S.k_flank + 2 * kPadding);
         std::vector<uint8_t> pc(m);
         for (int i = 0; i < m; i++) pc[i] = kAlpha.code[static_cast<uint8_t>(S.flank[i])];
         std::vector<int> ov(m + 1);
@@ -439,6 +463,25 @@ int bb_set_groups(bb_ctx* c, const bb_group* groups, int32_t n_groups) {
                 for (int i = 0; i < m; i++)
                     if (pc[i] & code) blob[off_eq[g] + (static_cast<size_t>(s) * 256 + ch) * D.nw + (i >> 6)] |= 1ull << (i & 63);
             }
+        // top-aligned copy for the scan kernel: row i at bit i + shift, wildcard rows (all ones) below
+        off_eqt[g] = blob.size();
+        blob.resize(blob.size() + 2 * 256 * D.nw, 0);
+        {
+            const int shift = 64 * D.nw - m;
+            for (int i = 0; i < m; i++) {
+                const int bpos = i + shift;
+                D.pv_plain_top[bpos >> 6] |= 1ull << (bpos & 63);
+                if (ov[i + 1] - ov[i]) D.pv_over_top[bpos >> 6] |= 1ull << (bpos & 63);
+            }
+            for (int s = 0; s < 2; s++)
+                for (int ch = 0; ch < 256; ch++) {
+                    uint64_t* dst = &blob[off_eqt[g] + (static_cast<size_t>(s) * 256 + ch) * D.nw];
+                    const uint64_t* src = &blob[off_eq[g] + (static_cast<size_t>(s) * 256 + ch) * D.nw];
+                    for (int i = 0; i < m; i++)
+                        if ((src[i >> 6] >> (i & 63)) & 1ull) dst[(i + shift) >> 6] |= 1ull << ((i + shift) & 63);
+                    for (int bpos = 0; bpos < shift; bpos++) dst[bpos >> 6] |= 1ull << (bpos & 63);
+                }
+        }
         off_bar[g] = blob.size();
         blob.resize(blob.size() + static_cast<size_t>(2) * S.n_barcodes * 16, 0);
         for (int b = 0; b < S.n_barcodes; b++)
@@ -463,6 +506,7 @@ int bb_set_groups(bb_ctx* c, const bb_group* groups, int32_t n_groups) {
     const uint64_t* base = T.d_blob.as<uint64_t>();
     for (int g = 0; g < n_groups; g++) {
         hg[g].eq = base + off_eq[g];
+        hg[g].eq_top = base + off_eqt[g];
         hg[g].bar_eq = base + off_bar[g];
         hg[g].ov = reinterpret_cast<const int*>(base + off_ov[g]);
     }
@@ -470,7 +514,7 @@ int bb_set_groups(bb_ctx* c, const bb_group* groups, int32_t n_groups) {
     cudaError_t e2 = cudaMemcpy(T.d_groups.p, hg.data(), sizeof(DevGroup) * n_groups, cudaMemcpyHostToDevice);
     cudaError_t e3 = cudaMemcpy(T.d_code.p, kAlpha.code, 256, cudaMemcpyHostToDevice);
     if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) return (ctx_error(c, "cudaMemcpy of the pattern tables failed"), BB_ERR_CUDA);
-    T.host = hg; T.n = n_groups; T.max_trace_cols = max_trace; T.max_nw = max_nw;
+    T.host = hg; T.n = n_groups; T.max_trace_cols = max_trace; T.max_nw = max_nw; T.max_region = max_region;
     return BB_OK;
 }
 

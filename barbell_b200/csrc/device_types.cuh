@@ -21,12 +21,16 @@ struct DevGroup {
     int bar0, bar1, pad0, pad1;          // reference barcodes.rs:160-192
     int bar_len, n_barcodes, match_type, k_bar;   // k_bar = (int)(bar_len * 0.4f)   searcher.rs:460
     int pbar0, pbar1;                    // bar0 - pad0, bar1 - pad0                   searcher.rs:379-382
-    int ov_m, halo;                      // floor(m*alpha); m + k rounded up to 16
+    int ov_m, halo;                      // floor(m*alpha); shared-memory halo of the scan tile (multiple of 16, >= warm)
+    int warm, pad2_;                     // warm-up columns of a scan chunk: m + k rounded up to the scan group size
     int trace_cols, pad_;                // m + 2k + 8 (+1 columns of history)
     double perfect;                      // Lodhi of pad1-pad0 matches                 searcher.rs:229-239
     uint64_t pv_plain[kMaxFlankWords];   // first column D[i] = i
     uint64_t pv_over[kMaxFlankWords];    // first column D[i] = floor(i*alpha)
+    uint64_t pv_plain_top[kMaxFlankWords];   // the same two columns with the pattern moved to the top of the bit-vector
+    uint64_t pv_over_top[kMaxFlankWords];    //   (row i at bit i + 64*nw - m; the low bits are wildcard rows, zero deltas)
     const uint64_t* eq;                  // [2 strands][256 bytes][nw]  flank match masks indexed by the raw text byte
+    const uint64_t* eq_top;              // same, top-aligned, wildcard rows below (used by the scan kernel)
     const int* ov;                       // [m+1] floor(t*alpha)
     const uint64_t* bar_eq;              // [2 strands][n_barcodes][16 codes]
 };

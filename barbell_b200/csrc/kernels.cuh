@@ -82,11 +82,6 @@ __device__ __forceinline__ uint64_t make_key(uint32_t read, int group, int stran
            static_cast<uint64_t>(cost & 0xff);
 }
 
-__device__ __noinline__ void emit_entry(uint64_t* entries, uint32_t* n_entries, uint32_t cap, uint64_t key) {
-    const uint32_t idx = atomicAdd(n_entries, 1u);
-    if (idx < cap) entries[idx] = key;
-}
-
 // ---------------------------------------------------------------------------------------------------------------
 // mbarrier / TMA bulk copy (1-D) helpers -- SASS: SYNCS.*, UBLKCP
 // ---------------------------------------------------------------------------------------------------------------
@@ -117,155 +112,240 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gme
 
 // ---------------------------------------------------------------------------------------------------------------
 // K1: flank scan
+//
+// Work unit = one CHUNK of kChunk consecutive bases of ONE read (chunks never straddle reads, so no lane ever switches
+// reads; a tiny pre-pass turns the read lengths into a chunk index).  A CTA owns 256 consecutive chunks; their bytes are
+// contiguous in the batch buffer, so the CTA's text (plus a warm-up halo on both sides) arrives in shared memory by ONE
+// TMA bulk copy (cp.async.bulk -> mbarrier).  Lane t scans its chunk twice: ascending with the forward masks, descending
+// with the complemented masks (= forward search of the reverse-complemented read, oracle policy S4), each time after
+// `warm` >= m+k warm-up columns inside the same read (the bottom-row cost at j depends on text[j-(m+k), j) only).
+// The pattern sits at the TOP of the bit-vector (last flank row = bit 63 of the last word); the unused low bits are
+// wildcard rows with zero vertical deltas, which is exactly the semi-global top boundary, so the bottom-row delta of a
+// column is the sign bit of Ph / Mh.  Per character: 1 LDS.U8 (text) + 1 LDS.64/128 (match mask) + ~21 ALU-pipe ops.
+// Control flow is uniform across the warp: groups of kGroup characters run branch-free and only track the minimum
+// score; a group whose minimum drops to <= k is replayed character by character to emit the sub-threshold positions.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kScanThreads = 256;
+constexpr int kGroup = 20;           // characters per unrolled group; chunk and warm-up are multiples of it
+constexpr int kChunk = 340;          // bases per lane: 17 groups; 340/4 = 85 is odd (LDS.U8 of a warp is conflict-free)
 
 struct ScanArgs {
     const uint8_t* bases;        // concatenated read bytes, 16-byte aligned
     const uint64_t* offsets;     // n_reads + 1
+    const uint32_t* chunk_base;  // n_reads + 1: exclusive prefix sum of ceil(len / kChunk)
+    const uint32_t* tile_first;  // per CTA: read owning the CTA's first chunk
     uint32_t n_reads;
-    uint64_t total;              // bytes in `bases`
-    uint64_t total16;            // readable bytes (total rounded up to 16)
+    uint64_t total16;            // readable bytes of `bases` (total rounded up to 16)
     int group;
-    int chunk;                   // bytes of text per lane (multiple of 16; odd multiple keeps LDS.128 conflict-free)
     uint64_t* entries;
     uint32_t* n_entries;
     uint32_t cap;
 };
 
-// index of the read containing global byte g: largest r with offsets[r] <= g (skipping empty reads lands on the
-// non-empty one because upper_bound returns the first offset > g)
-__device__ __forceinline__ uint32_t find_read(const uint64_t* __restrict__ offsets, uint32_t n_reads, uint64_t g) {
-    uint32_t lo = 0, hi = n_reads + 1;   // first index with offsets[idx] > g
-    while (lo < hi) {
-        const uint32_t mid = (lo + hi) >> 1;
-        if (__ldg(offsets + mid) <= g) lo = mid + 1; else hi = mid;
+// chunks per read (thread per read; entry n_reads is 0 so the exclusive scan yields the total)
+__global__ void k_chunk_count(const uint64_t* __restrict__ offsets, uint32_t n_reads, uint32_t* __restrict__ nch) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r > n_reads) return;
+    nch[r] = r < n_reads ? static_cast<uint32_t>((offsets[r + 1] - offsets[r] + kChunk - 1) / kChunk) : 0u;
+}
+
+// largest r in [lo, n_reads] with chunk_base[r] <= c and the read non-empty-for-c (upper_bound - 1)
+__device__ __forceinline__ uint32_t find_chunk_read(const uint32_t* __restrict__ chunk_base, uint32_t n_reads, uint32_t lo, uint32_t c) {
+    // gallop from lo, then bisect: first index with chunk_base[idx] > c
+    uint32_t step = 1, hi = lo + 1;
+    while (hi <= n_reads && __ldg(chunk_base + hi) <= c) { lo = hi; step <<= 1; hi = lo + step; }
+    if (hi > n_reads + 1) hi = n_reads + 1;
+    uint32_t a = lo + 1, b = hi;
+    while (a < b) {
+        const uint32_t mid = (a + b) >> 1;
+        if (__ldg(chunk_base + mid) <= c) a = mid + 1; else b = mid;
     }
-    return lo - 1;
+    return a - 1;
+}
+
+// per CTA: the read that owns chunk cta*256 (thread per CTA)
+__global__ void k_tile_index(const uint32_t* __restrict__ chunk_base, uint32_t n_reads, uint32_t n_tiles, uint32_t* __restrict__ tile_first) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tiles) return;
+    const uint32_t c = t * kScanThreads;
+    uint32_t a = 0, b = n_reads + 1;                   // first index with chunk_base[idx] > c
+    while (a < b) {
+        const uint32_t mid = (a + b) >> 1;
+        if (chunk_base[mid] <= c) a = mid + 1; else b = mid;
+    }
+    tile_first[t] = a - 1;
+}
+
+// top-aligned column step: returns the bottom-row delta (+1 / 0 / -1)
+template <int NW>
+__device__ __forceinline__ int col_step_top(Col<NW>& c, const uint64_t* __restrict__ eq) {
+    if constexpr (NW == 1) {
+        const uint64_t e = eq[0], pv = c.pv[0], mv = c.mv[0];
+        const uint64_t sum = (e & pv) + pv;
+        uint64_t ph = mv | ~(sum | pv | e);
+        uint64_t mh = pv & ((sum ^ pv) | e);
+        const int d = static_cast<int>(ph >> 63) - static_cast<int>(mh >> 63);
+        ph <<= 1; mh <<= 1;
+        c.pv[0] = mh | ~(e | mv | ph);
+        c.mv[0] = ph & (e | mv);
+        return d;
+    } else {
+        const uint64_t e0 = eq[0], e1 = eq[1], pv0 = c.pv[0], pv1 = c.pv[1], mv0 = c.mv[0], mv1 = c.mv[1];
+        const uint64_t t0 = e0 & pv0, t1 = e1 & pv1;
+        const uint64_t s0 = t0 + pv0;
+        const uint64_t s1 = t1 + pv1 + (s0 < t0 ? 1ull : 0ull);
+        uint64_t ph0 = mv0 | ~(s0 | pv0 | e0), ph1 = mv1 | ~(s1 | pv1 | e1);
+        uint64_t mh0 = pv0 & ((s0 ^ pv0) | e0), mh1 = pv1 & ((s1 ^ pv1) | e1);
+        const int d = static_cast<int>(ph1 >> 63) - static_cast<int>(mh1 >> 63);
+        ph1 = (ph1 << 1) | (ph0 >> 63); ph0 <<= 1;
+        mh1 = (mh1 << 1) | (mh0 >> 63); mh0 <<= 1;
+        c.pv[0] = mh0 | ~(e0 | mv0 | ph0); c.pv[1] = mh1 | ~(e1 | mv1 | ph1);
+        c.mv[0] = ph0 & (e0 | mv0);        c.mv[1] = ph1 & (e1 | mv1);
+        return d;
+    }
+}
+
+__device__ __forceinline__ void scan_emit(const ScanArgs& A, uint32_t r, int strand, uint32_t pos, int cost) {
+    const uint32_t idx = atomicAdd(A.n_entries, 1u);
+    if (idx < A.cap) A.entries[idx] = make_key(r, A.group, strand, pos, cost);
 }
 
 template <int NW>
 __global__ void __launch_bounds__(kScanThreads, 2) k_flank_scan(const ScanArgs A, const DevGroup G) {
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
+    int64_t* s_origin = reinterpret_cast<int64_t*>(smem + 16);
     uint64_t* s_eq = reinterpret_cast<uint64_t*>(smem + 128);                       // [2][256][NW]
-    unsigned char* s_text = smem + 128 + 2 * 256 * NW * sizeof(uint64_t);           // halo + tile + halo
+    unsigned char* s_text = smem + 128 + 2 * 256 * NW * sizeof(uint64_t);           // warm-up + 256 chunks + warm-up
 
     const int tid = threadIdx.x;
-    const int halo = G.halo;
-    const uint64_t tile_bytes = static_cast<uint64_t>(kScanThreads) * A.chunk;
-    const uint64_t tile_base = static_cast<uint64_t>(blockIdx.x) * tile_bytes;
-    const int64_t s_origin = static_cast<int64_t>(tile_base) - halo;                // global byte at s_text[0]
+    const int W = G.warm;                                                           // multiple of kGroup, >= m + k
+    const uint32_t total_chunks = __ldg(A.chunk_base + A.n_reads);
+    const uint32_t c_first = blockIdx.x * kScanThreads;
+    if (c_first >= total_chunks) return;
+    const uint32_t r_first = __ldg(A.tile_first + blockIdx.x);
 
     if (tid == 0) {
         mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        const uint64_t lo = tile_base >= static_cast<uint64_t>(halo) ? tile_base - halo : 0;
-        uint64_t hi = tile_base + tile_bytes + halo;
+        const uint32_t c_last = min(c_first + kScanThreads, total_chunks) - 1;
+        const uint32_t r_last = find_chunk_read(A.chunk_base, A.n_reads, r_first, c_last);
+        const uint64_t g_lo = __ldg(A.offsets + r_first) + static_cast<uint64_t>(c_first - __ldg(A.chunk_base + r_first)) * kChunk;
+        uint64_t g_hi = __ldg(A.offsets + r_last) + static_cast<uint64_t>(c_last - __ldg(A.chunk_base + r_last) + 1) * kChunk;
+        const uint64_t r_end = __ldg(A.offsets + r_last + 1);
+        if (g_hi > r_end) g_hi = r_end;
+        uint64_t lo = g_lo >= static_cast<uint64_t>(W) ? g_lo - W : 0;
+        lo &= ~15ull;
+        uint64_t hi = (g_hi + W + 15) & ~15ull;
         if (hi > A.total16) hi = A.total16;
+        *s_origin = static_cast<int64_t>(lo);
         const uint32_t bytes = static_cast<uint32_t>(hi - lo);
         mbar_expect_tx(bar, bytes);
-        tma_bulk_g2s(s_text + (static_cast<int64_t>(lo) - s_origin), A.bases + lo, bytes, bar);
+        tma_bulk_g2s(s_text, A.bases + lo, bytes, bar);
     }
     // stage the match masks while the bulk copy is in flight
-    for (int i = tid; i < 2 * 256 * NW; i += kScanThreads) s_eq[i] = __ldg(G.eq + i);
+    for (int i = tid; i < 2 * 256 * NW; i += kScanThreads) s_eq[i] = __ldg(G.eq_top + i);
+
+    // this lane's chunk
+    const uint32_t c = c_first + tid;
+    const bool active = c < total_chunks;
+    uint32_t r = 0;
+    int n = 0, a = 0, b = 0;
+    uint64_t rs_g = 0;
+    if (active) {
+        r = find_chunk_read(A.chunk_base, A.n_reads, r_first, c);
+        rs_g = __ldg(A.offsets + r);
+        n = static_cast<int>(__ldg(A.offsets + r + 1) - rs_g);
+        a = static_cast<int>(c - __ldg(A.chunk_base + r)) * kChunk;
+        b = min(a + kChunk, n);
+    }
     __syncthreads();
     mbar_wait(bar, 0);
-
-    const uint64_t g0 = tile_base + static_cast<uint64_t>(tid) * A.chunk;
-    if (g0 >= A.total) return;
-    const uint64_t g1 = (g0 + A.chunk < A.total) ? g0 + A.chunk : A.total;
-    const int m = G.m, k = G.k, last_bit = G.last_bit, W = G.halo;
+    if (!active) return;
+    const unsigned char* text = s_text + (static_cast<int64_t>(rs_g) - *s_origin);  // text[x] = base x of read r
+    const int m = G.m, k = G.k, shift = 64 * NW - G.m;
     const int* __restrict__ ov = G.ov;
-    const uint64_t* eq_f = s_eq;
-    const uint64_t* eq_r = s_eq + 256 * NW;
 
-#define BB_TEXT(x) (s_text[static_cast<int64_t>(x) - s_origin])
-#define BB_STEP(EQ, CH, EMITCOND, POS)                                                    \
-    {                                                                                     \
-        score += col_step<NW>(col, (EQ) + static_cast<uint32_t>(CH) * NW, last_bit);      \
-        if (score <= k) {                                                                 \
-            if (EMITCOND) emit_entry(A.entries, A.n_entries, A.cap, make_key(r, A.group, strand, static_cast<uint32_t>(POS), score)); \
-        }                                                                                 \
-    }
-
-    uint32_t r = find_read(A.offsets, A.n_reads, g0);
-    for (; r < A.n_reads; r++) {
-        const uint64_t rs = __ldg(A.offsets + r), re = __ldg(A.offsets + r + 1);
-        if (rs >= g1) break;
-        if (re <= rs || re <= g0) continue;
-        const uint64_t a = rs > g0 ? rs : g0, b = re < g1 ? re : g1;   // this lane reports end positions in (a, b]
-        const uint32_t n = static_cast<uint32_t>(re - rs);
-
-        // ---------------- forward strand: ascending text ----------------
-        {
-            const int strand = BB_FWD;
-            const uint64_t ws = (a - rs > static_cast<uint64_t>(W)) ? a - W : rs;
-            Col<NW> col;
-            int score;
+    // ---------------- forward strand: ascending text; reports end positions x+1 for x in [a, b) ----------------
+    {
+        const uint64_t* eqp = s_eq;
+        Col<NW> col;
+        const bool fresh = a - W > 0;                       // warm-up starts inside the read
 #pragma unroll
-            for (int w = 0; w < NW; w++) { col.pv[w] = (ws == rs) ? G.pv_over[w] : G.pv_plain[w]; col.mv[w] = 0; }
-            score = (ws == rs) ? G.ov_m : m;
-            if (a == rs && score <= k) emit_entry(A.entries, A.n_entries, A.cap, make_key(r, A.group, strand, 0u, score));
-            uint64_t x = ws;
-            while (x < b && (x & 15)) { BB_STEP(eq_f, BB_TEXT(x), x >= a, x - rs + 1); x++; }
-            while (x + 16 <= b) {
-                const uint4 w4 = *reinterpret_cast<const uint4*>(&BB_TEXT(x));
-                const uint32_t ws4[4] = {w4.x, w4.y, w4.z, w4.w};
+        for (int w = 0; w < NW; w++) { col.pv[w] = fresh ? G.pv_plain_top[w] : G.pv_over_top[w]; col.mv[w] = 0; }
+        int score = fresh ? m : G.ov_m;
+        if (a == 0 && score <= k) scan_emit(A, r, BB_FWD, 0u, score);
+#pragma unroll 1
+        for (int x = a - W; x < b; x += kGroup) {
+            if (x < 0) continue;
+            int redo_to = x;                                 // characters [x, redo_to) need the per-character path
+            if (x + kGroup <= b) {
+                const Col<NW> saved = col;
+                const int saved_score = score;
+                int mn = 1 << 20;
 #pragma unroll
-                for (int q = 0; q < 4; q++) {
-#pragma unroll
-                    for (int t = 0; t < 4; t++) {
-                        const uint32_t ch = (ws4[q] >> (8 * t)) & 0xffu;
-                        BB_STEP(eq_f, ch, x + (4 * q + t) >= a, x + (4 * q + t) - rs + 1);
-                    }
+                for (int t = 0; t < kGroup; t++) {
+                    score += col_step_top<NW>(col, eqp + static_cast<uint32_t>(text[x + t]) * NW);
+                    mn = min(mn, score);
                 }
-                x += 16;
+                if (mn <= k && x + kGroup > a) { col = saved; score = saved_score; redo_to = x + kGroup; }
+            } else {
+                redo_to = b;
             }
-            while (x < b) { BB_STEP(eq_f, BB_TEXT(x), x >= a, x - rs + 1); x++; }
-            if (b == re) {   // virtual end positions past the text end (oracle policy S3)
-                for (int t = 1; t <= m; t++) {
-                    const int v = col_val<NW>(col.pv, col.mv, m - t) + __ldg(ov + t);
-                    if (v <= k) emit_entry(A.entries, A.n_entries, A.cap, make_key(r, A.group, strand, n + t, v));
-                }
+#pragma unroll 1
+            for (int xx = x; xx < redo_to; xx++) {
+                score += col_step_top<NW>(col, eqp + static_cast<uint32_t>(text[xx]) * NW);
+                if (score <= k && xx >= a) scan_emit(A, r, BB_FWD, static_cast<uint32_t>(xx + 1), score);
             }
         }
-        // ---------------- reverse-complement strand: descending text, complemented masks ----------------
-        {
-            const int strand = BB_RC;
-            const uint64_t we = (re - b > static_cast<uint64_t>(W)) ? b + W : re;
-            Col<NW> col;
-            int score;
-#pragma unroll
-            for (int w = 0; w < NW; w++) { col.pv[w] = (we == re) ? G.pv_over[w] : G.pv_plain[w]; col.mv[w] = 0; }
-            score = (we == re) ? G.ov_m : m;
-            if (b == re && score <= k) emit_entry(A.entries, A.n_entries, A.cap, make_key(r, A.group, strand, 0u, score));
-            uint64_t x = we;   // next char to consume is x-1
-            while (x > a && (x & 15)) { x--; BB_STEP(eq_r, BB_TEXT(x), x < b, re - x); }
-            while (x >= a + 16) {
-                x -= 16;
-                const uint4 w4 = *reinterpret_cast<const uint4*>(&BB_TEXT(x));
-                const uint32_t ws4[4] = {w4.x, w4.y, w4.z, w4.w};
-#pragma unroll
-                for (int q = 3; q >= 0; q--) {
-#pragma unroll
-                    for (int t = 3; t >= 0; t--) {
-                        const uint32_t ch = (ws4[q] >> (8 * t)) & 0xffu;
-                        BB_STEP(eq_r, ch, x + (4 * q + t) < b, re - (x + (4 * q + t)));
-                    }
-                }
-            }
-            while (x > a) { x--; BB_STEP(eq_r, BB_TEXT(x), x < b, re - x); }
-            if (a == rs) {
-                for (int t = 1; t <= m; t++) {
-                    const int v = col_val<NW>(col.pv, col.mv, m - t) + __ldg(ov + t);
-                    if (v <= k) emit_entry(A.entries, A.n_entries, A.cap, make_key(r, A.group, strand, n + t, v));
-                }
+        if (b == n) {                                        // virtual end positions past the text end (oracle policy S3)
+            for (int t = 1; t <= m; t++) {
+                const int v = col_val<NW>(col.pv, col.mv, shift + m - t) + __ldg(ov + t);
+                if (v <= k) scan_emit(A, r, BB_FWD, static_cast<uint32_t>(n + t), v);
             }
         }
     }
-#undef BB_STEP
-#undef BB_TEXT
+    // ---------------- reverse-complement strand: descending text, complemented masks; frame position n - x ----------------
+    {
+        const uint64_t* eqp = s_eq + 256 * NW;
+        Col<NW> col;
+        const bool fresh = b + W < n;                        // warm-up starts inside the read
+#pragma unroll
+        for (int w = 0; w < NW; w++) { col.pv[w] = fresh ? G.pv_plain_top[w] : G.pv_over_top[w]; col.mv[w] = 0; }
+        int score = fresh ? m : G.ov_m;
+        if (b == n && score <= k) scan_emit(A, r, BB_RC, 0u, score);
+        // same group grid as the forward pass (multiples of kGroup from the read start), walked from the top down
+#pragma unroll 1
+        for (int x = a + kChunk + W - kGroup; x >= a; x -= kGroup) {
+            if (x >= n) continue;
+            int redo_from = x + kGroup;                      // characters [redo_from, x + kGroup) -> per-character path
+            if (x + kGroup <= n) {
+                const Col<NW> saved = col;
+                const int saved_score = score;
+                int mn = 1 << 20;
+#pragma unroll
+                for (int t = kGroup - 1; t >= 0; t--) {
+                    score += col_step_top<NW>(col, eqp + static_cast<uint32_t>(text[x + t]) * NW);
+                    mn = min(mn, score);
+                }
+                if (mn <= k && x < b) { col = saved; score = saved_score; redo_from = x; }
+            } else {
+                redo_from = x;
+            }
+            const int top = min(x + kGroup, n);
+#pragma unroll 1
+            for (int xx = top - 1; xx >= redo_from; xx--) {
+                score += col_step_top<NW>(col, eqp + static_cast<uint32_t>(text[xx]) * NW);
+                if (score <= k && xx < b) scan_emit(A, r, BB_RC, static_cast<uint32_t>(n - xx), score);
+            }
+        }
+        if (a == 0) {
+            for (int t = 1; t <= m; t++) {
+                const int v = col_val<NW>(col.pv, col.mv, shift + m - t) + __ldg(ov + t);
+                if (v <= k) scan_emit(A, r, BB_RC, static_cast<uint32_t>(n + t), v);
+            }
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -417,10 +497,12 @@ struct BarArgs {
     Params prm;
     bb_row* rows;             // one slot per hit
     uint8_t* row_valid;
+    int hist_cols;            // history columns per lane in shared memory (longest region + 1)
 };
 
-constexpr int kBarWarps = 4;
+constexpr int kBarWarps = 2;
 constexpr int kMaxBarRounds = 16;   // up to 512 barcodes per group
+constexpr int kCodesPad = (kRegionMax + 15) & ~15;
 
 __device__ __forceinline__ int64_t rel_dist_to_end(int64_t pos, int64_t read_len) {   // searcher.rs:183-199
     if (pos < 0) return 1;
@@ -441,9 +523,37 @@ __device__ __forceinline__ void fill_flank_row(bb_row& row, const Hit& H, const 
     for (int q = 0; q < 6; q++) row.pad_[q] = 0;
 }
 
+// running top-two of the candidates a lane has scored, under (normalised score desc, barcode index asc)
+struct TopTwo {
+    double top_s = -1.0, sec_s = -1.0;
+    int top_b = 1 << 30;
+    int ok = 0, pi = 0, ei = 0, pj = 0, ej = 0, cost = 0, ts = 0, te = 0;   // map_pat_to_text_with_cost of the top
+};
+
+// Shared-memory size of k_barcode for `cols` DP columns per lane: every second column (Pv, Mv) of the lane's current
+// pattern, its 16 match masks, and the region's base codes.
+__host__ __device__ inline size_t barcode_smem_bytes(int cols) {
+    const size_t half = static_cast<size_t>(cols + 1) / 2 + 1;
+    return static_cast<size_t>(kBarWarps) * (2 * half * 32 * sizeof(uint64_t) + 16 * 32 * sizeof(uint64_t) + kCodesPad);
+}
+
+// One warp per flank match; lane = barcode pattern (rounds of 32).  Per pattern: one bit-vector pass over the region
+// that records every second column (Pv, Mv) in shared memory ([column][lane], conflict-free) and walks the S1 minima,
+// then the S2 traceback from the best minimum -- the horizontal deltas of a column pair are re-derived from the stored
+// vertical deltas (odd columns by one extra column step), so no cost value is ever materialised -- and the Lodhi
+// recurrence over the recovered ops.
+// The per-pattern best minimum is the same with k = floor(0.4*len) and with the fallback k = len (the first
+// lowest-cost minimum); the threshold only decides WHICH patterns are candidates, so both candidate sets are reduced
+// side by side and the fallback rule (searcher.rs:303-306) picks one at the end.
 __global__ void __launch_bounds__(kBarWarps * 32) k_barcode(const BarArgs A) {
-    __shared__ uint8_t s_codes[kBarWarps][kRegionMax];
+    extern __shared__ __align__(16) unsigned char bar_smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int half = (A.hist_cols + 1) / 2 + 1;
+    const size_t per_warp_u64 = 2 * static_cast<size_t>(half) * 32 + 16 * 32;
+    uint64_t* hpv = reinterpret_cast<uint64_t*>(bar_smem) + static_cast<size_t>(wib) * per_warp_u64;
+    uint64_t* hmv = hpv + static_cast<size_t>(half) * 32;
+    uint64_t* eqs_s = hmv + static_cast<size_t>(half) * 32;                  // [16 codes][32 lanes]
+    uint8_t* codes = bar_smem + static_cast<size_t>(kBarWarps) * per_warp_u64 * sizeof(uint64_t) + wib * kCodesPad;
     const uint32_t n_warps = gridDim.x * kBarWarps;
     for (uint32_t h = blockIdx.x * kBarWarps + wib; h < A.n_hits; h += n_warps) {
         const Hit H = A.hits[h];
@@ -452,123 +562,128 @@ __global__ void __launch_bounds__(kBarWarps * 32) k_barcode(const BarArgs A) {
         const uint64_t rs0 = A.offsets[H.read];
         const int n = static_cast<int>(A.offsets[H.read + 1] - rs0);
         const int rn = H.re - H.rs;
-        const int L = G.bar_len, nb = G.n_barcodes, k1 = G.k_bar, lb = L - 1;
+        const int L = G.bar_len, nb = G.n_barcodes, k1 = G.k_bar;
+        const int sh = 64 - L;                                  // patterns are top-aligned like the flank scan
         __syncwarp();
-        for (int q = lane; q < rn; q += 32) s_codes[wib][q] = __ldg(A.code + A.bases[rs0 + H.rs + q]);
-        __syncwarp();
-        const uint8_t* codes = s_codes[wib];
+        for (int q = lane; q < rn; q += 32) codes[q] = __ldg(A.code + A.bases[rs0 + H.rs + q]);
         const uint64_t* eqs = G.bar_eq + static_cast<size_t>(H.strand) * nb * 16;
-        const uint64_t pv_init = L >= 64 ? ~0ull : ((1ull << L) - 1ull);
+        const uint64_t pv_init = (L >= 64 ? ~0ull : ((1ull << L) - 1ull)) << sh;
+        const uint64_t wild = sh ? ((1ull << sh) - 1ull) : 0ull;
 
-        // pass A: bottom rows + S1 walk; best local minimum under k1 and under k = L (fallback)
-        int16_t best1_pos[kMaxBarRounds], bestL_pos[kMaxBarRounds];
+        TopTwo all, strict;          // candidates under the fallback k = len / under k1
         int matched = 0;
 #pragma unroll 1
         for (int rd = 0; rd * 32 < nb; rd++) {
             const int b = rd * 32 + lane;
-            int p1 = -1, c1 = 1 << 20, pL = -1, cL = 1 << 20;
+            bool has1 = false;
+            __syncwarp();
             if (b < nb) {
-                const uint64_t* eq = eqs + static_cast<size_t>(b) * 16;
+#pragma unroll
+                for (int cde = 0; cde < 16; cde++) eqs_s[cde * 32 + lane] = (__ldg(eqs + static_cast<size_t>(b) * 16 + cde) << sh) | wild;
+            }
+            __syncwarp();
+            if (b < nb) {
+                const uint64_t* eq = eqs_s + lane;
+                // ---- forward pass: record even columns, walk the minima (S1) ----
                 Col<1> col; col.pv[0] = pv_init; col.mv[0] = 0;
-                int prev = L, dec = 1;
+                hpv[lane] = pv_init; hmv[lane] = 0;
+                int prev = L, dec = 1, jend = -1, cbest = 1 << 20;
+                uint64_t e_next = rn > 0 ? eq[codes[0] * 32] : 0;
                 for (int p = 1; p <= rn; p++) {
-                    const uint64_t e = __ldg(eq + codes[p - 1]);
-                    const int cur = prev + col_step<1>(col, &e, lb);
-                    if (cur > prev && dec) {
-                        if (prev <= k1 && prev < c1) { c1 = prev; p1 = p - 1; }
-                        if (prev < cL) { cL = prev; pL = p - 1; }
-                    }
+                    const uint64_t e = e_next;
+                    if (p < rn) e_next = eq[codes[p] * 32];
+                    const int cur = prev + col_step_top<1>(col, &e);
+                    if ((p & 1) == 0) { hpv[(p >> 1) * 32 + lane] = col.pv[0]; hmv[(p >> 1) * 32 + lane] = col.mv[0]; }
+                    if (cur > prev && dec && prev < cbest) { cbest = prev; jend = p - 1; }
                     if (cur < prev) dec = 1; else if (cur > prev) dec = 0;
                     prev = cur;
                 }
-                if (dec) {
-                    if (prev <= k1 && prev < c1) { c1 = prev; p1 = rn; }
-                    if (prev < cL) { cL = prev; pL = rn; }
+                if (dec && prev < cbest) { cbest = prev; jend = rn; }
+                has1 = cbest <= k1;
+                // ---- traceback (S2; no overhang: column 0 is walked with pattern-only steps) ----
+                uint64_t mbits[4] = {0, 0, 0, 0};            // is-match bit of op q counted from the END of the path
+                int n_ops = 0, i = L, j = jend;
+                int cnt = 0, i_first = 0, i_last = 0, j_first = 0, j_last = 0, sub_cost = 0;
+                uint64_t e = 0, pvp = 0, mvp = 0, ph = 0, mh = 0;
+                bool have = false;
+                while (i > 0) {
+                    int di = 1, dj = 0, is_match = 0;
+                    if (j > 0) {
+                        if (!have) {                          // column pair (j-1, j): horizontal deltas from the stored verticals
+                            const int jp = j - 1;
+                            pvp = hpv[(jp >> 1) * 32 + lane]; mvp = hmv[(jp >> 1) * 32 + lane];
+                            if (jp & 1) {                     // odd column: one step from the stored even column below it
+                                Col<1> c2; c2.pv[0] = pvp; c2.mv[0] = mvp;
+                                const uint64_t e2 = eq[codes[jp - 1] * 32];
+                                col_step_top<1>(c2, &e2);
+                                pvp = c2.pv[0]; mvp = c2.mv[0];
+                            }
+                            e = eq[codes[j - 1] * 32];
+                            const uint64_t sum = (e & pvp) + pvp;
+                            ph = mvp | ~(sum | pvp | e); mh = pvp & ((sum ^ pvp) | e);
+                            have = true;
+                        }
+                        const uint64_t bit = 1ull << (i - 1 + sh);
+                        if (e & bit) { dj = 1; is_match = 1; }
+                        else {
+                            const int dh = (ph & bit) ? 1 : ((mh & bit) ? -1 : 0);
+                            const int dvp = (pvp & bit) ? 1 : ((mvp & bit) ? -1 : 0);
+                            if (dh + dvp == 1) dj = 1;                       // substitution
+                            else if (dh == 1) { di = 0; dj = 1; }            // text-only step
+                        }
+                    }
+                    i -= di; j -= dj;
+                    if (dj) have = false;
+                    if (is_match) mbits[(n_ops >> 6) & 3] |= 1ull << (n_ops & 63);
+                    n_ops++;
+                    if (i >= G.pbar0 && i < G.pbar1) {       // map_pat_to_text_with_cost range (cigar_parse.rs:22-30)
+                        if (cnt == 0) { i_last = i; j_last = j; }
+                        i_first = i; j_first = j;
+                        sub_cost += !is_match;
+                        cnt++;
+                    }
+                }
+                const int ts = j;
+                // ---- Lodhi S_3(C, 1/2), forward over the ops (same recurrence and order as orc_lodhi) ----
+                double a1 = 0.0, a2 = 0.0, s = 0.0;
+                for (int q = n_ops - 1; q >= 0; q--) {
+                    const bool mt = (mbits[(q >> 6) & 3] >> (q & 63)) & 1ull;
+                    if (mt) { s = s + 0.5 * a2; a2 = 0.5 * (a2 + a1); a1 = 0.5 * (a1 + 1.0); }
+                    else { a2 = 0.5 * a2; a1 = 0.5 * a1; }
+                }
+                const double sn = G.perfect > 0.0 ? s / G.perfect : 0.0;
+#pragma unroll
+                for (int set = 0; set < 2; set++) {
+                    TopTwo& T = set == 0 ? all : strict;
+                    if (set == 1 && !has1) continue;
+                    if (sn > T.top_s) {                       // ascending b within a lane: strict > keeps the lower index
+                        T.sec_s = T.top_s;
+                        T.top_s = sn; T.top_b = b;
+                        T.ok = cnt > 0; T.pi = i_first; T.ei = i_last; T.pj = j_first; T.ej = j_last; T.cost = sub_cost;
+                        T.ts = ts; T.te = jend;
+                    } else if (sn > T.sec_s) T.sec_s = sn;
                 }
             }
-            best1_pos[rd] = static_cast<int16_t>(p1); bestL_pos[rd] = static_cast<int16_t>(pL);
-            matched += __popc(__ballot_sync(0xffffffffu, p1 >= 0));
+            matched += __popc(__ballot_sync(0xffffffffu, has1));
         }
         const bool fallback = matched <= 1 && k1 < L;          // searcher.rs:303-306
-
-        // pass B: traceback + Lodhi of every candidate; per-lane top two under (score desc, index asc)
-        double top_s = -1.0, sec_s = -1.0;
-        int top_b = 1 << 30;
-        int t_ok = 0, t_pi = 0, t_ei = 0, t_pj = 0, t_ej = 0, t_cost = 0, t_ts = 0, t_te = 0;
-        int n_cand = 0;
-#pragma unroll 1
-        for (int rd = 0; rd * 32 < nb; rd++) {
-            const int b = rd * 32 + lane;
-            const int jend = b < nb ? (fallback ? bestL_pos[rd] : best1_pos[rd]) : -1;
-            if (jend < 0) continue;
-            n_cand++;
-            const uint64_t* eq = eqs + static_cast<size_t>(b) * 16;
-            uint64_t hpv[kRegionMax + 1], hmv[kRegionMax + 1];
-            Col<1> col; col.pv[0] = pv_init; col.mv[0] = 0;
-            hpv[0] = pv_init; hmv[0] = 0;
-            for (int j = 0; j < jend; j++) {
-                const uint64_t e = __ldg(eq + codes[j]);
-                col_step<1>(col, &e, lb);
-                hpv[j + 1] = col.pv[0]; hmv[j + 1] = col.mv[0];
-            }
-            // traceback (S2), no overhang: column 0 is walked with pattern-only steps
-            uint64_t mbits[4] = {0, 0, 0, 0};                  // is-match bit of op q counted from the END of the path
-            int n_ops = 0, i = L, j = jend;
-            int cnt = 0, i_first = 0, i_last = 0, j_first = 0, j_last = 0, sub_cost = 0;
-            while (i > 0) {
-                int di = 1, dj = 0, is_match = 0;
-                if (j > 0) {
-                    const int gcur = col_val<1>(&hpv[j], &hmv[j], i), d = col_val<1>(&hpv[j - 1], &hmv[j - 1], i - 1);
-                    const bool match = (__ldg(eq + codes[j - 1]) >> (i - 1)) & 1ull;
-                    if (match && d == gcur) { dj = 1; is_match = 1; }
-                    else if (d + 1 == gcur) { dj = 1; }
-                    else if (col_val<1>(&hpv[j - 1], &hmv[j - 1], i) + 1 == gcur) { di = 0; dj = 1; }
-                }
-                i -= di; j -= dj;
-                if (is_match && n_ops < 256) mbits[n_ops >> 6] |= 1ull << (n_ops & 63);
-                n_ops++;
-                if (i >= G.pbar0 && i < G.pbar1) {             // map_pat_to_text_with_cost range (cigar_parse.rs:22-30)
-                    if (cnt == 0) { i_last = i; j_last = j; }
-                    i_first = i; j_first = j;
-                    sub_cost += !is_match;
-                    cnt++;
-                }
-            }
-            const int ts = j;
-            // Lodhi S_3(C, 1/2), forward over the ops (same recurrence and order as orc_lodhi)
-            double a1 = 0.0, a2 = 0.0, s = 0.0;
-            for (int q = n_ops - 1; q >= 0; q--) {
-                const bool mt = q < 256 && ((mbits[q >> 6] >> (q & 63)) & 1ull);
-                if (mt) { s = s + 0.5 * a2; a2 = 0.5 * (a2 + a1); a1 = 0.5 * (a1 + 1.0); }
-                else { a2 = 0.5 * a2; a1 = 0.5 * a1; }
-            }
-            const double sn = G.perfect > 0.0 ? s / G.perfect : 0.0;
-            if (sn > top_s) {                                   // ascending b within a lane: strict > keeps the lower index
-                sec_s = top_s;
-                top_s = sn; top_b = b;
-                t_ok = cnt > 0; t_pi = i_first; t_ei = i_last; t_pj = j_first; t_ej = j_last; t_cost = sub_cost;
-                t_ts = ts; t_te = jend;
-            } else if (sn > sec_s) sec_s = sn;
-        }
+        const TopTwo& T = fallback ? all : strict;
+        const int total_cand = fallback ? nb : matched;
         // warp reduction: global top (score desc, index asc), then the best of the rest
-        double g_s = top_s; int g_b = top_b;
+        double g_s = T.top_s; int g_b = T.top_b;
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) {
             const double os = __shfl_xor_sync(0xffffffffu, g_s, off);
             const int ob = __shfl_xor_sync(0xffffffffu, g_b, off);
             if (os > g_s || (os == g_s && ob < g_b)) { g_s = os; g_b = ob; }
         }
-        const bool owner = (g_b == top_b) && top_b != (1 << 30);
-        double rest = owner ? sec_s : top_s;
+        const bool owner = (g_b == T.top_b) && T.top_b != (1 << 30);
+        double rest = owner ? T.sec_s : T.top_s;
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) {
             const double os = __shfl_xor_sync(0xffffffffu, rest, off);
             if (os > rest) rest = os;
         }
-        int total_cand = n_cand;
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) total_cand += __shfl_xor_sync(0xffffffffu, total_cand, off);
-
         if (total_cand == 0) {
             if (lane == 0) { bb_row row; fill_flank_row(row, H, G, n); A.rows[h] = row; A.row_valid[h] = 1; }
             continue;
@@ -577,17 +692,17 @@ __global__ void __launch_bounds__(kBarWarps * 32) k_barcode(const BarArgs A) {
             bool valid = g_s >= A.prm.min_score;                                   // searcher.rs:391-396
             if (total_cand > 1) valid = valid && (g_s - rest) >= A.prm.min_score_diff;
             bb_row row;
-            if (valid && t_ok) {
+            if (valid && T.ok) {
                 // to_path of the candidate with its strand overwritten by the flank's (S4, searcher.rs:333)
                 int64_t pj, ej;
-                if (H.strand == BB_FWD) { pj = t_pj; ej = t_ej; }
-                else { pj = static_cast<int64_t>(t_te) - 1 - (t_pj - t_ts); ej = static_cast<int64_t>(t_te) - 1 - (t_ej - t_ts); }
+                if (H.strand == BB_FWD) { pj = T.pj; ej = T.ej; }
+                else { pj = static_cast<int64_t>(T.te) - 1 - (T.pj - T.ts); ej = static_cast<int64_t>(T.te) - 1 - (T.ej - T.ts); }
                 row.read_idx = H.read; row.read_len = static_cast<uint32_t>(n);
                 row.rel_dist_to_end = rel_dist_to_end(H.text_start, n);
                 row.read_start_bar = H.rs + pj; row.read_end_bar = H.rs + ej + 1;
                 row.read_start_flank = H.text_start; row.read_end_flank = H.text_end;
-                row.bar_start = H.rs + t_pi; row.bar_end = H.rs + t_ei + 1;
-                row.flank_cost = H.cost; row.barcode_cost = t_cost; row.label_idx = g_b; row.group_idx = H.group;
+                row.bar_start = H.rs + T.pi; row.bar_end = H.rs + T.ei + 1;
+                row.flank_cost = H.cost; row.barcode_cost = T.cost; row.label_idx = g_b; row.group_idx = H.group;
                 row.match_type = static_cast<uint8_t>(G.match_type); row.strand = static_cast<uint8_t>(H.strand);
                 for (int q = 0; q < 6; q++) row.pad_[q] = 0;
             } else {

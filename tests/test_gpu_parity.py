@@ -144,7 +144,7 @@ def test_device_api_and_pipeline_equal_host_api():
             an.submit(sb.ctypes.data, so.ctypes.data, len(so) - 1, tag=nxt)
             nxt += 1; inflight += 1
         tag, rows = an.collect()
-        rows["read_idx"] += subs[tag][2]
+        rows["read_idx"] += np.uint32(subs[tag][2])
         parts.append((tag, rows)); inflight -= 1
     assert [t for t, _ in parts] == [0, 1, 2, 3, 4]
     assert np.concatenate([r for _, r in parts]).tobytes() == want.tobytes()
@@ -166,7 +166,7 @@ def test_full_size_properties():
     h = n // 2
     a1 = an.annotate(b[:int(o[h])], o[:h + 1])
     a2 = an.annotate(b[int(o[h]):], (o[h:] - o[h]).astype(np.uint64))
-    a2["read_idx"] += h
+    a2["read_idx"] += np.uint32(h)
     assert np.concatenate([a1, a2]).tobytes() == whole.tobytes()
     assert (np.diff(whole["read_idx"].astype(np.int64)) >= 0).all()            # grouped by read, input order
     idx = np.arange(0, n, 97)

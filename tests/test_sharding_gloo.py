@@ -22,7 +22,7 @@ def _worker(rank, world, port, q):
     lo, hi = sharding.shard_range(len(offsets) - 1, rank, world)
     sb, so = sharding.slice_reads(bases, offsets, lo, hi)
     mine = O.demux_batch(gs.as_dicts(), sb, so, n_threads=2)
-    mine["read_idx"] += lo
+    mine["read_idx"] += np.uint32(lo)
     kept = len(np.unique(mine["read_idx"]))
     counters = sharding.all_reduce_counters(hi - lo, kept, backend_device="cpu")
     q.put((rank, mine.tobytes(), counters))
