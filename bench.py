@@ -48,7 +48,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
@@ -57,9 +57,12 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
-    def stop(self):
+    def mark(self):
+        return time.time()
+
+    def stop(self, t0=None, t1=None):
         if not self.proc:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
         self.proc.terminate()
@@ -68,7 +71,12 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], None, set()
-        for ln in self.lines:
+        lines = [ln for ts, ln in self.lines if t0 is None or (t0 <= ts <= t1 + 0.05)]
+        window = "timed region"
+        if len(lines) < 3:                      # region shorter than the sampling period: use warm-up + timed region (same load)
+            lines = [ln for ts, ln in self.lines]
+            window = "warm-up + timed region"
+        for ln in lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -79,7 +87,7 @@ class ClockSampler:
             for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm), window=window)
 
 
 def make_batch(groups, n_reads, seed):
@@ -167,11 +175,12 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(args.warmup):
         n_rows = step()
-    sampler = ClockSampler(local)
     barrier()
-    sampler.start()
+    t_mark0 = sampler.mark()
     l0 = an.kernel_launches()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     scan_ms = []
@@ -185,7 +194,7 @@ def main():
             stage_acc[k] = stage_acc.get(k, 0.0) + v
     ev1.record(stream)
     barrier()
-    clocks = sampler.stop()
+    clocks = sampler.stop(t_mark0, sampler.mark())
     launches = an.kernel_launches() - l0
     ms = ev0.elapsed_time(ev1)
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
@@ -243,8 +252,8 @@ def main():
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
-            try:
-                traffic = json.load(open(tp)).get("k_flank_scan_dram_bytes_per_launch")
+            try:    # dram__bytes_read+write per launch from the committed ncu --set full capture, scaled to this batch size
+                traffic = json.load(open(tp))["k_flank_scan_dram_bytes_per_algorithmic_byte"] * algo_bytes
             except Exception:
                 traffic = None
         out = dict(metric="reads_per_s", value=value, unit="reads/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
