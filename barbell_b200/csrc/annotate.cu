@@ -635,4 +635,11 @@ int bb_fetch_flank_hits(bb_ctx* c, int32_t* out6, uint64_t cap, uint64_t* n_hits
     return BB_OK;
 }
 
+void* bb_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) return nullptr;
+    return p;
+}
+void bb_host_free(void* p) { if (p) cudaFreeHost(p); }
+
 }  // extern "C"

@@ -135,6 +135,10 @@ uint64_t bb_kernel_launches(const bb_ctx *ctx);
    6 int32 per hit {read_idx, group, strand, text_start, text_end, cost} in (read, group, Fwd-before-Rc, end) order */
 int  bb_fetch_flank_hits(bb_ctx *ctx, int32_t *out6, uint64_t cap, uint64_t *n_hits);
 
+/* page-locked host memory for the batch buffers handed to bb_submit / bb_annotate (NULL on failure) */
+void *bb_host_alloc(size_t bytes);
+void bb_host_free(void *p);
+
 int  bb_abi_version(void);
 
 #ifdef __cplusplus

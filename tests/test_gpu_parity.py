@@ -184,3 +184,34 @@ def test_set_groups_rejects_unsupported_geometry():
     gs = bb.GroupSet.from_kit("SQK-NBD114-96", max_flank_errors=30)     # k >= floor(0.4*46)-1
     with pytest.raises(bb.BarbellError):
         _annotator(gs)
+
+
+def test_cli_fastq_to_annotation_tsv(tmp_path):
+    """`barbell annotate --kit ... -i reads.fastq(.gz) -o out.tsv` == golden annotation.tsv of configs[0]; `kit` subcommand too."""
+    import gzip
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(bb.lib_path()), "barbell")
+    gs, bases, offsets, rows, _ = cases.load_case("nbd_1k")
+    n = len(offsets) - 1
+    fq1, fq2 = tmp_path / "a.fastq", tmp_path / "b.fastq.gz"
+    def rec(i):
+        s = bases[int(offsets[i]):int(offsets[i + 1])].tobytes().decode()
+        return f"@read_{i} runid=abc ch=7\n{s}\n+\n{'I' * len(s)}\n"
+    with open(fq1, "w") as f:
+        f.write("".join(rec(i) for i in range(n // 2)))
+    with gzip.open(fq2, "wt") as f:
+        f.write("".join(rec(i) for i in range(n // 2, n)))
+    want = open(cases.GOLD + "/nbd_1k.annotation.tsv").read()
+    out = tmp_path / "anno.tsv"
+    r = subprocess.run([exe, "annotate", "--kit", "SQK-NBD114-96", "-i", str(fq1), str(fq2), "-o", str(out), "-t", "4", "--batch-mb", "1"],
+                       capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "Annotation complete!" in r.stdout and "Auto edit flank cut off: 4" in r.stdout, r.stdout + r.stderr
+    assert open(out).read() == want
+    outdir = tmp_path / "kit_out"
+    r = subprocess.run([exe, "kit", "-k", "SQK-NBD114-96", "-i", str(fq1), str(fq2), "-o", str(outdir)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert open(outdir / "annotation.tsv").read() == want
+    # unknown kit: message, exit code 0 (reference bin/main.rs:301-304), empty/no output
+    r = subprocess.run([exe, "annotate", "--kit", "SQK-NOPE", "-i", str(fq1), "-o", str(tmp_path / "x.tsv")], capture_output=True, text=True)
+    assert r.returncode == 0 and "Error during processing" in r.stdout
