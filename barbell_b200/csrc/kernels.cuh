@@ -530,30 +530,36 @@ struct TopTwo {
     int ok = 0, pi = 0, ei = 0, pj = 0, ej = 0, cost = 0, ts = 0, te = 0;   // map_pat_to_text_with_cost of the top
 };
 
-// Shared-memory size of k_barcode for `cols` DP columns per lane: every second column (Pv, Mv) of the lane's current
-// pattern, its 16 match masks, and the region's base codes.
+// Shared-memory size of k_barcode for `cols` DP columns per lane: every column (Pv, Mv) of the lane's current pattern,
+// its 16 match masks, one traceback record per column, and the region's base codes.
 __host__ __device__ inline size_t barcode_smem_bytes(int cols) {
-    const size_t half = static_cast<size_t>(cols + 1) / 2 + 1;
-    return static_cast<size_t>(kBarWarps) * (2 * half * 32 * sizeof(uint64_t) + 16 * 32 * sizeof(uint64_t) + kCodesPad);
+    const size_t c = static_cast<size_t>(cols) + 1;
+    return static_cast<size_t>(kBarWarps) * (2 * c * 32 * sizeof(uint64_t) + 16 * 32 * sizeof(uint64_t) + c * 32 * sizeof(uint16_t) + kCodesPad);
 }
 
-// One warp per flank match; lane = barcode pattern (rounds of 32).  Per pattern: one bit-vector pass over the region
-// that records every second column (Pv, Mv) in shared memory ([column][lane], conflict-free) and walks the S1 minima,
-// then the S2 traceback from the best minimum -- the horizontal deltas of a column pair are re-derived from the stored
-// vertical deltas (odd columns by one extra column step), so no cost value is ever materialised -- and the Lodhi
-// recurrence over the recovered ops.
+// One warp per flank match; lane = barcode pattern (rounds of 32).  Per pattern:
+//  * one top-aligned bit-vector pass over the region that records every column (Pv, Mv) in shared memory
+//    ([column][lane], conflict-free) and walks the S1 minima online;
+//  * the S2 traceback from the best minimum, one COLUMN per iteration and branch-free: the horizontal deltas of the
+//    column pair are re-derived from the stored vertical deltas, the rows at which the path may leave the column
+//    (match/substitution first, then text-only) form a bit-vector, and the highest such row at or below the current one
+//    (count-leading-zeros) gives the number of pattern-only steps and the leaving op -- no cost value is materialised;
+//  * the Lodhi recurrence over the per-column records (leaving op + run of non-match ops; a run of d non-match ops is
+//    the exact scaling by 2^-d), in the oracle's op order.
 // The per-pattern best minimum is the same with k = floor(0.4*len) and with the fallback k = len (the first
 // lowest-cost minimum); the threshold only decides WHICH patterns are candidates, so both candidate sets are reduced
 // side by side and the fallback rule (searcher.rs:303-306) picks one at the end.
 __global__ void __launch_bounds__(kBarWarps * 32) k_barcode(const BarArgs A) {
     extern __shared__ __align__(16) unsigned char bar_smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int half = (A.hist_cols + 1) / 2 + 1;
-    const size_t per_warp_u64 = 2 * static_cast<size_t>(half) * 32 + 16 * 32;
-    uint64_t* hpv = reinterpret_cast<uint64_t*>(bar_smem) + static_cast<size_t>(wib) * per_warp_u64;
-    uint64_t* hmv = hpv + static_cast<size_t>(half) * 32;
-    uint64_t* eqs_s = hmv + static_cast<size_t>(half) * 32;                  // [16 codes][32 lanes]
-    uint8_t* codes = bar_smem + static_cast<size_t>(kBarWarps) * per_warp_u64 * sizeof(uint64_t) + wib * kCodesPad;
+    const size_t ncol = static_cast<size_t>(A.hist_cols) + 1;
+    const size_t per_warp = 2 * ncol * 32 * sizeof(uint64_t) + 16 * 32 * sizeof(uint64_t) + ncol * 32 * sizeof(uint16_t) + kCodesPad;
+    unsigned char* wbase = bar_smem + static_cast<size_t>(wib) * per_warp;
+    uint64_t* hpv = reinterpret_cast<uint64_t*>(wbase);
+    uint64_t* hmv = hpv + ncol * 32;
+    uint64_t* eqs_s = hmv + ncol * 32;                                       // [16 codes][32 lanes]
+    uint16_t* rec = reinterpret_cast<uint16_t*>(eqs_s + 16 * 32);            // [column][lane]
+    uint8_t* codes = reinterpret_cast<uint8_t*>(rec + ncol * 32);
     const uint32_t n_warps = gridDim.x * kBarWarps;
     for (uint32_t h = blockIdx.x * kBarWarps + wib; h < A.n_hits; h += n_warps) {
         const Hit H = A.hits[h];
@@ -563,6 +569,7 @@ __global__ void __launch_bounds__(kBarWarps * 32) k_barcode(const BarArgs A) {
         const int n = static_cast<int>(A.offsets[H.read + 1] - rs0);
         const int rn = H.re - H.rs;
         const int L = G.bar_len, nb = G.n_barcodes, k1 = G.k_bar;
+        const int pb0 = G.pbar0, pb1 = G.pbar1;
         const int sh = 64 - L;                                  // patterns are top-aligned like the flank scan
         __syncwarp();
         for (int q = lane; q < rn; q += 32) codes[q] = __ldg(A.code + A.bases[rs0 + H.rs + q]);
@@ -584,7 +591,7 @@ __global__ void __launch_bounds__(kBarWarps * 32) k_barcode(const BarArgs A) {
             __syncwarp();
             if (b < nb) {
                 const uint64_t* eq = eqs_s + lane;
-                // ---- forward pass: record even columns, walk the minima (S1) ----
+                // ---- forward pass: record the columns, walk the minima (S1) ----
                 Col<1> col; col.pv[0] = pv_init; col.mv[0] = 0;
                 hpv[lane] = pv_init; hmv[lane] = 0;
                 int prev = L, dec = 1, jend = -1, cbest = 1 << 20;
@@ -593,63 +600,60 @@ __global__ void __launch_bounds__(kBarWarps * 32) k_barcode(const BarArgs A) {
                     const uint64_t e = e_next;
                     if (p < rn) e_next = eq[codes[p] * 32];
                     const int cur = prev + col_step_top<1>(col, &e);
-                    if ((p & 1) == 0) { hpv[(p >> 1) * 32 + lane] = col.pv[0]; hmv[(p >> 1) * 32 + lane] = col.mv[0]; }
+                    hpv[p * 32 + lane] = col.pv[0]; hmv[p * 32 + lane] = col.mv[0];
                     if (cur > prev && dec && prev < cbest) { cbest = prev; jend = p - 1; }
                     if (cur < prev) dec = 1; else if (cur > prev) dec = 0;
                     prev = cur;
                 }
                 if (dec && prev < cbest) { cbest = prev; jend = rn; }
                 has1 = cbest <= k1;
-                // ---- traceback (S2; no overhang: column 0 is walked with pattern-only steps) ----
-                uint64_t mbits[4] = {0, 0, 0, 0};            // is-match bit of op q counted from the END of the path
-                int n_ops = 0, i = L, j = jend;
+                // ---- traceback (S2), one column per iteration; no overhang: column 0 is walked with pattern-only steps ----
+                int i = L, j = jend, nrec = 0;
                 int cnt = 0, i_first = 0, i_last = 0, j_first = 0, j_last = 0, sub_cost = 0;
-                uint64_t e = 0, pvp = 0, mvp = 0, ph = 0, mh = 0;
-                bool have = false;
-                while (i > 0) {
-                    int di = 1, dj = 0, is_match = 0;
-                    if (j > 0) {
-                        if (!have) {                          // column pair (j-1, j): horizontal deltas from the stored verticals
-                            const int jp = j - 1;
-                            pvp = hpv[(jp >> 1) * 32 + lane]; mvp = hmv[(jp >> 1) * 32 + lane];
-                            if (jp & 1) {                     // odd column: one step from the stored even column below it
-                                Col<1> c2; c2.pv[0] = pvp; c2.mv[0] = mvp;
-                                const uint64_t e2 = eq[codes[jp - 1] * 32];
-                                col_step_top<1>(c2, &e2);
-                                pvp = c2.pv[0]; mvp = c2.mv[0];
-                            }
-                            e = eq[codes[j - 1] * 32];
-                            const uint64_t sum = (e & pvp) + pvp;
-                            ph = mvp | ~(sum | pvp | e); mh = pvp & ((sum ^ pvp) | e);
-                            have = true;
-                        }
-                        const uint64_t bit = 1ull << (i - 1 + sh);
-                        if (e & bit) { dj = 1; is_match = 1; }
-                        else {
-                            const int dh = (ph & bit) ? 1 : ((mh & bit) ? -1 : 0);
-                            const int dvp = (pvp & bit) ? 1 : ((mvp & bit) ? -1 : 0);
-                            if (dh + dvp == 1) dj = 1;                       // substitution
-                            else if (dh == 1) { di = 0; dj = 1; }            // text-only step
-                        }
+                while (i > 0 && j > 0) {
+                    const int jp = j - 1;
+                    const uint64_t pvp = hpv[jp * 32 + lane], mvp = hmv[jp * 32 + lane];
+                    const uint64_t e = eq[codes[jp] * 32];
+                    const uint64_t sum = (e & pvp) + pvp;
+                    const uint64_t ph = mvp | ~(sum | pvp | e), mh = pvp & ((sum ^ pvp) | e);   // deltas between columns j-1 and j
+                    const uint64_t diag = e | (ph & ~(pvp | mvp)) | (pvp & ~(ph | mh));       // match, or D[i-1][j-1] + 1 == D[i][j]
+                    const uint64_t stop = diag | ph;                                            // ... else text-only if D[i][j-1] + 1 == D[i][j]
+                    const int sbit = i - 1 + sh;
+                    const uint64_t below = (sbit >= 63 ? ~0ull : ((2ull << sbit) - 1ull)) & ~wild;
+                    const uint64_t cand = stop & below;
+                    if (cand == 0) break;                       // only pattern-only steps remain in this column
+                    const int t = 63 - __clzll(static_cast<long long>(cand));
+                    const int il = t - sh + 1;                  // the path leaves the column at row il
+                    const int d = i - il;                       // after d pattern-only steps (pre-op rows i-1 .. il)
+                    {
+                        const int lo = max(il, pb0), hi = min(i - 1, pb1 - 1);
+                        if (hi >= lo) { if (cnt == 0) { i_last = hi; j_last = j; } i_first = lo; j_first = j; sub_cost += hi - lo + 1; cnt += hi - lo + 1; }
                     }
-                    i -= di; j -= dj;
-                    if (dj) have = false;
-                    if (is_match) mbits[(n_ops >> 6) & 3] |= 1ull << (n_ops & 63);
-                    n_ops++;
-                    if (i >= G.pbar0 && i < G.pbar1) {       // map_pat_to_text_with_cost range (cigar_parse.rs:22-30)
+                    const int is_diag = static_cast<int>((diag >> t) & 1ull), is_match = static_cast<int>((e >> t) & 1ull);
+                    i = il - is_diag; j = jp;                   // pre-op position of the leaving op
+                    if (i >= pb0 && i < pb1) {                  // map_pat_to_text_with_cost range (cigar_parse.rs:22-30)
                         if (cnt == 0) { i_last = i; j_last = j; }
-                        i_first = i; j_first = j;
-                        sub_cost += !is_match;
-                        cnt++;
+                        i_first = i; j_first = j; sub_cost += 1 - is_match; cnt++;
                     }
+                    rec[nrec * 32 + lane] = static_cast<uint16_t>((d << 1) | is_match);
+                    nrec++;
+                }
+                if (i > 0) {                                    // leading pattern-only steps at column j (first ops of the path)
+                    const int lo = max(0, pb0), hi = min(i - 1, pb1 - 1);
+                    if (hi >= lo) { if (cnt == 0) { i_last = hi; j_last = j; } i_first = lo; j_first = j; sub_cost += hi - lo + 1; cnt += hi - lo + 1; }
                 }
                 const int ts = j;
-                // ---- Lodhi S_3(C, 1/2), forward over the ops (same recurrence and order as orc_lodhi) ----
+                // ---- Lodhi S_3(C, 1/2) in path order (same recurrence and order as orc_lodhi; leading non-match ops act on zeros) ----
                 double a1 = 0.0, a2 = 0.0, s = 0.0;
-                for (int q = n_ops - 1; q >= 0; q--) {
-                    const bool mt = (mbits[(q >> 6) & 3] >> (q & 63)) & 1ull;
-                    if (mt) { s = s + 0.5 * a2; a2 = 0.5 * (a2 + a1); a1 = 0.5 * (a1 + 1.0); }
+                for (int q = nrec - 1; q >= 0; q--) {
+                    const int r = rec[q * 32 + lane];
+                    if (r & 1) { s = s + 0.5 * a2; a2 = 0.5 * (a2 + a1); a1 = 0.5 * (a1 + 1.0); }
                     else { a2 = 0.5 * a2; a1 = 0.5 * a1; }
+                    const int d = r >> 1;
+                    if (d) {                                    // d non-match ops = exact scaling by 2^-d
+                        const double f = __longlong_as_double(static_cast<long long>(1023 - d) << 52);
+                        a2 = a2 * f; a1 = a1 * f;
+                    }
                 }
                 const double sn = G.perfect > 0.0 ? s / G.perfect : 0.0;
 #pragma unroll
