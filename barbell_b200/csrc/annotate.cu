@@ -78,7 +78,7 @@ static double lodhi_all_match(int l) {   // reference searcher.rs:229-239 with t
 struct GroupTables {          // device copies for all groups of a ctx (shared by its engines)
     std::vector<DevGroup> host;
     DBuf d_groups, d_blob, d_code;
-    int n = 0, max_trace_cols = 0, max_nw = 1, max_region = 0;
+    int n = 0, max_trace_cols = 0, max_nw = 1, max_region = 0, max_bar_len = 0;
     void release() { d_groups.release(); d_blob.release(); d_code.release(); host.clear(); n = 0; }
 };
 
@@ -254,10 +254,16 @@ struct Engine {
             B.bases = bases; B.offsets = offsets; B.hits = d_hits.as<Hit>(); B.n_hits = n_hits; B.groups = d_groups();
             B.code = gt->d_code.as<uint8_t>(); B.prm = prm; B.rows = d_rows.as<bb_row>(); B.row_valid = d_valid.as<uint8_t>();
             B.hist_cols = gt->max_region + 1;
-            const size_t smem = barcode_smem_bytes(B.hist_cols);
-            BB_CUDA(cudaFuncSetAttribute(k_barcode, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-            const unsigned blocks = std::min<unsigned>((n_hits + kBarWarps - 1) / kBarWarps, 148 * 16);
-            k_barcode<<<blocks, kBarWarps * 32, smem, st>>>(B);
+            const bool packed = gt->max_bar_len <= 48;
+            const size_t smem = barcode_smem_bytes(B.hist_cols, packed);
+            const unsigned blocks = std::min<unsigned>((n_hits + kBarWarps - 1) / kBarWarps, 148 * 32);
+            if (packed) {
+                BB_CUDA(cudaFuncSetAttribute(k_barcode<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+                k_barcode<true><<<blocks, kBarWarps * 32, smem, st>>>(B);
+            } else {
+                BB_CUDA(cudaFuncSetAttribute(k_barcode<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+                k_barcode<false><<<blocks, kBarWarps * 32, smem, st>>>(B);
+            }
             launches++;
             BB_CUDA(cudaGetLastError());
         }
@@ -420,7 +426,7 @@ int bb_set_groups(bb_ctx* c, const bb_group* groups, int32_t n_groups) {
     std::vector<uint64_t> blob;
     std::vector<size_t> off_eq(n_groups), off_eqt(n_groups), off_bar(n_groups), off_ov(n_groups);
     std::vector<DevGroup> hg(n_groups);
-    int max_trace = 0, max_nw = 1, max_region = 0;
+    int max_trace = 0, max_nw = 1, max_region = 0, max_bar_len = 0;
     for (int g = 0; g < n_groups; g++) {
         const bb_group& S = groups[g];
         DevGroup& D = hg[g];
@@ -446,6 +452,7 @@ int bb_set_groups(bb_ctx* c, const bb_group* groups, int32_t n_groups) {
         D.perfect = lodhi_all_match(S.pad1 - S.pad0);
         max_trace = std::max(max_trace, D.trace_cols); max_nw = std::max(max_nw, D.nw);
         max_region = std::max(max_region, S.bar1 - S.bar0 + 1 + S.k_flank + 2 * kPadding);
+        max_bar_len = std::max(max_bar_len, S.bar_len);
         std::vector<uint8_t> pc(m);
         for (int i = 0; i < m; i++) pc[i] = kAlpha.code[static_cast<uint8_t>(S.flank[i])];
         std::vector<int> ov(m + 1);
@@ -514,7 +521,7 @@ int bb_set_groups(bb_ctx* c, const bb_group* groups, int32_t n_groups) {
     cudaError_t e2 = cudaMemcpy(T.d_groups.p, hg.data(), sizeof(DevGroup) * n_groups, cudaMemcpyHostToDevice);
     cudaError_t e3 = cudaMemcpy(T.d_code.p, kAlpha.code, 256, cudaMemcpyHostToDevice);
     if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) return (ctx_error(c, "cudaMemcpy of the pattern tables failed"), BB_ERR_CUDA);
-    T.host = hg; T.n = n_groups; T.max_trace_cols = max_trace; T.max_nw = max_nw; T.max_region = max_region;
+    T.host = hg; T.n = n_groups; T.max_trace_cols = max_trace; T.max_nw = max_nw; T.max_region = max_region; T.max_bar_len = max_bar_len;
     return BB_OK;
 }
 

@@ -500,7 +500,7 @@ struct BarArgs {
     int hist_cols;            // history columns per lane in shared memory (longest region + 1)
 };
 
-constexpr int kBarWarps = 2;
+constexpr int kBarWarps = 1;
 constexpr int kMaxBarRounds = 16;   // up to 512 barcodes per group
 constexpr int kCodesPad = (kRegionMax + 15) & ~15;
 
@@ -530,12 +530,42 @@ struct TopTwo {
     int ok = 0, pi = 0, ei = 0, pj = 0, ej = 0, cost = 0, ts = 0, te = 0;   // map_pat_to_text_with_cost of the top
 };
 
-// Shared-memory size of k_barcode for `cols` DP columns per lane: every column (Pv, Mv) of the lane's current pattern,
-// its 16 match masks, one traceback record per column, and the region's base codes.
-__host__ __device__ inline size_t barcode_smem_bytes(int cols) {
+// Shared-memory size of k_barcode for `cols` DP columns per lane: every column (Pv, Mv) of the lane's current pattern
+// (12 bytes when the pattern has <= 48 rows: the low 16 bits of both words are wildcard rows and always zero, so the two
+// low halves share one 32-bit word; 16 bytes otherwise), its 16 match masks, one traceback record per column, and the
+// region's base codes.
+__host__ __device__ inline size_t barcode_warp_bytes(int cols, bool packed) {
     const size_t c = static_cast<size_t>(cols) + 1;
-    return static_cast<size_t>(kBarWarps) * (2 * c * 32 * sizeof(uint64_t) + 16 * 32 * sizeof(uint64_t) + c * 32 * sizeof(uint16_t) + kCodesPad);
+    return c * 32 * (packed ? 12 : 16) + 16 * 32 * sizeof(uint64_t) + ((c * 32 + 15) & ~static_cast<size_t>(15)) + kCodesPad;
 }
+__host__ __device__ inline size_t barcode_smem_bytes(int cols, bool packed) { return kBarWarps * barcode_warp_bytes(cols, packed); }
+
+template <bool PACKED>
+struct ColHist {                        // [column][word][lane] so that a warp's accesses are conflict-free
+    uint32_t* w;
+    int lane;
+    __device__ __forceinline__ void store(int col, uint64_t pv, uint64_t mv) const {
+        if constexpr (PACKED) {
+            uint32_t* q = w + static_cast<size_t>(col) * 96 + lane;
+            q[0] = static_cast<uint32_t>(pv >> 32); q[32] = static_cast<uint32_t>(mv >> 32);
+            q[64] = (static_cast<uint32_t>(pv) >> 16) | (static_cast<uint32_t>(mv) & 0xffff0000u);
+        } else {
+            uint64_t* q = reinterpret_cast<uint64_t*>(w) + static_cast<size_t>(col) * 64 + lane;
+            q[0] = pv; q[32] = mv;
+        }
+    }
+    __device__ __forceinline__ void load(int col, uint64_t& pv, uint64_t& mv) const {
+        if constexpr (PACKED) {
+            const uint32_t* q = w + static_cast<size_t>(col) * 96 + lane;
+            const uint32_t lo = q[64];
+            pv = (static_cast<uint64_t>(q[0]) << 32) | (lo << 16);
+            mv = (static_cast<uint64_t>(q[32]) << 32) | (lo & 0xffff0000u);
+        } else {
+            const uint64_t* q = reinterpret_cast<const uint64_t*>(w) + static_cast<size_t>(col) * 64 + lane;
+            pv = q[0]; mv = q[32];
+        }
+    }
+};
 
 // One warp per flank match; lane = barcode pattern (rounds of 32).  Per pattern:
 //  * one top-aligned bit-vector pass over the region that records every column (Pv, Mv) in shared memory
@@ -549,17 +579,16 @@ __host__ __device__ inline size_t barcode_smem_bytes(int cols) {
 // The per-pattern best minimum is the same with k = floor(0.4*len) and with the fallback k = len (the first
 // lowest-cost minimum); the threshold only decides WHICH patterns are candidates, so both candidate sets are reduced
 // side by side and the fallback rule (searcher.rs:303-306) picks one at the end.
+template <bool PACKED>
 __global__ void __launch_bounds__(kBarWarps * 32) k_barcode(const BarArgs A) {
     extern __shared__ __align__(16) unsigned char bar_smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const size_t ncol = static_cast<size_t>(A.hist_cols) + 1;
-    const size_t per_warp = 2 * ncol * 32 * sizeof(uint64_t) + 16 * 32 * sizeof(uint64_t) + ncol * 32 * sizeof(uint16_t) + kCodesPad;
-    unsigned char* wbase = bar_smem + static_cast<size_t>(wib) * per_warp;
-    uint64_t* hpv = reinterpret_cast<uint64_t*>(wbase);
-    uint64_t* hmv = hpv + ncol * 32;
-    uint64_t* eqs_s = hmv + ncol * 32;                                       // [16 codes][32 lanes]
-    uint16_t* rec = reinterpret_cast<uint16_t*>(eqs_s + 16 * 32);            // [column][lane]
-    uint8_t* codes = reinterpret_cast<uint8_t*>(rec + ncol * 32);
+    unsigned char* wbase = bar_smem + static_cast<size_t>(wib) * barcode_warp_bytes(A.hist_cols, PACKED);
+    uint64_t* eqs_s = reinterpret_cast<uint64_t*>(wbase);                    // [16 codes][32 lanes]
+    const ColHist<PACKED> hist{reinterpret_cast<uint32_t*>(eqs_s + 16 * 32), lane};
+    uint8_t* rec = wbase + 16 * 32 * sizeof(uint64_t) + ncol * 32 * (PACKED ? 12 : 16);   // [column][lane]
+    uint8_t* codes = rec + ((ncol * 32 + 15) & ~static_cast<size_t>(15));
     const uint32_t n_warps = gridDim.x * kBarWarps;
     for (uint32_t h = blockIdx.x * kBarWarps + wib; h < A.n_hits; h += n_warps) {
         const Hit H = A.hits[h];
@@ -593,14 +622,14 @@ __global__ void __launch_bounds__(kBarWarps * 32) k_barcode(const BarArgs A) {
                 const uint64_t* eq = eqs_s + lane;
                 // ---- forward pass: record the columns, walk the minima (S1) ----
                 Col<1> col; col.pv[0] = pv_init; col.mv[0] = 0;
-                hpv[lane] = pv_init; hmv[lane] = 0;
+                hist.store(0, pv_init, 0);
                 int prev = L, dec = 1, jend = -1, cbest = 1 << 20;
                 uint64_t e_next = rn > 0 ? eq[codes[0] * 32] : 0;
                 for (int p = 1; p <= rn; p++) {
                     const uint64_t e = e_next;
                     if (p < rn) e_next = eq[codes[p] * 32];
                     const int cur = prev + col_step_top<1>(col, &e);
-                    hpv[p * 32 + lane] = col.pv[0]; hmv[p * 32 + lane] = col.mv[0];
+                    hist.store(p, col.pv[0], col.mv[0]);
                     if (cur > prev && dec && prev < cbest) { cbest = prev; jend = p - 1; }
                     if (cur < prev) dec = 1; else if (cur > prev) dec = 0;
                     prev = cur;
@@ -610,14 +639,24 @@ __global__ void __launch_bounds__(kBarWarps * 32) k_barcode(const BarArgs A) {
                 // ---- traceback (S2), one column per iteration; no overhang: column 0 is walked with pattern-only steps ----
                 int i = L, j = jend, nrec = 0;
                 int cnt = 0, i_first = 0, i_last = 0, j_first = 0, j_last = 0, sub_cost = 0;
-                while (i > 0 && j > 0) {
-                    const int jp = j - 1;
-                    const uint64_t pvp = hpv[jp * 32 + lane], mvp = hmv[jp * 32 + lane];
-                    const uint64_t e = eq[codes[jp] * 32];
+                // the bit-vectors of a column pair do not depend on the path, so the pair for the NEXT iteration is
+                // prepared while the current one resolves its row (software pipelining of the LDS + vector work)
+                uint64_t n_e = 0, n_diag = 0, n_stop = 0;
+                auto prepare = [&](int jj) {                    // pair (jj-1, jj), jj >= 1
+                    uint64_t pvp, mvp;
+                    hist.load(jj - 1, pvp, mvp);
+                    const uint64_t e = eq[codes[jj - 1] * 32];
                     const uint64_t sum = (e & pvp) + pvp;
-                    const uint64_t ph = mvp | ~(sum | pvp | e), mh = pvp & ((sum ^ pvp) | e);   // deltas between columns j-1 and j
-                    const uint64_t diag = e | (ph & ~(pvp | mvp)) | (pvp & ~(ph | mh));       // match, or D[i-1][j-1] + 1 == D[i][j]
-                    const uint64_t stop = diag | ph;                                            // ... else text-only if D[i][j-1] + 1 == D[i][j]
+                    const uint64_t ph = mvp | ~(sum | pvp | e), mh = pvp & ((sum ^ pvp) | e);   // deltas between columns jj-1 and jj
+                    n_e = e;
+                    n_diag = e | (ph & ~(pvp | mvp)) | (pvp & ~(ph | mh));   // match, or D[i-1][j-1] + 1 == D[i][j]
+                    n_stop = n_diag | ph;                                      // ... else text-only if D[i][j-1] + 1 == D[i][j]
+                };
+                if (j > 0) prepare(j);
+                while (i > 0 && j > 0) {
+                    const uint64_t e = n_e, diag = n_diag, stop = n_stop;
+                    const int jp = j - 1;
+                    if (jp > 0) prepare(jp);
                     const int sbit = i - 1 + sh;
                     const uint64_t below = (sbit >= 63 ? ~0ull : ((2ull << sbit) - 1ull)) & ~wild;
                     const uint64_t cand = stop & below;
@@ -635,7 +674,7 @@ __global__ void __launch_bounds__(kBarWarps * 32) k_barcode(const BarArgs A) {
                         if (cnt == 0) { i_last = i; j_last = j; }
                         i_first = i; j_first = j; sub_cost += 1 - is_match; cnt++;
                     }
-                    rec[nrec * 32 + lane] = static_cast<uint16_t>((d << 1) | is_match);
+                    rec[nrec * 32 + lane] = static_cast<uint8_t>((d << 1) | is_match);
                     nrec++;
                 }
                 if (i > 0) {                                    // leading pattern-only steps at column j (first ops of the path)
