@@ -197,10 +197,10 @@ class GroupSet:
 class Annotator:
     """One GPU context = the reference's Demuxer (src/annotate/searcher.rs:12-29, 202-227, 430-490) in batch form."""
 
-    def __init__(self, groups: GroupSet, device=0, alpha=0.4, min_score=0.2, min_score_diff=0.1):
+    def __init__(self, groups: GroupSet, device=0, alpha=0.4, min_score=0.2, min_score_diff=0.1, use_filter=True):
         self._ctx = C.c_void_p()
         self.groups = groups
-        o = _Opts(device, alpha, min_score, min_score_diff, 0, 0, 0)
+        o = _Opts(device, alpha, min_score, min_score_diff, 0, 0, 0 if use_filter else 1)
         err = C.create_string_buffer(512)
         rc = lib().bb_create(C.byref(o), C.byref(self._ctx), err, 512)
         if rc != 0:

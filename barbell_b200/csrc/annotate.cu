@@ -90,9 +90,11 @@ struct Engine {
     std::string err;
     uint64_t launches = 0;
     // device buffers
-    DBuf d_bases, d_offsets, d_nch, d_chunk_base, d_tile_first, d_entries, d_sorted, d_cub, d_flags, d_hitkeys, d_hits, d_hist, d_rows, d_valid, d_rows_out, d_hits6;
+    DBuf d_bases, d_offsets, d_nch, d_chunk_base, d_tile_first, d_windows, d_entries, d_sorted, d_cub, d_flags, d_hitkeys, d_hits, d_hist, d_rows, d_valid, d_rows_out, d_hits6;
     DBuf d_counters;                     // [0] n_entries (u32) [2] n_selected (u32) [4..5] kept reads (u64)
     uint32_t entries_cap = 0;
+    bool use_filter = true;              // bb_opts.flags bit 0 disables the pre-filter (exact scan everywhere)
+    uint64_t last_windows = 0;
     uint32_t* h_counters = nullptr;      // pinned, 8 x u32
     bb_row* h_rows = nullptr; size_t h_rows_cap = 0;   // pinned
     cudaEvent_t ev[6] = {};
@@ -116,7 +118,7 @@ struct Engine {
     }
     void destroy() {
         cudaSetDevice(device);
-        for (DBuf* b : {&d_bases, &d_offsets, &d_nch, &d_chunk_base, &d_tile_first, &d_entries, &d_sorted, &d_cub, &d_flags, &d_hitkeys, &d_hits, &d_hist, &d_rows,
+        for (DBuf* b : {&d_bases, &d_offsets, &d_nch, &d_chunk_base, &d_tile_first, &d_windows, &d_entries, &d_sorted, &d_cub, &d_flags, &d_hitkeys, &d_hits, &d_hist, &d_rows,
                         &d_valid, &d_rows_out, &d_hits6, &d_counters})
             b->release();
         if (h_counters) cudaFreeHost(h_counters);
@@ -168,13 +170,15 @@ struct Engine {
 
         // ---- K1: flank scan, one launch per group ----
         uint32_t n_entries = 0;
-        for (int attempt = 0; attempt < 4; attempt++) {
+        bool force_exact = false, any_filtered = false;
+        for (int attempt = 0; attempt < 5; attempt++) {
             if (entries_cap == 0) {
                 uint64_t want = std::max<uint64_t>(1u << 20, static_cast<uint64_t>(n_reads) * 32);
                 entries_cap = static_cast<uint32_t>(std::min<uint64_t>(want, 1u << 28));
             }
             BB_CUDA(d_entries.ensure(static_cast<size_t>(entries_cap) * 8));
             BB_CUDA(cudaMemsetAsync(d_cnt, 0, 64, st));
+            bool filtered = false;
             for (int g = 0; g < gt->n; g++) {
                 const DevGroup& G = gt->host[g];
                 ScanArgs A{};
@@ -182,6 +186,24 @@ struct Engine {
                 A.chunk_base = d_chunk_base.as<uint32_t>(); A.tile_first = d_tile_first.as<uint32_t>();
                 A.group = g;
                 A.entries = d_entries.as<uint64_t>(); A.n_entries = d_cnt; A.cap = entries_cap;
+                if (G.f_on && use_filter && !force_exact) {
+                    // pre-filter (both strands in one 32-bit word) + exact verification of the candidate and read-end windows
+                    const uint32_t win_cap = static_cast<uint32_t>(std::min<uint64_t>(total / 48 + (1u << 20), 1u << 30));
+                    BB_CUDA(d_windows.ensure(static_cast<size_t>(win_cap) * 8));
+                    BB_CUDA(cudaMemsetAsync(d_cnt + 6, 0, 4, st));          // [6] window count ([7] overflow flag is sticky per attempt)
+                    FilterArgs F{A, d_windows.as<uint64_t>(), d_cnt + 6, win_cap, d_cnt + 7};
+                    const int fw = ((G.f_q + G.k + kGroup - 1) / kGroup) * kGroup;
+                    const size_t smem = 128 + 1024 + kFiltQueue * sizeof(uint64_t) + static_cast<size_t>(kScanThreads) * kChunk + fw + 48;
+                    BB_CUDA(cudaFuncSetAttribute(k_flank_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+                    k_flank_filter<<<n_tiles, kScanThreads, smem, st>>>(F, G);
+                    VerifyArgs V{A, d_windows.as<uint64_t>(), d_cnt + 6};
+                    if (G.nw == 1) k_flank_verify<1><<<148 * 8, 128, 0, st>>>(V, G);
+                    else k_flank_verify<2><<<148 * 8, 128, 0, st>>>(V, G);
+                    launches += 2;
+                    filtered = true;
+                    BB_CUDA(cudaGetLastError());
+                    continue;
+                }
                 const size_t smem = 128 + 2 * 256 * G.nw * sizeof(uint64_t) + static_cast<size_t>(kScanThreads) * kChunk + 2 * static_cast<size_t>(G.warm) + 48;
                 if (G.nw == 1) {
                     BB_CUDA(cudaFuncSetAttribute(k_flank_scan<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
@@ -193,11 +215,15 @@ struct Engine {
                 launches++;
                 BB_CUDA(cudaGetLastError());
             }
+            any_filtered = filtered;
+            BB_CUDA(cudaMemcpyAsync(h_counters + 6, d_cnt + 6, 8, cudaMemcpyDeviceToHost, st));
             BB_CUDA(cudaMemcpyAsync(h_counters, d_cnt, 4, cudaMemcpyDeviceToHost, st));
             BB_CUDA(cudaStreamSynchronize(st));
             n_entries = h_counters[0];
+            last_windows = h_counters[6];
+            if (any_filtered && h_counters[7]) { force_exact = true; continue; }   // candidate queue overflow: exact scan instead
             if (n_entries <= entries_cap) break;
-            if (attempt == 3 || n_entries > (1u << 28)) { set_error("flank scan produced %u sub-threshold positions; batch too dense", n_entries); return BB_ERR_INVALID; }
+            if (attempt == 4 || n_entries > (1u << 28)) { set_error("flank scan produced %u sub-threshold positions; batch too dense", n_entries); return BB_ERR_INVALID; }
             entries_cap = static_cast<uint32_t>(std::min<uint64_t>(static_cast<uint64_t>(n_entries) + n_entries / 4, 1u << 28));
         }
         BB_CUDA(cudaEventRecord(ev[1], st));
@@ -212,6 +238,17 @@ struct Engine {
             cub::DeviceRadixSort::SortKeys(nullptr, tmp, d_entries.as<uint64_t>(), d_sorted.as<uint64_t>(), static_cast<int>(n_entries), kKeyPosShift, end_bit, st);
             BB_CUDA(d_cub.ensure(tmp));
             BB_CUDA(cub::DeviceRadixSort::SortKeys(d_cub.p, tmp, d_entries.as<uint64_t>(), d_sorted.as<uint64_t>(), static_cast<int>(n_entries), kKeyPosShift, end_bit, st));
+        }
+        if (any_filtered) {     // overlapping verification windows emit the same (position, cost) more than once
+            size_t tmp = 0;
+            uint64_t* uniq = d_entries.as<uint64_t>();     // the unsorted copy is no longer needed
+            cub::DeviceSelect::Unique(nullptr, tmp, d_sorted.as<uint64_t>(), uniq, d_cnt + 1, static_cast<int>(n_entries), st);
+            BB_CUDA(d_cub.ensure(tmp));
+            BB_CUDA(cub::DeviceSelect::Unique(d_cub.p, tmp, d_sorted.as<uint64_t>(), uniq, d_cnt + 1, static_cast<int>(n_entries), st));
+            BB_CUDA(cudaMemcpyAsync(h_counters + 1, d_cnt + 1, 4, cudaMemcpyDeviceToHost, st));
+            BB_CUDA(cudaStreamSynchronize(st));
+            n_entries = h_counters[1];
+            BB_CUDA(cudaMemcpyAsync(d_sorted.p, uniq, static_cast<size_t>(n_entries) * 8, cudaMemcpyDeviceToDevice, st));
         }
         BB_CUDA(d_flags.ensure(n_entries));
         k_resolve<<<(n_entries + 255) / 256, 256, 0, st>>>(d_sorted.as<uint64_t>(), n_entries, offsets, d_groups(), d_flags.as<uint8_t>());
@@ -394,6 +431,7 @@ int bb_create(const bb_opts* opts, bb_ctx** out, char* err, size_t errlen) {
         if (rc != BB_OK) { std::string m = c->eng[i].err; for (int j = 0; j <= i; j++) c->eng[j].destroy(); delete c; return fail(rc, m); }
         c->eng[i].gt = &c->gt;
         c->eng[i].prm.min_score = opts->min_score; c->eng[i].prm.min_score_diff = opts->min_score_diff;
+        c->eng[i].use_filter = (opts->flags & 1u) == 0;
     }
     *out = c;
     return BB_OK;
@@ -424,7 +462,7 @@ int bb_set_groups(bb_ctx* c, const bb_group* groups, int32_t n_groups) {
     const float alpha = c->opts.alpha;
     // blob layout per group: eq[2][256][nw] u64 | bar_eq[2][nb][16] u64 | ov[m+1] i32 (padded to 8)
     std::vector<uint64_t> blob;
-    std::vector<size_t> off_eq(n_groups), off_eqt(n_groups), off_bar(n_groups), off_ov(n_groups);
+    std::vector<size_t> off_eq(n_groups), off_eqt(n_groups), off_feq(n_groups), off_bar(n_groups), off_ov(n_groups);
     std::vector<DevGroup> hg(n_groups);
     int max_trace = 0, max_nw = 1, max_region = 0, max_bar_len = 0;
     for (int g = 0; g < n_groups; g++) {
@@ -489,6 +527,29 @@ int bb_set_groups(bb_ctx* c, const bb_group* groups, int32_t n_groups) {
                     for (int bpos = 0; bpos < shift; bpos++) dst[bpos >> 6] |= 1ull << (bpos & 63);
                 }
         }
+        // pre-filter: the longest N-free run of the flank, at most 15 rows; enabled when 3k <= rows (selective enough)
+        off_feq[g] = blob.size();
+        blob.resize(blob.size() + 128, 0);
+        {
+            int best0 = 0, bestn = 0, cur0 = 0, curn = 0;
+            for (int i = 0; i <= m; i++) {
+                if (i < m && pc[i] != 15 && pc[i] != 0) { if (!curn) cur0 = i; curn++; }
+                else { if (curn > bestn) { bestn = curn; best0 = cur0; } curn = 0; }
+            }
+            const int q = std::min(bestn, 15);
+            D.f_q = q; D.f_q0 = best0;
+            D.f_on = (q >= 8 && 3 * S.k_flank <= q) ? 1 : 0;
+            uint32_t* feq = reinterpret_cast<uint32_t*>(blob.data() + off_feq[g]);
+            for (int ch = 0; ch < 256 && q > 0; ch++) {
+                const uint8_t code = kAlpha.code[ch], ccode = Alphabet::comp(code);
+                uint32_t v = 0;
+                for (int r = 0; r < q; r++) {
+                    if (pc[best0 + r] & code) v |= 1u << r;                       // run, forward strand
+                    if (pc[best0 + q - 1 - r] & ccode) v |= 1u << (16 + r);       // reverse complement of the run
+                }
+                feq[ch] = v;
+            }
+        }
         off_bar[g] = blob.size();
         blob.resize(blob.size() + static_cast<size_t>(2) * S.n_barcodes * 16, 0);
         for (int b = 0; b < S.n_barcodes; b++)
@@ -514,6 +575,7 @@ int bb_set_groups(bb_ctx* c, const bb_group* groups, int32_t n_groups) {
     for (int g = 0; g < n_groups; g++) {
         hg[g].eq = base + off_eq[g];
         hg[g].eq_top = base + off_eqt[g];
+        hg[g].f_eq = reinterpret_cast<const uint32_t*>(base + off_feq[g]);
         hg[g].bar_eq = base + off_bar[g];
         hg[g].ov = reinterpret_cast<const int*>(base + off_ov[g]);
     }

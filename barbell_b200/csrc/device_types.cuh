@@ -33,7 +33,14 @@ struct DevGroup {
     const uint64_t* eq_top;              // same, top-aligned, wildcard rows below (used by the scan kernel)
     const int* ov;                       // [m+1] floor(t*alpha)
     const uint64_t* bar_eq;              // [2 strands][n_barcodes][16 codes]
+    // lossless pre-filter (0 = off): rows [f_q0, f_q0 + f_q) of the flank are an N-free run with f_q <= 15 and 3k <= f_q
+    int f_on, f_q, f_q0, f_pad;
+    const uint32_t* f_eq;                // [256] bits [0,q): the run; bits [16,16+q): its reverse complement (both vs the forward text)
 };
+
+// candidate window of the pre-filter / read-end window: end positions [lo, lo+len] of one strand's frame to verify exactly
+//   [63:40] read | [39] strand | [38:11] lo (28 bit) | [10:0] len
+constexpr int kWinReadShift = 40, kWinStrandShift = 39, kWinLoShift = 11;
 
 struct Params {
     double min_score, min_score_diff;

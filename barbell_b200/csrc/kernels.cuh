@@ -349,6 +349,233 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_flank_scan(const ScanArgs A
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// K1f/K1v: lossless pre-filter + exact window verification (used instead of k_flank_scan when DevGroup::f_on)
+//
+// If the flank matches with <= k edits ending at j, then its N-free run Q = rows [q0, q0+q) matches with e <= k edits
+// ending at some p, and the D = m-q0-q rows after Q are aligned to text (p, j] with <= k-e edits, so
+// |j - p - D| <= k - e.  K1f therefore runs ONLY the q <= 15 rows of Q for the forward strand and the q rows of rc(Q)
+// for the reverse-complement strand -- both blocks side by side in ONE 32-bit word, one ascending pass, ~19 ALU ops per
+// base for both strands -- and every position where a block's cost drops to <= k becomes a candidate WINDOW of end
+// positions that K1v verifies with the exact full-length bit-vector DP (same arithmetic as k_flank_scan, incl. warm-up
+// and overhang).  Matches that touch a read end may have Q itself hanging over the end (overhang cost alpha < 1 per row,
+// which the filter does not model), so the first and last m+k end positions of every read and strand (and the virtual
+// positions past the end) are ALWAYS verified.  Windows may overlap: duplicates are removed after the sort.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kFiltQueue = 2048;     // candidate windows a CTA can stage in shared memory
+
+struct FilterArgs {
+    ScanArgs S;
+    uint64_t* windows;           // global candidate queue
+    uint32_t* n_windows;
+    uint32_t win_cap;
+    uint32_t* overflow;          // set when a CTA queue or the global queue overflowed (host falls back to the exact scan)
+};
+
+__device__ __forceinline__ uint64_t make_window(uint32_t read, int strand, int lo, int len) {
+    return (static_cast<uint64_t>(read) << kWinReadShift) | (static_cast<uint64_t>(strand) << kWinStrandShift) |
+           (static_cast<uint64_t>(static_cast<uint32_t>(lo)) << kWinLoShift) | static_cast<uint64_t>(len);
+}
+
+__global__ void __launch_bounds__(kScanThreads, 2) k_flank_filter(const FilterArgs F, const DevGroup G) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const ScanArgs& A = F.S;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
+    int64_t* s_origin = reinterpret_cast<int64_t*>(smem + 16);
+    uint32_t* s_qn = reinterpret_cast<uint32_t*>(smem + 32);
+    uint32_t* s_qbase = reinterpret_cast<uint32_t*>(smem + 36);
+    uint32_t* s_eq = reinterpret_cast<uint32_t*>(smem + 128);                       // [256]
+    uint64_t* s_queue = reinterpret_cast<uint64_t*>(smem + 128 + 1024);             // [kFiltQueue]
+    unsigned char* s_text = smem + 128 + 1024 + kFiltQueue * sizeof(uint64_t);
+
+    const int tid = threadIdx.x;
+    const int q = G.f_q, k = G.k, m = G.m;
+    const int W = ((q + k + kGroup - 1) / kGroup) * kGroup;                         // warm-up columns of the filter
+    const uint32_t total_chunks = __ldg(A.chunk_base + A.n_reads);
+    const uint32_t c_first = blockIdx.x * kScanThreads;
+    if (c_first >= total_chunks) return;
+    const uint32_t r_first = __ldg(A.tile_first + blockIdx.x);
+
+    if (tid == 0) {
+        *s_qn = 0;
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const uint32_t c_last = min(c_first + kScanThreads, total_chunks) - 1;
+        const uint32_t r_last = find_chunk_read(A.chunk_base, A.n_reads, r_first, c_last);
+        const uint64_t g_lo = __ldg(A.offsets + r_first) + static_cast<uint64_t>(c_first - __ldg(A.chunk_base + r_first)) * kChunk;
+        uint64_t g_hi = __ldg(A.offsets + r_last) + static_cast<uint64_t>(c_last - __ldg(A.chunk_base + r_last) + 1) * kChunk;
+        const uint64_t r_end = __ldg(A.offsets + r_last + 1);
+        if (g_hi > r_end) g_hi = r_end;
+        uint64_t lo = g_lo >= static_cast<uint64_t>(W) ? g_lo - W : 0;
+        lo &= ~15ull;
+        uint64_t hi = (g_hi + 15) & ~15ull;
+        if (hi > A.total16) hi = A.total16;
+        *s_origin = static_cast<int64_t>(lo);
+        const uint32_t bytes = static_cast<uint32_t>(hi - lo);
+        mbar_expect_tx(bar, bytes);
+        tma_bulk_g2s(s_text, A.bases + lo, bytes, bar);
+    }
+    for (int i = tid; i < 256; i += kScanThreads) s_eq[i] = __ldg(G.f_eq + i);
+
+    const uint32_t c = c_first + tid;
+    const bool active = c < total_chunks;
+    uint32_t r = 0;
+    int n = 0, a = 0, b = 0;
+    uint64_t rs_g = 0;
+    if (active) {
+        r = find_chunk_read(A.chunk_base, A.n_reads, r_first, c);
+        rs_g = __ldg(A.offsets + r);
+        n = static_cast<int>(__ldg(A.offsets + r + 1) - rs_g);
+        a = static_cast<int>(c - __ldg(A.chunk_base + r)) * kChunk;
+        b = min(a + kChunk, n);
+    }
+    __syncthreads();
+    mbar_wait(bar, 0);
+    if (active) {
+        const unsigned char* text = s_text + (static_cast<int64_t>(rs_g) - *s_origin);
+        const uint32_t blk = (1u << q) - 1u;
+        const uint32_t keep = ~(1u << 16);                      // the upper block's row 0 gets no horizontal input
+        const uint32_t last2 = 0x00010001u;
+        const int sb = q - 1;
+        const uint32_t bias = (0x8000u - static_cast<uint32_t>(k + 1)) * 0x00010001u;
+        const uint32_t pvmask = blk | (blk << 16);
+        uint32_t pv = pvmask, mv = 0;
+        uint32_t packed = static_cast<uint32_t>(q) * 0x00010001u + bias;       // bit 15 / 31 set <=> the block's cost >= k+1
+        const int Df = m - (G.f_q0 + q);                         // flank rows after the run (forward strand)
+        const int Dr = m - G.f_q0;                               // rows of rc(flank) up to the end of rc(run)
+        // pending (merged) window per strand: consecutive candidates give overlapping windows
+        int f_lo = 1, f_hi = 0, r_lo = 1, r_hi = 0;
+        auto push = [&](int strand, int lo, int hi) {
+            const uint32_t idx = atomicAdd(s_qn, 1u);
+            if (idx < kFiltQueue) s_queue[idx] = make_window(r, strand, lo, hi - lo);
+        };
+        auto candidate = [&](int x) {                            // rare path: at least one block's cost is <= k after base x
+            const int p = x + 1;
+            const int cf = static_cast<int>((packed - bias) & 0xffffu), cr = static_cast<int>((packed - bias) >> 16);
+            if (cf <= k) {
+                // forward strand: the Df rows after the run are aligned to (p, j] with <= k - cf edits: j = p + Df +- (k - cf)
+                const int kk = k - cf;
+                const int lo = max(p + Df - kk, 1), hi = min(p + Df + kk, n);
+                if (lo <= hi) {
+                    if (f_lo <= f_hi && lo <= f_hi + 1 && hi + 1 >= f_lo) { f_lo = min(f_lo, lo); f_hi = max(f_hi, hi); }
+                    else { if (f_lo <= f_hi) push(BB_FWD, f_lo, f_hi); f_lo = lo; f_hi = hi; }
+                }
+            }
+            if (cr <= k) {
+                // rc strand: the match starts at s = p - Dr +- k (the run's own indels shift its end), frame position n - s
+                const int lo = max(n - (p - Dr + k), 1), hi = min(n - (p - Dr - k), n);
+                if (lo <= hi) {
+                    if (r_lo <= r_hi && lo <= r_hi + 1 && hi + 1 >= r_lo) { r_lo = min(r_lo, lo); r_hi = max(r_hi, hi); }
+                    else { if (r_lo <= r_hi) push(BB_RC, r_lo, r_hi); r_lo = lo; r_hi = hi; }
+                }
+            }
+        };
+#define BB_FSTEP(XX)                                                             \
+        {                                                                        \
+            const uint32_t e = s_eq[text[(XX)]];                                 \
+            const uint32_t sum = (e & pv) + pv;                                  \
+            uint32_t ph = mv | ~(sum | pv | e);                                  \
+            uint32_t mh = pv & ((sum ^ pv) | e);                                 \
+            packed += ((ph >> sb) & last2) - ((mh >> sb) & last2);               \
+            ph = (ph << 1) & keep; mh <<= 1;                                     \
+            pv = (mh | ~(e | mv | ph)) & pvmask;   /* spacer bits stay 0: no carry ripples from the lower block into the upper */ \
+            mv = ph & (e | mv);                                                  \
+            if ((packed & 0x80008000u) != 0x80008000u) { if ((XX) >= a) candidate(XX); } \
+        }
+#pragma unroll 1
+        for (int x0 = a - W; x0 < b; x0 += kGroup) {
+            if (x0 < 0) continue;                               // W and the chunk are multiples of kGroup: groups never straddle 0
+            if (x0 + kGroup <= b) {
+#pragma unroll
+                for (int t = 0; t < kGroup; t++) BB_FSTEP(x0 + t)
+            } else {
+#pragma unroll 1
+                for (int x = x0; x < b; x++) BB_FSTEP(x)
+            }
+        }
+#undef BB_FSTEP
+        if (f_lo <= f_hi) push(BB_FWD, f_lo, f_hi);
+        if (r_lo <= r_hi) push(BB_RC, r_lo, r_hi);
+    }
+    __syncthreads();
+    // flush the CTA queue with one global atomic
+    const uint32_t nq = *s_qn;
+    if (nq > kFiltQueue) { if (tid == 0) atomicExch(F.overflow, 1u); return; }
+    if (tid == 0) *s_qbase = nq ? atomicAdd(F.n_windows, nq) : 0u;
+    __syncthreads();
+    const uint32_t base = *s_qbase;
+    if (base + nq > F.win_cap) { if (tid == 0) atomicExch(F.overflow, 1u); return; }
+    for (uint32_t i = tid; i < nq; i += kScanThreads) F.windows[base + i] = s_queue[i];
+}
+
+// K1v: exact verification of windows; items [0, 4*n_reads) are the read-end windows, the rest come from the queue.
+struct VerifyArgs {
+    ScanArgs S;
+    const uint64_t* windows;
+    const uint32_t* n_windows;
+};
+
+template <int NW>
+__device__ void verify_window(const ScanArgs& A, const DevGroup& G, uint32_t r, int strand, int lo, int hi) {
+    const uint64_t rs_g = __ldg(A.offsets + r);
+    const int n = static_cast<int>(__ldg(A.offsets + r + 1) - rs_g);
+    const int m = G.m, k = G.k, shift = 64 * NW - G.m;
+    if (lo > hi) return;
+    const uint8_t* text = A.bases + rs_g;
+    const uint64_t* eq = G.eq_top + static_cast<size_t>(strand) * 256 * NW;
+    // frame character c of this strand: forward text[c] / reverse-complement text[n-1-c] (masks are complemented)
+    const int c_end = min(hi, n);                               // characters [c0, c_end) are consumed
+    int c0 = max(lo, 1) - 1 - G.warm;
+    const bool fresh = c0 > 0;
+    if (c0 < 0) c0 = 0;
+    Col<NW> col;
+#pragma unroll
+    for (int w = 0; w < NW; w++) { col.pv[w] = fresh ? G.pv_plain_top[w] : G.pv_over_top[w]; col.mv[w] = 0; }
+    int score = fresh ? m : G.ov_m;
+    if (lo == 0 && score <= k) scan_emit(A, r, strand, 0u, score);
+    for (int c = c0; c < c_end; c++) {
+        const uint32_t ch = strand == BB_FWD ? text[c] : text[n - 1 - c];
+        uint64_t e[NW];
+#pragma unroll
+        for (int w = 0; w < NW; w++) e[w] = __ldg(eq + ch * NW + w);
+        score += col_step_top<NW>(col, e);
+        if (score <= k && c + 1 >= lo) scan_emit(A, r, strand, static_cast<uint32_t>(c + 1), score);
+    }
+    if (hi > n && c_end == n) {                                  // virtual end positions past the text end (oracle policy S3)
+        const int tmax = min(hi - n, m);
+        for (int t = 1; t <= tmax; t++) {
+            const int v = col_val<NW>(col.pv, col.mv, shift + m - t) + __ldg(G.ov + t);
+            if (v <= k) scan_emit(A, r, strand, static_cast<uint32_t>(n + t), v);
+        }
+    }
+}
+
+template <int NW>
+__global__ void __launch_bounds__(128) k_flank_verify(const VerifyArgs V, const DevGroup G) {
+    const ScanArgs& A = V.S;
+    const uint64_t n_end = 4ull * A.n_reads;
+    const uint64_t total = n_end + __ldg(V.n_windows);
+    const int span = G.m + G.k;
+    for (uint64_t it = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; it < total; it += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+        if (it < n_end) {
+            const uint32_t r = static_cast<uint32_t>(it >> 2);
+            const int strand = static_cast<int>((it >> 1) & 1), which = static_cast<int>(it & 1);
+            const int n = static_cast<int>(__ldg(A.offsets + r + 1) - __ldg(A.offsets + r));
+            if (n == 0) continue;
+            // head: end positions [0, m+k]; tail: [n-m-k, n+m]; one window when they touch
+            const bool joined = n - span <= span + 1;
+            if (which == 0) verify_window<NW>(A, G, r, strand, 0, joined ? n + G.m : span);
+            else if (!joined) verify_window<NW>(A, G, r, strand, n - span, n + G.m);
+        } else {
+            const uint64_t w = V.windows[it - n_end];
+            const uint32_t r = static_cast<uint32_t>(w >> kWinReadShift);
+            const int strand = static_cast<int>((w >> kWinStrandShift) & 1);
+            const int lo = static_cast<int>((w >> kWinLoShift) & ((1u << 28) - 1)), len = static_cast<int>(w & ((1u << kWinLoShift) - 1));
+            verify_window<NW>(A, G, r, strand, lo, lo + len);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // K2a: local-minimum rule on the sorted entries (oracle policy S1)
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void k_resolve(const uint64_t* __restrict__ keys, uint32_t n, const uint64_t* __restrict__ offsets,

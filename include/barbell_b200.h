@@ -72,7 +72,7 @@ typedef struct {
     double  min_score_diff;     /* --min-score-diff, bin/main.rs:102-105 (default 0.1) */
     uint64_t max_batch_bytes;   /* capacity of the staging buffers for bb_annotate (0 = 256 MiB) */
     uint32_t max_batch_reads;   /* (0 = 4 Mi reads) */
-    uint32_t flags;             /* reserved, 0 */
+    uint32_t flags;             /* bit 0: disable the lossless pre-filter (exact full-length scan everywhere); else 0 */
 } bb_opts;
 
 typedef struct bb_ctx bb_ctx;

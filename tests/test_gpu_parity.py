@@ -18,12 +18,16 @@ def _annotator(gs, **kw):
 
 
 def _check(gs, bases, offsets, **kw):
-    an = _annotator(gs, **kw)
-    try:
-        rows = an.annotate(bases, offsets)
-        hits = an.flank_hits()
-    finally:
-        an.close()
+    """Both scan paths (lossless pre-filter + window verification, and the exact full-length scan) against the oracle."""
+    out = []
+    for use_filter in (True, False):
+        an = _annotator(gs, use_filter=use_filter, **kw)
+        try:
+            out.append((an.annotate(bases, offsets), an.flank_hits()))
+        finally:
+            an.close()
+    assert out[0][0].tobytes() == out[1][0].tobytes(), "pre-filter path differs from the exact scan"
+    rows, hits = out[0]
     G = gs.as_dicts()
     want = O.demux_batch(G, bases, offsets, alpha=kw.get("alpha", 0.4), min_score=kw.get("min_score", 0.2),
                          min_score_diff=kw.get("min_score_diff", 0.1))
@@ -215,3 +219,14 @@ def test_cli_fastq_to_annotation_tsv(tmp_path):
     # unknown kit: message, exit code 0 (reference bin/main.rs:301-304), empty/no output
     r = subprocess.run([exe, "annotate", "--kit", "SQK-NOPE", "-i", str(fq1), "-o", str(tmp_path / "x.tsv")], capture_output=True, text=True)
     assert r.returncode == 0 and "Error during processing" in r.stdout
+
+
+def test_prefilter_queue_overflow_falls_back_to_exact_scan():
+    """A read of N (matches everything) makes every position a filter candidate: the CTA queue overflows and the batch is
+    re-run with the exact scan; the result must still equal the oracle."""
+    gs = bb.GroupSet.from_kit("SQK-NBD114-96")
+    b, o, _ = synth.make_reads(gs.as_dicts(), 40, (500, 3000), seed=31)
+    junk = np.frombuffer(b"N" * 6000 + b"ATTGCTAAGGTTAA" * 300, np.uint8)
+    bases = np.concatenate([b, junk])
+    offsets = np.concatenate([o, [o[-1] + 6000, o[-1] + len(junk)]]).astype(np.uint64)
+    _check(gs, bases, offsets)
