@@ -193,7 +193,7 @@ struct Engine {
                     BB_CUDA(cudaMemsetAsync(d_cnt + 6, 0, 4, st));          // [6] window count ([7] overflow flag is sticky per attempt)
                     FilterArgs F{A, d_windows.as<uint64_t>(), d_cnt + 6, win_cap, d_cnt + 7};
                     const int fw = ((G.f_q + G.k + kGroup - 1) / kGroup) * kGroup;
-                    const size_t smem = 128 + 1024 + kFiltQueue * sizeof(uint64_t) + static_cast<size_t>(kScanThreads) * kChunk + fw + 48;
+                    const size_t smem = filter_smem_bytes(fw);
                     BB_CUDA(cudaFuncSetAttribute(k_flank_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
                     k_flank_filter<<<n_tiles, kScanThreads, smem, st>>>(F, G);
                     VerifyArgs V{A, d_windows.as<uint64_t>(), d_cnt + 6};

@@ -127,7 +127,7 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gme
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kScanThreads = 256;
 constexpr int kGroup = 20;           // characters per unrolled group; chunk and warm-up are multiples of it
-constexpr int kChunk = 340;          // bases per lane: 17 groups; 340/4 = 85 is odd (LDS.U8 of a warp is conflict-free)
+constexpr int kChunk = 300;          // bases per lane: 15 groups; 300/4 = 75 is odd (LDS.U8 of a warp is conflict-free)
 
 struct ScanArgs {
     const uint8_t* bases;        // concatenated read bytes, 16-byte aligned
@@ -361,7 +361,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_flank_scan(const ScanArgs A
 // which the filter does not model), so the first and last m+k end positions of every read and strand (and the virtual
 // positions past the end) are ALWAYS verified.  Windows may overlap: duplicates are removed after the sort.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int kFiltQueue = 2048;     // candidate windows a CTA can stage in shared memory
+constexpr int kFiltQueue = 1024;     // candidate windows a CTA can stage in shared memory
 
 struct FilterArgs {
     ScanArgs S;
@@ -376,6 +376,18 @@ __device__ __forceinline__ uint64_t make_window(uint32_t read, int strand, int l
            (static_cast<uint64_t>(static_cast<uint32_t>(lo)) << kWinLoShift) | static_cast<uint64_t>(len);
 }
 
+constexpr int kFiltGroups = kChunk / kGroup;     // candidate-bitmap groups per chunk (17)
+
+// Shared memory of k_flank_filter for a filter warm-up of `fw` columns.
+__host__ __device__ inline size_t filter_smem_bytes(int fw) {
+    return 128 + 1024 + kFiltQueue * sizeof(uint64_t) + static_cast<size_t>(kFiltGroups) * kScanThreads * 5 +
+           static_cast<size_t>(kScanThreads) * kChunk + fw + 48;
+}
+
+// The scan loop is branch-free: per base it advances both 15-row blocks (one 32-bit word), updates the two packed
+// costs and shifts the two "cost > k" flags into per-strand bit registers; after every group of 20 bases the 2 x 20
+// flags go to a per-lane bitmap in shared memory.  Only after the whole chunk is scanned does the lane turn its bitmap
+// into runs of candidate positions and the runs into windows (CTA queue in shared memory, ONE global atomic per CTA).
 __global__ void __launch_bounds__(kScanThreads, 2) k_flank_filter(const FilterArgs F, const DevGroup G) {
     extern __shared__ __align__(128) unsigned char smem[];
     const ScanArgs& A = F.S;
@@ -385,7 +397,9 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_flank_filter(const FilterAr
     uint32_t* s_qbase = reinterpret_cast<uint32_t*>(smem + 36);
     uint32_t* s_eq = reinterpret_cast<uint32_t*>(smem + 128);                       // [256]
     uint64_t* s_queue = reinterpret_cast<uint64_t*>(smem + 128 + 1024);             // [kFiltQueue]
-    unsigned char* s_text = smem + 128 + 1024 + kFiltQueue * sizeof(uint64_t);
+    uint32_t* s_bm32 = reinterpret_cast<uint32_t*>(smem + 128 + 1024 + kFiltQueue * sizeof(uint64_t));   // [group][lane]
+    uint8_t* s_bm8 = reinterpret_cast<uint8_t*>(s_bm32 + kFiltGroups * kScanThreads);                     // [group][lane]
+    unsigned char* s_text = s_bm8 + kFiltGroups * kScanThreads;
 
     const int tid = threadIdx.x;
     const int q = G.f_q, k = G.k, m = G.m;
@@ -440,35 +454,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_flank_filter(const FilterAr
         const uint32_t pvmask = blk | (blk << 16);
         uint32_t pv = pvmask, mv = 0;
         uint32_t packed = static_cast<uint32_t>(q) * 0x00010001u + bias;       // bit 15 / 31 set <=> the block's cost >= k+1
-        const int Df = m - (G.f_q0 + q);                         // flank rows after the run (forward strand)
-        const int Dr = m - G.f_q0;                               // rows of rc(flank) up to the end of rc(run)
-        // pending (merged) window per strand: consecutive candidates give overlapping windows
-        int f_lo = 1, f_hi = 0, r_lo = 1, r_hi = 0;
-        auto push = [&](int strand, int lo, int hi) {
-            const uint32_t idx = atomicAdd(s_qn, 1u);
-            if (idx < kFiltQueue) s_queue[idx] = make_window(r, strand, lo, hi - lo);
-        };
-        auto candidate = [&](int x) {                            // rare path: at least one block's cost is <= k after base x
-            const int p = x + 1;
-            const int cf = static_cast<int>((packed - bias) & 0xffffu), cr = static_cast<int>((packed - bias) >> 16);
-            if (cf <= k) {
-                // forward strand: the Df rows after the run are aligned to (p, j] with <= k - cf edits: j = p + Df +- (k - cf)
-                const int kk = k - cf;
-                const int lo = max(p + Df - kk, 1), hi = min(p + Df + kk, n);
-                if (lo <= hi) {
-                    if (f_lo <= f_hi && lo <= f_hi + 1 && hi + 1 >= f_lo) { f_lo = min(f_lo, lo); f_hi = max(f_hi, hi); }
-                    else { if (f_lo <= f_hi) push(BB_FWD, f_lo, f_hi); f_lo = lo; f_hi = hi; }
-                }
-            }
-            if (cr <= k) {
-                // rc strand: the match starts at s = p - Dr +- k (the run's own indels shift its end), frame position n - s
-                const int lo = max(n - (p - Dr + k), 1), hi = min(n - (p - Dr - k), n);
-                if (lo <= hi) {
-                    if (r_lo <= r_hi && lo <= r_hi + 1 && hi + 1 >= r_lo) { r_lo = min(r_lo, lo); r_hi = max(r_hi, hi); }
-                    else { if (r_lo <= r_hi) push(BB_RC, r_lo, r_hi); r_lo = lo; r_hi = hi; }
-                }
-            }
-        };
+        uint32_t fm = ~0u, rm = ~0u;                             // per base: 1 = "cost > k" (forward block / rc block)
 #define BB_FSTEP(XX)                                                             \
         {                                                                        \
             const uint32_t e = s_eq[text[(XX)]];                                 \
@@ -479,7 +465,8 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_flank_filter(const FilterAr
             ph = (ph << 1) & keep; mh <<= 1;                                     \
             pv = (mh | ~(e | mv | ph)) & pvmask;   /* spacer bits stay 0: no carry ripples from the lower block into the upper */ \
             mv = ph & (e | mv);                                                  \
-            if ((packed & 0x80008000u) != 0x80008000u) { if ((XX) >= a) candidate(XX); } \
+            rm = __funnelshift_l(packed, rm, 1);                                 \
+            fm = __funnelshift_l(packed << 16, fm, 1);                           \
         }
 #pragma unroll 1
         for (int x0 = a - W; x0 < b; x0 += kGroup) {
@@ -490,11 +477,53 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_flank_filter(const FilterAr
             } else {
 #pragma unroll 1
                 for (int x = x0; x < b; x++) BB_FSTEP(x)
+                const int missing = x0 + kGroup - b;            // pad the partial group with "no candidate" flags
+                fm = (fm << missing) | ((1u << missing) - 1u); rm = (rm << missing) | ((1u << missing) - 1u);
+            }
+            if (x0 >= a) {                                      // bit 19-t of the group's masks = base x0+t is a candidate
+                const uint32_t cf = ~fm & 0xfffffu, cr = ~rm & 0xfffffu;
+                const int gi = (x0 - a) / kGroup;
+                s_bm32[gi * kScanThreads + tid] = cf | (cr << 20);
+                s_bm8[gi * kScanThreads + tid] = static_cast<uint8_t>(cr >> 12);
             }
         }
 #undef BB_FSTEP
-        if (f_lo <= f_hi) push(BB_FWD, f_lo, f_hi);
-        if (r_lo <= r_hi) push(BB_RC, r_lo, r_hi);
+        // ---- candidate runs -> windows (windows are linear in p because the half-width is the full k for both strands):
+        //   forward: the Df rows after the run are aligned to (p, j] with <= k edits        -> j  in [ps + Df - k, pe + Df + k]
+        //   rc     : the match starts at s = p - Dr +- k (the run's own indels shift its end) -> n-s in [n - pe + Dr - k, n - ps + Dr + k]
+        const int Df = m - (G.f_q0 + q);                         // flank rows after the run (forward strand)
+        const int Dr = m - G.f_q0;                               // rows of rc(flank) up to the end of rc(run)
+        auto push = [&](int strand, int lo, int hi) {
+            lo = max(lo, 1); hi = min(hi, n);
+            if (lo > hi) return;
+            const uint32_t idx = atomicAdd(s_qn, 1u);
+            if (idx < kFiltQueue) s_queue[idx] = make_window(r, strand, lo, hi - lo);
+        };
+        const int ng = (b - a + kGroup - 1) / kGroup;
+        int f_s = 0, f_e = -2, r_s = 0, r_e = -2;               // run start / last position per strand (empty: e = -2)
+#pragma unroll 1
+        for (int gi = 0; gi < ng; gi++) {
+            const uint32_t w32 = s_bm32[gi * kScanThreads + tid];
+            const uint32_t w8 = s_bm8[gi * kScanThreads + tid];
+            uint32_t cf = w32 & 0xfffffu, cr = (w32 >> 20) | (w8 << 12);
+            const int p0 = a + gi * kGroup + 1;                  // position after the group's first base
+            while (cf) {
+                const int t = 19 - (31 - __clz(cf));             // candidates in ascending position: highest bit first
+                cf &= ~(1u << (19 - t));
+                const int p = p0 + t;
+                if (p != f_e + 1) { if (f_e >= 0) push(BB_FWD, f_s + Df - k, f_e + Df + k); f_s = p; }
+                f_e = p;
+            }
+            while (cr) {
+                const int t = 19 - (31 - __clz(cr));
+                cr &= ~(1u << (19 - t));
+                const int p = p0 + t;
+                if (p != r_e + 1) { if (r_e >= 0) push(BB_RC, n - r_e + Dr - k, n - r_s + Dr + k); r_s = p; }
+                r_e = p;
+            }
+        }
+        if (f_e >= 0) push(BB_FWD, f_s + Df - k, f_e + Df + k);
+        if (r_e >= 0) push(BB_RC, n - r_e + Dr - k, n - r_s + Dr + k);
     }
     __syncthreads();
     // flush the CTA queue with one global atomic
@@ -515,13 +544,13 @@ struct VerifyArgs {
 };
 
 template <int NW>
-__device__ void verify_window(const ScanArgs& A, const DevGroup& G, uint32_t r, int strand, int lo, int hi) {
+__device__ void verify_window(const ScanArgs& A, const DevGroup& G, const uint64_t* __restrict__ s_eq, uint32_t r, int strand, int lo, int hi) {
     const uint64_t rs_g = __ldg(A.offsets + r);
     const int n = static_cast<int>(__ldg(A.offsets + r + 1) - rs_g);
     const int m = G.m, k = G.k, shift = 64 * NW - G.m;
     if (lo > hi) return;
     const uint8_t* text = A.bases + rs_g;
-    const uint64_t* eq = G.eq_top + static_cast<size_t>(strand) * 256 * NW;
+    const uint64_t* eq = s_eq + static_cast<size_t>(strand) * 256 * NW;
     // frame character c of this strand: forward text[c] / reverse-complement text[n-1-c] (masks are complemented)
     const int c_end = min(hi, n);                               // characters [c0, c_end) are consumed
     int c0 = max(lo, 1) - 1 - G.warm;
@@ -532,12 +561,12 @@ __device__ void verify_window(const ScanArgs& A, const DevGroup& G, uint32_t r, 
     for (int w = 0; w < NW; w++) { col.pv[w] = fresh ? G.pv_plain_top[w] : G.pv_over_top[w]; col.mv[w] = 0; }
     int score = fresh ? m : G.ov_m;
     if (lo == 0 && score <= k) scan_emit(A, r, strand, 0u, score);
+    const int64_t base = strand == BB_FWD ? 0 : static_cast<int64_t>(n) - 1, step = strand == BB_FWD ? 1 : -1;
+    uint32_t ch_next = c0 < c_end ? __ldg(text + base + step * c0) : 0u;
     for (int c = c0; c < c_end; c++) {
-        const uint32_t ch = strand == BB_FWD ? text[c] : text[n - 1 - c];
-        uint64_t e[NW];
-#pragma unroll
-        for (int w = 0; w < NW; w++) e[w] = __ldg(eq + ch * NW + w);
-        score += col_step_top<NW>(col, e);
+        const uint32_t ch = ch_next;
+        if (c + 1 < c_end) ch_next = __ldg(text + base + step * (c + 1));
+        score += col_step_top<NW>(col, eq + ch * NW);
         if (score <= k && c + 1 >= lo) scan_emit(A, r, strand, static_cast<uint32_t>(c + 1), score);
     }
     if (hi > n && c_end == n) {                                  // virtual end positions past the text end (oracle policy S3)
@@ -551,6 +580,9 @@ __device__ void verify_window(const ScanArgs& A, const DevGroup& G, uint32_t r, 
 
 template <int NW>
 __global__ void __launch_bounds__(128) k_flank_verify(const VerifyArgs V, const DevGroup G) {
+    __shared__ uint64_t s_eq[2 * 256 * NW];
+    for (int i = threadIdx.x; i < 2 * 256 * NW; i += blockDim.x) s_eq[i] = __ldg(G.eq_top + i);
+    __syncthreads();
     const ScanArgs& A = V.S;
     const uint64_t n_end = 4ull * A.n_reads;
     const uint64_t total = n_end + __ldg(V.n_windows);
@@ -563,14 +595,14 @@ __global__ void __launch_bounds__(128) k_flank_verify(const VerifyArgs V, const 
             if (n == 0) continue;
             // head: end positions [0, m+k]; tail: [n-m-k, n+m]; one window when they touch
             const bool joined = n - span <= span + 1;
-            if (which == 0) verify_window<NW>(A, G, r, strand, 0, joined ? n + G.m : span);
-            else if (!joined) verify_window<NW>(A, G, r, strand, n - span, n + G.m);
+            if (which == 0) verify_window<NW>(A, G, s_eq, r, strand, 0, joined ? n + G.m : span);
+            else if (!joined) verify_window<NW>(A, G, s_eq, r, strand, n - span, n + G.m);
         } else {
             const uint64_t w = V.windows[it - n_end];
             const uint32_t r = static_cast<uint32_t>(w >> kWinReadShift);
             const int strand = static_cast<int>((w >> kWinStrandShift) & 1);
             const int lo = static_cast<int>((w >> kWinLoShift) & ((1u << 28) - 1)), len = static_cast<int>(w & ((1u << kWinLoShift) - 1));
-            verify_window<NW>(A, G, r, strand, lo, lo + len);
+            verify_window<NW>(A, G, s_eq, r, strand, lo, lo + len);
         }
     }
 }
