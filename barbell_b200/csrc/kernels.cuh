@@ -794,8 +794,8 @@ struct TopTwo {
 // low halves share one 32-bit word; 16 bytes otherwise), its 16 match masks, one traceback record per column, and the
 // region's base codes.
 __host__ __device__ inline size_t barcode_warp_bytes(int cols, bool packed) {
-    const size_t c = static_cast<size_t>(cols) + 1;
-    return c * 32 * (packed ? 12 : 16) + 16 * 32 * sizeof(uint64_t) + ((c * 32 + 15) & ~static_cast<size_t>(15)) + kCodesPad;
+    const size_t c = static_cast<size_t>(cols) + 1, ch = c / 2 + 1;      // only the even columns are kept
+    return ch * 32 * (packed ? 12 : 16) + 16 * 32 * sizeof(uint64_t) + ((c * 32 + 15) & ~static_cast<size_t>(15)) + kCodesPad;
 }
 __host__ __device__ inline size_t barcode_smem_bytes(int cols, bool packed) { return kBarWarps * barcode_warp_bytes(cols, packed); }
 
@@ -846,7 +846,7 @@ __global__ void __launch_bounds__(kBarWarps * 32) k_barcode(const BarArgs A) {
     unsigned char* wbase = bar_smem + static_cast<size_t>(wib) * barcode_warp_bytes(A.hist_cols, PACKED);
     uint64_t* eqs_s = reinterpret_cast<uint64_t*>(wbase);                    // [16 codes][32 lanes]
     const ColHist<PACKED> hist{reinterpret_cast<uint32_t*>(eqs_s + 16 * 32), lane};
-    uint8_t* rec = wbase + 16 * 32 * sizeof(uint64_t) + ncol * 32 * (PACKED ? 12 : 16);   // [column][lane]
+    uint8_t* rec = wbase + 16 * 32 * sizeof(uint64_t) + (ncol / 2 + 1) * 32 * (PACKED ? 12 : 16);   // [column][lane]
     uint8_t* codes = rec + ((ncol * 32 + 15) & ~static_cast<size_t>(15));
     const uint32_t n_warps = gridDim.x * kBarWarps;
     for (uint32_t h = blockIdx.x * kBarWarps + wib; h < A.n_hits; h += n_warps) {
@@ -888,7 +888,7 @@ __global__ void __launch_bounds__(kBarWarps * 32) k_barcode(const BarArgs A) {
                     const uint64_t e = e_next;
                     if (p < rn) e_next = eq[codes[p] * 32];
                     const int cur = prev + col_step_top<1>(col, &e);
-                    hist.store(p, col.pv[0], col.mv[0]);
+                    if ((p & 1) == 0) hist.store(p >> 1, col.pv[0], col.mv[0]);       // even columns only; odd ones are re-derived
                     if (cur > prev && dec && prev < cbest) { cbest = prev; jend = p - 1; }
                     if (cur < prev) dec = 1; else if (cur > prev) dec = 0;
                     prev = cur;
@@ -903,7 +903,14 @@ __global__ void __launch_bounds__(kBarWarps * 32) k_barcode(const BarArgs A) {
                 uint64_t n_e = 0, n_diag = 0, n_stop = 0;
                 auto prepare = [&](int jj) {                    // pair (jj-1, jj), jj >= 1
                     uint64_t pvp, mvp;
-                    hist.load(jj - 1, pvp, mvp);
+                    const int jp = jj - 1;
+                    hist.load(jp >> 1, pvp, mvp);               // even column at or below jj-1
+                    {                                           // odd jj-1: one column step from the stored even column (branch-free)
+                        Col<1> c2; c2.pv[0] = pvp; c2.mv[0] = mvp;
+                        const uint64_t e2 = eq[codes[jp > 0 ? jp - 1 : 0] * 32];
+                        col_step_top<1>(c2, &e2);
+                        if (jp & 1) { pvp = c2.pv[0]; mvp = c2.mv[0]; }
+                    }
                     const uint64_t e = eq[codes[jj - 1] * 32];
                     const uint64_t sum = (e & pvp) + pvp;
                     const uint64_t ph = mvp | ~(sum | pvp | e), mh = pvp & ((sum ^ pvp) | e);   // deltas between columns jj-1 and jj
