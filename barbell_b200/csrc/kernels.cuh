@@ -553,7 +553,7 @@ __device__ void verify_window(const ScanArgs& A, const DevGroup& G, const uint64
     const uint64_t* eq = s_eq + static_cast<size_t>(strand) * 256 * NW;
     // frame character c of this strand: forward text[c] / reverse-complement text[n-1-c] (masks are complemented)
     const int c_end = min(hi, n);                               // characters [c0, c_end) are consumed
-    int c0 = max(lo, 1) - 1 - G.warm;
+    int c0 = max(lo, 1) - 1 - (m + k);                         // the cost at j depends on text[j-(m+k), j) only
     const bool fresh = c0 > 0;
     if (c0 < 0) c0 = 0;
     Col<NW> col;
