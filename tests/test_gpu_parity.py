@@ -230,3 +230,24 @@ def test_prefilter_queue_overflow_falls_back_to_exact_scan():
     bases = np.concatenate([b, junk])
     offsets = np.concatenate([o, [o[-1] + 6000, o[-1] + len(junk)]]).astype(np.uint64)
     _check(gs, bases, offsets)
+
+
+def test_long_barcodes_unpacked_history_and_odd_counts():
+    """Custom panel with 40-base barcodes (padded patterns of 60 rows: the 16-byte column history of k_barcode), 37 barcodes
+    (not a multiple of 32), one-sided short flanks, mixed with an exact-scan-only group."""
+    rnd = np.random.default_rng(33)
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    pre, suf = b"GGTCTAGACCATGCTAGGAT", b"TTGACCGATTCAGGCATCAA"
+    seqs = []
+    for i in range(37):
+        core = bytes(rnd.choice(acgt, 40))
+        core = b"ACGT"[i % 4:i % 4 + 1] + core[1:-1] + b"ACGT"[(i // 4) % 4:(i // 4) % 4 + 1]
+        seqs.append(pre + core + suf)
+    short = [b"ACGTTGCA" + bytes(rnd.choice(acgt, 12)) + b"GT" for _ in range(5)]
+    short = [s[:8] + b"ACGT"[i % 4:i % 4 + 1] + s[9:19] + b"ACGT"[(i + 1) % 4:(i + 1) % 4 + 1] + s[20:] for i, s in enumerate(short)]
+    gs = bb.GroupSet.from_seqs([(seqs, [f"X{i}" for i in range(37)], api.FTAG), (short, [f"S{i}" for i in range(5)], api.RTAG)])
+    G = gs.as_dicts()
+    assert G[0]["bar_len"] == 60 and len(G[0]["barcodes"]) == 37
+    b, o, _ = synth.make_reads(G, 300, (150, 1500), seed=34)
+    rows = _check(gs, b, o)
+    assert (rows["match_type"] < 2).sum() > 50
