@@ -11,8 +11,12 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
+#include <condition_variable>
 #include <deque>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../../include/barbell_b200.h"
@@ -47,7 +51,7 @@ Args parse(int argc, char** argv) {
     if (argc < 2) usage(nullptr);
     a.cmd = argv[1];
     if (a.cmd == "-h" || a.cmd == "--help") usage(nullptr);
-    if (a.cmd != "annotate" && a.cmd != "kit") usage("only the `annotate` and `kit` subcommands exist in this build");
+    if (a.cmd != "annotate" && a.cmd != "kit" && a.cmd != "fastq-stats") usage("only the `annotate` and `kit` subcommands exist in this build");
     bool types_given = false;
     for (int i = 2; i < argc; i++) {
         std::string f = argv[i];
@@ -76,56 +80,76 @@ Args parse(int argc, char** argv) {
     return a;
 }
 
-// FASTQ(.gz) reader over several files (reference io.rs:27-32: one paraseq Collection over all paths)
+// FASTQ(.gz) reader over several files (reference io.rs:27-32: one paraseq Collection over all paths).  Records are
+// parsed in place from a large read buffer (memchr per line) and handed out as views; the caller copies the bases
+// straight into the page-locked batch buffer, so every base is copied exactly once on the host.
 class FastqReader {
   public:
-    explicit FastqReader(std::vector<std::string> paths) : paths_(std::move(paths)) {}
+    explicit FastqReader(std::vector<std::string> paths) : paths_(std::move(paths)), buf_(kBuf) {}
     ~FastqReader() { if (gz_) gzclose(gz_); }
-    // next record: header (without '@'), sequence; false at the end of the last file
-    bool next(std::string& header, std::string& seq, std::string& err) {
+    struct View { const char* id; size_t id_len; const char* seq; size_t seq_len; };
+    // next record; false at the end of the last file or on error (err non-empty)
+    bool next(View& v, std::string& err) {
         for (;;) {
             if (!gz_) {
                 if (file_ >= paths_.size()) return false;
                 gz_ = gzopen(paths_[file_].c_str(), "rb");
                 if (!gz_) { err = "Failed to open FASTQ input: " + paths_[file_]; return false; }
                 gzbuffer(gz_, 1 << 20);
-                pos_ = len_ = 0;
+                pos_ = len_ = 0; eof_ = false;
             }
-            if (!line(header)) { gzclose(gz_); gz_ = nullptr; file_++; continue; }
-            if (header.empty()) continue;
-            if (header[0] != '@') { err = "malformed FASTQ record in " + paths_[file_]; return false; }
-            header.erase(0, 1);
-            std::string plus, qual;
-            if (!line(seq) || !line(plus) || !line(qual)) { err = "truncated FASTQ record in " + paths_[file_]; return false; }
-            return true;
+            size_t p = pos_;
+            const char *l0, *l1, *l2, *l3; size_t n0, n1, n2, n3;
+            if (line(p, l0, n0) && line(p, l1, n1) && line(p, l2, n2) && line(p, l3, n3)) {
+                pos_ = p;
+                if (n0 == 0 && n1 == 0) continue;                 // blank lines between records
+                if (l0[0] != '@' || n2 == 0 || l2[0] != '+') { err = "malformed FASTQ record in " + paths_[file_]; return false; }
+                if (n3 != n1) { err = "truncated FASTQ record (quality length differs from sequence length) in " + paths_[file_]; return false; }
+                (void)l3;
+                size_t idl = 0;                                    // split_fastq_header, io.rs:5-16: id = header up to whitespace
+                while (idl < n0 - 1 && l0[1 + idl] != ' ' && l0[1 + idl] != '\t') idl++;
+                v.id = l0 + 1; v.id_len = idl; v.seq = l1; v.seq_len = n1;
+                return true;
+            }
+            // incomplete record in the buffer: compact and refill
+            if (eof_) {
+                bool only_ws = true;
+                for (size_t i = pos_; i < len_; i++) if (buf_[i] != '\n' && buf_[i] != '\r') { only_ws = false; break; }
+                if (!only_ws) {
+                    // last record without a trailing newline: terminate it and parse once more
+                    if (len_ < buf_.size() && !patched_) { buf_[len_++] = '\n'; patched_ = true; continue; }
+                    err = "truncated FASTQ record in " + paths_[file_]; return false;
+                }
+                gzclose(gz_); gz_ = nullptr; file_++; patched_ = false;
+                continue;
+            }
+            if (pos_ > 0) { std::memmove(buf_.data(), buf_.data() + pos_, len_ - pos_); len_ -= pos_; pos_ = 0; }
+            if (len_ + 1 >= buf_.size()) buf_.resize(buf_.size() * 2);       // a single record longer than the buffer
+            const int n = gzread(gz_, buf_.data() + len_, static_cast<unsigned>(std::min<size_t>(buf_.size() - 1 - len_, 1u << 30)));
+            if (n < 0) { err = "read error in " + paths_[file_]; return false; }
+            if (n == 0) eof_ = true;
+            len_ += static_cast<size_t>(n);
         }
     }
 
   private:
-    bool line(std::string& out) {
-        out.clear();
-        for (;;) {
-            if (pos_ == len_) {
-                const int n = gzread(gz_, buf_, sizeof buf_);
-                if (n <= 0) return !out.empty();
-                pos_ = 0; len_ = static_cast<size_t>(n);
-            }
-            const char* p = static_cast<const char*>(std::memchr(buf_ + pos_, '\n', len_ - pos_));
-            if (p) {
-                out.append(buf_ + pos_, p - (buf_ + pos_));
-                pos_ = static_cast<size_t>(p - buf_) + 1;
-                if (!out.empty() && out.back() == '\r') out.pop_back();
-                return true;
-            }
-            out.append(buf_ + pos_, len_ - pos_);
-            pos_ = len_;
-        }
+    static constexpr size_t kBuf = 8u << 20;
+    // one line starting at p (without the terminator); false if the buffer holds no complete line
+    bool line(size_t& p, const char*& s, size_t& n) {
+        if (p >= len_) return false;
+        const char* e = static_cast<const char*>(std::memchr(buf_.data() + p, '\n', len_ - p));
+        if (!e) return false;
+        s = buf_.data() + p; n = static_cast<size_t>(e - s);
+        p += n + 1;
+        if (n && s[n - 1] == '\r') n--;
+        return true;
     }
     std::vector<std::string> paths_;
     size_t file_ = 0;
     gzFile gz_ = nullptr;
-    char buf_[1 << 16];
+    std::vector<char> buf_;
     size_t pos_ = 0, len_ = 0;
+    bool eof_ = false, patched_ = false;
 };
 
 struct Batch {
@@ -133,15 +157,26 @@ struct Batch {
     uint64_t* offsets = nullptr;
     size_t cap_bytes = 0, cap_reads = 0, bytes = 0;
     uint32_t n_reads = 0;
-    std::vector<std::string> ids;
+    std::vector<char> id_chars;          // read ids back to back
+    std::vector<uint32_t> id_off;        // n_reads + 1
     bool alloc(size_t cb, size_t cr) {
         cap_bytes = cb; cap_reads = cr;
         bases = static_cast<uint8_t*>(bb_host_alloc(cb + 64));
         offsets = static_cast<uint64_t*>(bb_host_alloc((cr + 1) * sizeof(uint64_t)));
         return bases && offsets;
     }
-    void clear() { bytes = 0; n_reads = 0; ids.clear(); if (offsets) offsets[0] = 0; }
+    void clear() { bytes = 0; n_reads = 0; id_chars.clear(); id_off.assign(1, 0); if (offsets) offsets[0] = 0; }
     void release() { bb_host_free(bases); bb_host_free(offsets); bases = nullptr; offsets = nullptr; }
+};
+
+// hand-off between the reader thread and the GPU/writer thread
+template <class T>
+class Channel {
+  public:
+    void push(T v) { { std::lock_guard<std::mutex> lk(mu_); q_.push_back(v); } cv_.notify_one(); }
+    T pop() { std::unique_lock<std::mutex> lk(mu_); cv_.wait(lk, [&] { return !q_.empty(); }); T v = q_.front(); q_.pop_front(); return v; }
+  private:
+    std::mutex mu_; std::condition_variable cv_; std::deque<T> q_;
 };
 
 const char* kTypeNames[] = {"Ftag", "Rtag", "Fflank", "Rflank"};
@@ -191,7 +226,7 @@ int run_annotate(const Args& a, const std::string& out_path) {
     std::setvbuf(out, outbuf, _IOFBF, sizeof outbuf);
 
     const size_t cap_bytes = a.batch_mb << 20, cap_reads = 1u << 22;
-    const int n_slots = 2 * n_gpus + 1;                 // 2 in flight per GPU + the one being filled
+    const int n_slots = 2 * n_gpus + 2;                 // 2 in flight per GPU + one filled + the one being filled
     std::vector<Batch> slots(n_slots);
     for (auto& b : slots) if (!b.alloc(cap_bytes, cap_reads)) { std::printf("Error during processing: pinned host allocation failed\n"); return BB_ERR_CUDA; }
 
@@ -200,6 +235,40 @@ int run_annotate(const Args& a, const std::string& out_path) {
     uint64_t total_reads = 0, total_rows = 0, kept = 0, submitted = 0;
     bool header_written = false;
     auto t0 = std::chrono::steady_clock::now();
+    Channel<int> free_slots, filled;                 // slot indices; filled: -1 = end of input, -2 = reader error
+    for (int s2 = 0; s2 < n_slots; s2++) free_slots.push(s2);
+    std::string reader_err;
+
+    // reader thread: FASTQ -> page-locked batches (annotator.rs:278-280: paraseq's reader thread fills record batches)
+    std::thread reader_thread([&] {
+        FastqReader reader(a.input);
+        FastqReader::View v;
+        int cur = free_slots.pop();
+        slots[cur].clear();
+        for (;;) {
+            std::string err;
+            const bool more = reader.next(v, err);
+            if (!more && !err.empty()) { reader_err = err; filled.push(-2); return; }
+            Batch* B = &slots[cur];
+            if (more && v.seq_len > B->cap_bytes) { reader_err = "read longer than the batch buffer (raise --batch-mb)"; filled.push(-2); return; }
+            const bool full = more && (B->bytes + v.seq_len > B->cap_bytes || B->n_reads + 1 > B->cap_reads);
+            if ((full || !more) && B->n_reads > 0) {
+                filled.push(cur);
+                if (!more) break;
+                cur = free_slots.pop();
+                if (cur < 0) return;                              // consumer aborted
+                B = &slots[cur];
+                B->clear();
+            }
+            if (!more) break;
+            std::memcpy(B->bases + B->bytes, v.seq, v.seq_len);
+            B->bytes += v.seq_len;
+            B->offsets[++B->n_reads] = B->bytes;
+            B->id_chars.insert(B->id_chars.end(), v.id, v.id + v.id_len);
+            B->id_off.push_back(static_cast<uint32_t>(B->id_chars.size()));
+        }
+        filled.push(-1);
+    });
 
     auto collect_one = [&]() -> int {
         const Flight f = flight.front(); flight.pop_front();
@@ -216,55 +285,37 @@ int run_annotate(const Args& a, const std::string& out_path) {
                 header_written = true;
             }
             if (w.read_idx != last) { kept++; last = w.read_idx; }
-            std::fprintf(out, "%s\t%u\t%lld\t%lld\t%lld\t%lld\t%lld\t%lld\t%lld\t%s\t%d\t%d\t%s\t%s\t\n", B.ids[w.read_idx].c_str(), w.read_len,
+            std::fwrite(B.id_chars.data() + B.id_off[w.read_idx], 1, B.id_off[w.read_idx + 1] - B.id_off[w.read_idx], out);
+            std::fprintf(out, "\t%u\t%lld\t%lld\t%lld\t%lld\t%lld\t%lld\t%lld\t%s\t%d\t%d\t%s\t%s\t\n", w.read_len,
                          static_cast<long long>(w.rel_dist_to_end), static_cast<long long>(w.read_start_bar), static_cast<long long>(w.read_end_bar),
                          static_cast<long long>(w.read_start_flank), static_cast<long long>(w.read_end_flank), static_cast<long long>(w.bar_start),
                          static_cast<long long>(w.bar_end), kTypeNames[w.match_type & 3], w.flank_cost, w.barcode_cost,
                          bb_groups_label(gs, w.group_idx, w.label_idx), w.strand ? "Rc" : "Fwd");
         }
         total_rows += n_rows;
+        free_slots.push(f.slot);
         return BB_OK;
     };
 
-    FastqReader reader(a.input);
-    std::string header, seq, rerr;
-    int cur = 0;
-    slots[cur].clear();
-    bool more = true;
     rc = BB_OK;
-    while (more && rc == BB_OK) {
-        more = reader.next(header, seq, rerr);
-        if (!more && !rerr.empty()) { std::printf("Error during processing: %s\n", rerr.c_str()); rc = BB_ERR_IO; break; }
+    for (;;) {
+        const int cur = filled.pop();
+        if (cur == -1) break;
+        if (cur == -2) { std::printf("Error during processing: %s\n", reader_err.c_str()); rc = BB_ERR_IO; break; }
         Batch& B = slots[cur];
-        const bool full = more && (B.bytes + seq.size() > B.cap_bytes || B.n_reads + 1 > B.cap_reads);
-        if ((full || !more) && B.n_reads > 0) {
-            const int dev = static_cast<int>(submitted % n_gpus);
-            // at most 2 batches in flight per GPU
-            size_t on_dev = 0; for (const auto& f : flight) on_dev += f.dev == dev;
-            while (on_dev >= 2 && rc == BB_OK) { const int d0 = flight.front().dev; rc = collect_one(); if (d0 == dev) on_dev--; }
-            if (rc != BB_OK) break;
-            rc = bb_submit(ctx[dev], B.bases, B.offsets, B.n_reads, submitted);
-            if (rc != BB_OK) { std::printf("Error during processing: %s\n", bb_last_error(ctx[dev])); break; }
-            flight.push_back({cur, dev});
-            submitted++;
-            total_reads += B.n_reads;
-            // next free slot: one that is not in flight
-            while (static_cast<int>(flight.size()) >= n_slots && rc == BB_OK) rc = collect_one();
-            std::vector<char> busy(n_slots, 0); for (const auto& f : flight) busy[f.slot] = 1;
-            for (int s = 0; s < n_slots; s++) if (!busy[s]) { cur = s; break; }
-            slots[cur].clear();
-        }
-        if (more) {
-            Batch& C = slots[cur];
-            if (seq.size() > C.cap_bytes) { std::printf("Error during processing: read longer than the batch buffer (raise --batch-mb)\n"); rc = BB_ERR_INVALID; break; }
-            const size_t sp = header.find_first_of(" \t");                   // split_fastq_header, io.rs:5-16
-            C.ids.emplace_back(sp == std::string::npos ? header : header.substr(0, sp));
-            std::memcpy(C.bases + C.bytes, seq.data(), seq.size());
-            C.bytes += seq.size();
-            C.offsets[++C.n_reads] = C.bytes;
-        }
+        const int dev = static_cast<int>(submitted % n_gpus);
+        size_t on_dev = 0; for (const auto& f : flight) on_dev += f.dev == dev;
+        while (on_dev >= 2 && rc == BB_OK) { const int d0 = flight.front().dev; rc = collect_one(); if (d0 == dev) on_dev--; }   // 2 in flight per GPU
+        if (rc != BB_OK) break;
+        rc = bb_submit(ctx[dev], B.bases, B.offsets, B.n_reads, submitted);
+        if (rc != BB_OK) { std::printf("Error during processing: %s\n", bb_last_error(ctx[dev])); break; }
+        flight.push_back({cur, dev});
+        submitted++;
+        total_reads += B.n_reads;
     }
     while (!flight.empty() && rc == BB_OK) rc = collect_one();
+    if (rc != BB_OK) { for (int s2 = 0; s2 < n_slots + 2; s2++) free_slots.push(-1); }   // unblock the reader
+    reader_thread.join();
     std::fclose(out);
     const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     if (rc == BB_OK) {
@@ -278,10 +329,26 @@ int run_annotate(const Args& a, const std::string& out_path) {
     return rc;
 }
 
+
+
+// `barbell fastq-stats -i files...`: parse only (no GPU): records, bases, FNV-1a of ids and sequences (reader self-check)
+int run_fastq_stats(const Args& a) {
+    FastqReader reader(a.input);
+    FastqReader::View v;
+    std::string err;
+    uint64_t n = 0, bases = 0, h = 1469598103934665603ull;
+    auto mix = [&](const char* p, size_t len) { for (size_t i = 0; i < len; i++) { h ^= static_cast<unsigned char>(p[i]); h *= 1099511628211ull; } h ^= 0xff; h *= 1099511628211ull; };
+    while (reader.next(v, err)) { n++; bases += v.seq_len; mix(v.id, v.id_len); mix(v.seq, v.seq_len); }
+    if (!err.empty()) { std::printf("Error during processing: %s\n", err.c_str()); return 1; }
+    std::printf("records=%llu bases=%llu fnv=%016llx\n", static_cast<unsigned long long>(n), static_cast<unsigned long long>(bases), static_cast<unsigned long long>(h));
+    return 0;
+}
+
 }  // namespace
 
 int main(int argc, char** argv) {
     const Args a = parse(argc, argv);
+    if (a.cmd == "fastq-stats") return run_fastq_stats(a);
     if (a.cmd == "annotate") {
         std::printf("Starting annotation...\n");
         if (run_annotate(a, a.output) == BB_OK) std::printf("Annotation complete!\n");

@@ -1,0 +1,57 @@
+"""FASTQ(.gz) reader of the `barbell` CLI (reference src/io/io.rs:5-32): plain / gzip / CRLF / multi-file / no trailing newline."""
+import gzip
+import os
+import subprocess
+
+import barbell_b200 as bb
+
+EXE = os.path.join(os.path.dirname(bb.lib_path()), "barbell")
+
+
+def fnv(records):
+    h = 1469598103934665603
+    for rid, seq in records:
+        for part in (rid, seq):
+            for c in part:
+                h = ((h ^ c) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+            h = ((h ^ 0xFF) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+    return h
+
+
+def stats(paths):
+    r = subprocess.run([EXE, "fastq-stats", "-i"] + [str(p) for p in paths], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0, r.stdout + r.stderr
+    kv = dict(x.split("=") for x in r.stdout.split())
+    return int(kv["records"]), int(kv["bases"]), int(kv["fnv"], 16)
+
+
+def test_reader_variants(tmp_path):
+    import random
+    rnd = random.Random(3)
+    recs = [(f"read{i}".encode(), bytes(rnd.choice(b"ACGTN") for _ in range(rnd.choice([0, 1, 50, 700, 70000])))) for i in range(60)]
+    def text(rs, nl="\n", desc=True, final_nl=True):
+        t = "".join(f"@{rid.decode()}{' runid=1 ch=2' if desc else ''}{nl}{seq.decode()}{nl}+{nl}{'I' * len(seq)}{nl}" for rid, seq in rs)
+        return t if final_nl else t[:-len(nl)]
+    want = (len(recs), sum(len(s) for _, s in recs), fnv(recs))
+    p1 = tmp_path / "a.fastq"; p1.write_text(text(recs))
+    assert stats([p1]) == want
+    p2 = tmp_path / "b.fastq.gz"
+    with gzip.open(p2, "wt") as f:
+        f.write(text(recs))
+    assert stats([p2]) == want
+    p3 = tmp_path / "c.fastq"; p3.write_bytes(text(recs, nl="\r\n").encode())
+    assert stats([p3]) == want
+    p4 = tmp_path / "d.fastq"; p4.write_text(text(recs, desc=False, final_nl=False))
+    assert stats([p4]) == want
+    # two files = one collection, in order (io.rs:27-32)
+    pa, pb = tmp_path / "e1.fastq", tmp_path / "e2.fastq.gz"
+    pa.write_text(text(recs[:25]))
+    with gzip.open(pb, "wt") as f:
+        f.write(text(recs[25:]) + "\n\n")
+    assert stats([pa, pb]) == want
+    # errors: truncated record, missing file -> message, non-zero exit of this debugging subcommand
+    p5 = tmp_path / "bad.fastq"; p5.write_text("@r1\nACGT\n+\n")
+    r = subprocess.run([EXE, "fastq-stats", "-i", str(p5)], capture_output=True, text=True)
+    assert r.returncode != 0 and "truncated" in r.stdout
+    r = subprocess.run([EXE, "fastq-stats", "-i", str(tmp_path / "nope.fastq")], capture_output=True, text=True)
+    assert r.returncode != 0 and "Failed to open" in r.stdout
