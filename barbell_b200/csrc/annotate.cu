@@ -90,7 +90,7 @@ struct Engine {
     std::string err;
     uint64_t launches = 0;
     // device buffers
-    DBuf d_bases, d_offsets, d_nch, d_chunk_base, d_tile_first, d_windows, d_entries, d_sorted, d_cub, d_flags, d_hitkeys, d_hits, d_hist, d_rows, d_valid, d_rows_out, d_hits6;
+    DBuf d_bases, d_offsets, d_nch, d_chunk_base, d_tile_first, d_windows, d_windows2, d_entries, d_sorted, d_cub, d_flags, d_hitkeys, d_hits, d_hist, d_rows, d_valid, d_rows_out, d_hits6;
     DBuf d_counters;                     // [0] n_entries (u32) [2] n_selected (u32) [4..5] kept reads (u64)
     uint32_t entries_cap = 0;
     bool use_filter = true;              // bb_opts.flags bit 0 disables the pre-filter (exact scan everywhere)
@@ -118,7 +118,7 @@ struct Engine {
     }
     void destroy() {
         cudaSetDevice(device);
-        for (DBuf* b : {&d_bases, &d_offsets, &d_nch, &d_chunk_base, &d_tile_first, &d_windows, &d_entries, &d_sorted, &d_cub, &d_flags, &d_hitkeys, &d_hits, &d_hist, &d_rows,
+        for (DBuf* b : {&d_bases, &d_offsets, &d_nch, &d_chunk_base, &d_tile_first, &d_windows, &d_windows2, &d_entries, &d_sorted, &d_cub, &d_flags, &d_hitkeys, &d_hits, &d_hist, &d_rows,
                         &d_valid, &d_rows_out, &d_hits6, &d_counters})
             b->release();
         if (h_counters) cudaFreeHost(h_counters);
@@ -196,7 +196,13 @@ struct Engine {
                     const size_t smem = filter_smem_bytes(fw);
                     BB_CUDA(cudaFuncSetAttribute(k_flank_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
                     k_flank_filter<<<n_tiles, kScanThreads, smem, st>>>(F, G);
-                    VerifyArgs V{A, d_windows.as<uint64_t>(), d_cnt + 6};
+                    // candidate runs -> (pre-check with the second N-free run) -> windows -> exact verification
+                    BB_CUDA(d_windows2.ensure(static_cast<size_t>(win_cap) * 8));
+                    BB_CUDA(cudaMemsetAsync(d_cnt + 8, 0, 4, st));
+                    PrecheckArgs P{A, d_windows.as<uint64_t>(), d_cnt + 6, d_windows2.as<uint64_t>(), d_cnt + 8, win_cap, d_cnt + 7};
+                    k_flank_precheck<<<148 * 8, 128, 0, st>>>(P, G);
+                    launches++;
+                    VerifyArgs V{A, d_windows2.as<uint64_t>(), d_cnt + 8};
                     if (G.nw == 1) k_flank_verify<1><<<148 * 8, 128, 0, st>>>(V, G);
                     else k_flank_verify<2><<<148 * 8, 128, 0, st>>>(V, G);
                     launches += 2;
@@ -529,7 +535,7 @@ int bb_set_groups(bb_ctx* c, const bb_group* groups, int32_t n_groups) {
         }
         // pre-filter: the longest N-free run of the flank, at most 15 rows; enabled when 3k <= rows (selective enough)
         off_feq[g] = blob.size();
-        blob.resize(blob.size() + 128, 0);
+        blob.resize(blob.size() + 256, 0);
         {
             int best0 = 0, bestn = 0, cur0 = 0, curn = 0;
             for (int i = 0; i <= m; i++) {
@@ -539,6 +545,27 @@ int bb_set_groups(bb_ctx* c, const bb_group* groups, int32_t n_groups) {
             const int q = std::min(bestn, 15);
             D.f_q = q; D.f_q0 = best0;
             D.f_on = (q >= 8 && 3 * S.k_flank <= q) ? 1 : 0;
+            // second N-free run (outside the first) for the pre-check of the candidates: at most 15 rows, taken next to the mask
+            int s_best0 = 0, s_bestn = 0; cur0 = 0; curn = 0;
+            for (int i = 0; i <= m; i++) {
+                const bool inside_q = i >= best0 && i < best0 + q;
+                if (i < m && !inside_q && pc[i] != 15 && pc[i] != 0) { if (!curn) cur0 = i; curn++; }
+                else { if (curn > s_bestn) { s_bestn = curn; s_best0 = cur0; } curn = 0; }
+            }
+            D.f_qs = s_bestn >= 4 ? std::min(s_bestn, 15) : 0;
+            D.f_s0 = (s_best0 > best0) ? s_best0 : s_best0 + (s_bestn - std::min(s_bestn, 15));   // keep the rows nearest to the first run
+            if (D.f_qs) {
+                uint32_t* seq = reinterpret_cast<uint32_t*>(blob.data() + off_feq[g]) + 256;
+                for (int ch = 0; ch < 256; ch++) {
+                    const uint8_t code = kAlpha.code[ch], ccode = Alphabet::comp(code);
+                    uint32_t v = 0;
+                    for (int r = 0; r < D.f_qs; r++) {
+                        if (pc[D.f_s0 + r] & code) v |= 1u << r;
+                        if (pc[D.f_s0 + D.f_qs - 1 - r] & ccode) v |= 1u << (16 + r);
+                    }
+                    seq[ch] = v;
+                }
+            }
             uint32_t* feq = reinterpret_cast<uint32_t*>(blob.data() + off_feq[g]);
             for (int ch = 0; ch < 256 && q > 0; ch++) {
                 const uint8_t code = kAlpha.code[ch], ccode = Alphabet::comp(code);
@@ -576,6 +603,7 @@ int bb_set_groups(bb_ctx* c, const bb_group* groups, int32_t n_groups) {
         hg[g].eq = base + off_eq[g];
         hg[g].eq_top = base + off_eqt[g];
         hg[g].f_eq = reinterpret_cast<const uint32_t*>(base + off_feq[g]);
+        hg[g].f_seq = hg[g].f_eq + 256;
         hg[g].bar_eq = base + off_bar[g];
         hg[g].ov = reinterpret_cast<const int*>(base + off_ov[g]);
     }

@@ -36,6 +36,9 @@ struct DevGroup {
     // lossless pre-filter (0 = off): rows [f_q0, f_q0 + f_q) of the flank are an N-free run with f_q <= 15 and 3k <= f_q
     int f_on, f_q, f_q0, f_pad;
     const uint32_t* f_eq;                // [256] bits [0,q): the run; bits [16,16+q): its reverse complement (both vs the forward text)
+    // second N-free run S = rows [f_s0, f_s0 + f_qs) (0 rows = none): pre-check of the filter's candidates
+    int f_qs, f_s0, f_pad2, f_pad3;
+    const uint32_t* f_seq;               // [256] same layout for S
 };
 
 // candidate window of the pre-filter / read-end window: end positions [lo, lo+len] of one strand's frame to verify exactly

@@ -488,16 +488,10 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_flank_filter(const FilterAr
             }
         }
 #undef BB_FSTEP
-        // ---- candidate runs -> windows (windows are linear in p because the half-width is the full k for both strands):
-        //   forward: the Df rows after the run are aligned to (p, j] with <= k edits        -> j  in [ps + Df - k, pe + Df + k]
-        //   rc     : the match starts at s = p - Dr +- k (the run's own indels shift its end) -> n-s in [n - pe + Dr - k, n - ps + Dr + k]
-        const int Df = m - (G.f_q0 + q);                         // flank rows after the run (forward strand)
-        const int Dr = m - G.f_q0;                               // rows of rc(flank) up to the end of rc(run)
-        auto push = [&](int strand, int lo, int hi) {
-            lo = max(lo, 1); hi = min(hi, n);
-            if (lo > hi) return;
+        // ---- candidate positions -> runs of consecutive positions per strand (queued as {read, strand, first, length-1}) ----
+        auto push = [&](int strand, int ps, int pe) {
             const uint32_t idx = atomicAdd(s_qn, 1u);
-            if (idx < kFiltQueue) s_queue[idx] = make_window(r, strand, lo, hi - lo);
+            if (idx < kFiltQueue) s_queue[idx] = make_window(r, strand, ps, pe - ps);
         };
         const int ng = (b - a + kGroup - 1) / kGroup;
         int f_s = 0, f_e = -2, r_s = 0, r_e = -2;               // run start / last position per strand (empty: e = -2)
@@ -511,19 +505,19 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_flank_filter(const FilterAr
                 const int t = 19 - (31 - __clz(cf));             // candidates in ascending position: highest bit first
                 cf &= ~(1u << (19 - t));
                 const int p = p0 + t;
-                if (p != f_e + 1) { if (f_e >= 0) push(BB_FWD, f_s + Df - k, f_e + Df + k); f_s = p; }
+                if (p != f_e + 1) { if (f_e >= 0) push(BB_FWD, f_s, f_e); f_s = p; }
                 f_e = p;
             }
             while (cr) {
                 const int t = 19 - (31 - __clz(cr));
                 cr &= ~(1u << (19 - t));
                 const int p = p0 + t;
-                if (p != r_e + 1) { if (r_e >= 0) push(BB_RC, n - r_e + Dr - k, n - r_s + Dr + k); r_s = p; }
+                if (p != r_e + 1) { if (r_e >= 0) push(BB_RC, r_s, r_e); r_s = p; }
                 r_e = p;
             }
         }
-        if (f_e >= 0) push(BB_FWD, f_s + Df - k, f_e + Df + k);
-        if (r_e >= 0) push(BB_RC, n - r_e + Dr - k, n - r_s + Dr + k);
+        if (f_e >= 0) push(BB_FWD, f_s, f_e);
+        if (r_e >= 0) push(BB_RC, r_s, r_e);
     }
     __syncthreads();
     // flush the CTA queue with one global atomic
@@ -534,6 +528,89 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_flank_filter(const FilterAr
     const uint32_t base = *s_qbase;
     if (base + nq > F.win_cap) { if (tid == 0) atomicExch(F.overflow, 1u); return; }
     for (uint32_t i = tid; i < nq; i += kScanThreads) F.windows[base + i] = s_queue[i];
+}
+
+// K1p: pre-check of the filter's candidate runs, then runs -> windows.
+// A candidate run [ps, pe] says "the run Q ends here with <= k edits".  In a real match the second N-free run S of the
+// flank ends at pS with |pS - p - d| <= k (d = signed row distance between the two run ends) and cost(Q) + cost(S) <= k.
+// One thread per run re-scores Q over [ps, pe] and S over [ps + d - k, pe + d + k] with single 32-bit block DPs (a few
+// hundred instructions) and drops the run when min cost(Q) + min cost(S) > k -- which removes ~95 % of the random
+// candidates before the ~4000-instruction exact verification.  Survivors become windows of end positions:
+//   forward: the Df rows after Q are aligned to (p, j] with <= k edits               -> j   in [ps + Df - k, pe + Df + k]
+//   rc     : the match starts at s = p - Dr +- k (the run's own indels shift its end) -> n-s in [n - pe + Dr - k, n - ps + Dr + k]
+struct PrecheckArgs {
+    ScanArgs S;
+    const uint64_t* runs;
+    const uint32_t* n_runs;
+    uint64_t* windows;
+    uint32_t* n_windows;
+    uint32_t win_cap;
+    uint32_t* overflow;
+};
+
+// min over end positions [lo, hi] (1-based, <= n) of the semi-global cost of a <=15-row block against text[0, n)
+__device__ __forceinline__ int block_min_cost(const uint8_t* __restrict__ text, const uint32_t* __restrict__ eq, int shiftbits, int rows,
+                                              int k, int lo, int hi) {
+    const uint32_t blk = (1u << rows) - 1u;
+    int c0 = lo - 1 - (rows + k);                            // the cost at p depends on text[p-(rows+k), p) only
+    if (c0 < 0) c0 = 0;
+    uint32_t pv = blk, mv = 0;
+    int score = rows, best = rows;
+    uint32_t ch_next = __ldg(text + c0);
+    for (int c = c0; c < hi; c++) {
+        const uint32_t e = (eq[ch_next] >> shiftbits) & blk;
+        if (c + 1 < hi) ch_next = __ldg(text + c + 1);
+        const uint32_t sum = (e & pv) + pv;
+        uint32_t ph = mv | ~(sum | pv | e);
+        uint32_t mh = pv & ((sum ^ pv) | e);
+        score += static_cast<int>((ph >> (rows - 1)) & 1u) - static_cast<int>((mh >> (rows - 1)) & 1u);
+        ph <<= 1; mh <<= 1;
+        pv = (mh | ~(e | mv | ph)) & blk;
+        mv = ph & (e | mv) & blk;
+        if (c + 1 >= lo) best = min(best, score);
+    }
+    return best;
+}
+
+__global__ void __launch_bounds__(128) k_flank_precheck(const PrecheckArgs P, const DevGroup G) {
+    __shared__ uint32_t s_q[256], s_s[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) { s_q[i] = __ldg(G.f_eq + i); s_s[i] = G.f_qs ? __ldg(G.f_seq + i) : 0u; }
+    __syncthreads();
+    const ScanArgs& A = P.S;
+    const uint32_t total = __ldg(P.n_runs);
+    const int m = G.m, k = G.k, q = G.f_q, qs = G.f_qs;
+    const int Df = m - (G.f_q0 + q), Dr = m - G.f_q0;
+    const int d_f = (G.f_s0 + qs) - (G.f_q0 + q);            // end(S) - end(Q) in the flank (forward strand)
+    const int d_r = G.f_q0 - G.f_s0;                         // end(rc S) - end(rc Q) in rc(flank)
+    for (uint32_t it = blockIdx.x * blockDim.x + threadIdx.x; it < total; it += gridDim.x * blockDim.x) {
+        const uint64_t w = P.runs[it];
+        const uint32_t r = static_cast<uint32_t>(w >> kWinReadShift);
+        const int strand = static_cast<int>((w >> kWinStrandShift) & 1);
+        const int ps = static_cast<int>((w >> kWinLoShift) & ((1u << 28) - 1)), pe = ps + static_cast<int>(w & ((1u << kWinLoShift) - 1));
+        const uint64_t rs_g = __ldg(A.offsets + r);
+        const int n = static_cast<int>(__ldg(A.offsets + r + 1) - rs_g);
+        const uint8_t* text = A.bases + rs_g;
+        bool keep = true;
+        if (qs > 0) {
+            const int d = strand == BB_FWD ? d_f : d_r;
+            const int slo = ps + d - k, shi = pe + d + k;
+            if (slo >= 1 && shi <= n) {                      // S entirely inside the read (else the read-end windows decide)
+                const int sbits = strand == BB_FWD ? 0 : 16;
+                const int cq = block_min_cost(text, s_q, sbits, q, k, ps, pe);
+                if (cq > k) keep = false;                    // cannot happen for a genuine candidate; cheap guard
+                else keep = cq + block_min_cost(text, s_s, sbits, qs, k, slo, shi) <= k;
+            }
+        }
+        if (!keep) continue;
+        int lo, hi;
+        if (strand == BB_FWD) { lo = ps + Df - k; hi = pe + Df + k; }
+        else { lo = n - pe + Dr - k; hi = n - ps + Dr + k; }
+        lo = max(lo, 1); hi = min(hi, n);
+        if (lo > hi) continue;
+        const uint32_t idx = atomicAdd(P.n_windows, 1u);
+        if (idx < P.win_cap) P.windows[idx] = make_window(r, strand, lo, hi - lo);
+        else atomicExch(P.overflow, 1u);
+    }
 }
 
 // K1v: exact verification of windows; items [0, 4*n_reads) are the read-end windows, the rest come from the queue.
