@@ -200,11 +200,11 @@ struct Engine {
                     BB_CUDA(d_windows2.ensure(static_cast<size_t>(win_cap) * 8));
                     BB_CUDA(cudaMemsetAsync(d_cnt + 8, 0, 4, st));
                     PrecheckArgs P{A, d_windows.as<uint64_t>(), d_cnt + 6, d_windows2.as<uint64_t>(), d_cnt + 8, win_cap, d_cnt + 7};
-                    k_flank_precheck<<<148 * 8, 128, 0, st>>>(P, G);
+                    k_flank_precheck<<<148 * 16, 128, 0, st>>>(P, G);
                     launches++;
                     VerifyArgs V{A, d_windows2.as<uint64_t>(), d_cnt + 8};
-                    if (G.nw == 1) k_flank_verify<1><<<148 * 8, 128, 0, st>>>(V, G);
-                    else k_flank_verify<2><<<148 * 8, 128, 0, st>>>(V, G);
+                    if (G.nw == 1) k_flank_verify<1><<<148 * 16, 128, 0, st>>>(V, G);
+                    else k_flank_verify<2><<<148 * 16, 128, 0, st>>>(V, G);
                     launches += 2;
                     filtered = true;
                     BB_CUDA(cudaGetLastError());
