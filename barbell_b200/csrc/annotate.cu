@@ -20,6 +20,7 @@
 #include <thread>
 #include <vector>
 
+#include "host/pack.hpp"
 #include "kernels.cuh"
 
 namespace bb {
@@ -94,6 +95,10 @@ struct Engine {
     DBuf d_counters;                     // [0] n_entries (u32) [2] n_selected (u32) [4..5] kept reads (u64)
     uint32_t entries_cap = 0;
     bool use_filter = true;              // bb_opts.flags bit 0 disables the pre-filter (exact scan everywhere)
+    bool pack_h2d = false;               // bb_opts.flags bit 1: nibble-pack the bases on the host before the PCIe copy
+    int pack_threads = 1;
+    uint8_t* h_pack = nullptr; size_t h_pack_cap = 0;   // pinned staging of the packed bases
+    DBuf d_packed;
     uint64_t last_windows = 0;
     uint32_t* h_counters = nullptr;      // pinned, 8 x u32
     bb_row* h_rows = nullptr; size_t h_rows_cap = 0;   // pinned
@@ -123,6 +128,8 @@ struct Engine {
             b->release();
         if (h_counters) cudaFreeHost(h_counters);
         if (h_rows) cudaFreeHost(h_rows);
+        if (h_pack) cudaFreeHost(h_pack);
+        d_packed.release();
         for (auto& e : ev) if (e) cudaEventDestroy(e);
         if (stream) cudaStreamDestroy(stream);
     }
@@ -353,7 +360,25 @@ struct Engine {
         if (offsets[0] != 0) { set_error("offsets[0] must be 0"); return BB_ERR_INVALID; }
         BB_CUDA(d_bases.ensure(((total + 15) & ~15ull) + 16));
         BB_CUDA(d_offsets.ensure(static_cast<size_t>(n_reads + 1) * 8));
-        BB_CUDA(cudaMemcpyAsync(d_bases.p, bases, total, cudaMemcpyHostToDevice, stream));
+        if (pack_h2d && total >= (1u << 20)) {
+            // two bases per byte over PCIe: pack on the host cores, expand on the device (lossless for this path)
+            const size_t pbytes = ((total + 15) & ~15ull) / 2 + 16;
+            if (pbytes > h_pack_cap) {
+                if (h_pack) cudaFreeHost(h_pack);
+                h_pack = nullptr; h_pack_cap = 0;
+                BB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&h_pack), pbytes + pbytes / 4));
+                h_pack_cap = pbytes + pbytes / 4;
+            }
+            BB_CUDA(d_packed.ensure(pbytes));
+            pack_nibbles(bases, total, h_pack, kAlpha.code, pack_threads);
+            BB_CUDA(cudaMemcpyAsync(d_packed.p, h_pack, (total + 1) / 2, cudaMemcpyHostToDevice, stream));
+            const uint64_t n16 = (total + 15) / 16;
+            k_unpack_nibbles<<<static_cast<unsigned>((n16 + 255) / 256), 256, 0, stream>>>(d_packed.as<uint8_t>(), d_bases.as<uint8_t>(), total);
+            launches++;
+            BB_CUDA(cudaGetLastError());
+        } else {
+            BB_CUDA(cudaMemcpyAsync(d_bases.p, bases, total, cudaMemcpyHostToDevice, stream));
+        }
         BB_CUDA(cudaMemcpyAsync(d_offsets.p, offsets, static_cast<size_t>(n_reads + 1) * 8, cudaMemcpyHostToDevice, stream));
         int rc = run(d_bases.as<uint8_t>(), d_offsets.as<uint64_t>(), n_reads, total, stream, n_rows);
         if (rc != BB_OK) return rc;
@@ -438,6 +463,8 @@ int bb_create(const bb_opts* opts, bb_ctx** out, char* err, size_t errlen) {
         c->eng[i].gt = &c->gt;
         c->eng[i].prm.min_score = opts->min_score; c->eng[i].prm.min_score_diff = opts->min_score_diff;
         c->eng[i].use_filter = (opts->flags & 1u) == 0;
+        c->eng[i].pack_h2d = (opts->flags & 2u) != 0;
+        c->eng[i].pack_threads = bb::pack_default_threads();
     }
     *out = c;
     return BB_OK;
@@ -729,6 +756,12 @@ int bb_fetch_flank_hits(bb_ctx* c, int32_t* out6, uint64_t cap, uint64_t* n_hits
     cudaError_t e = cudaMemcpyAsync(out6, E.d_hits6.p, static_cast<size_t>(E.last_hits) * 24, cudaMemcpyDeviceToHost, E.stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(E.stream);
     if (e != cudaSuccess) { ctx_error(c, std::string("export failed: ") + cudaGetErrorString(e)); return BB_ERR_CUDA; }
+    return BB_OK;
+}
+
+int bb_pack_nibbles(const uint8_t* src, uint64_t n, uint8_t* dst) {
+    if ((!src || !dst) && n) return BB_ERR_INVALID;
+    bb::pack_nibbles(src, n, dst, bb::kAlpha.code, bb::pack_default_threads());
     return BB_OK;
 }
 

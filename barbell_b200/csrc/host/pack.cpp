@@ -1,0 +1,138 @@
+// Nibble packing of the read bases on the host, so that the PCIe copy moves half the bytes.
+// The search depends on a text byte only through its 4-bit IUPAC base set (the match-mask tables are functions of it),
+// so two bases per byte is a lossless wire format for this path; the device expands it back to one representative
+// letter per set (k_unpack_nibbles).  AVX2 when the CPU has it (like the reference, which requires AVX2:
+// bin/main.rs:268 ensure_simd), scalar otherwise; a small persistent thread pool splits the batch.
+#include "pack.hpp"
+
+#include <immintrin.h>
+
+#include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+namespace bb {
+namespace {
+
+void pack_scalar(const uint8_t* src, size_t n, uint8_t* dst, const uint8_t* code) {
+    size_t i = 0;
+    for (; i + 1 < n; i += 2) dst[i >> 1] = static_cast<uint8_t>(code[src[i]] | (code[src[i + 1]] << 4));
+    if (i < n) dst[i >> 1] = code[src[i]];
+}
+
+// 32 bytes -> their 4-bit codes.  Only letters carry a code: idx = c & 15 selects from the two 16-entry halves of the
+// table for '@'..'_' (pshufb), bit 4 of c picks the half, and everything that is not a letter is masked to 0.
+__attribute__((target("avx2"))) static inline __m256i codes32(__m256i c, __m256i TL, __m256i TH) {
+    const __m256i idx = _mm256_and_si256(c, _mm256_set1_epi8(0x0f));
+    const __m256i lo = _mm256_shuffle_epi8(TL, idx), hi = _mm256_shuffle_epi8(TH, idx);
+    const __m256i v = _mm256_blendv_epi8(lo, hi, _mm256_slli_epi16(c, 3));       // bit 4 of c -> bit 7 (blendv selector)
+    const __m256i biased = _mm256_sub_epi8(_mm256_or_si256(c, _mm256_set1_epi8(0x20)), _mm256_set1_epi8('a'));
+    const __m256i is_letter = _mm256_cmpeq_epi8(_mm256_min_epu8(biased, _mm256_set1_epi8(25)), biased);   // 0..25 unsigned
+    return _mm256_and_si256(v, is_letter);
+}
+
+// 64 input bytes -> 32 output bytes per iteration.
+__attribute__((target("avx2"))) void pack_avx2(const uint8_t* src, size_t n, uint8_t* dst, const uint8_t* code) {
+    alignas(32) uint8_t tl[32], th[32];
+    for (int i = 0; i < 16; i++) { tl[i] = tl[i + 16] = code[0x40 + i]; th[i] = th[i + 16] = code[0x50 + i]; }   // '@'..'O', 'P'..'_'
+    const __m256i TL = _mm256_load_si256(reinterpret_cast<const __m256i*>(tl));
+    const __m256i TH = _mm256_load_si256(reinterpret_cast<const __m256i*>(th));
+    const __m256i mul = _mm256_set1_epi16(0x1001);               // bytes (1, 16): lo + 16 * hi per 16-bit lane
+    const bool aligned = (reinterpret_cast<uintptr_t>(dst) & 31) == 0;
+    size_t i = 0;
+    for (; i + 64 <= n; i += 64) {
+        const __m256i a = codes32(_mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + i)), TL, TH);
+        const __m256i b = codes32(_mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + i + 32)), TL, TH);
+        const __m256i pa = _mm256_maddubs_epi16(a, mul), pb = _mm256_maddubs_epi16(b, mul);   // 16 x u16 each, values < 256
+        const __m256i pk = _mm256_permute4x64_epi64(_mm256_packus_epi16(pa, pb), 0xD8);       // undo the per-lane interleave
+        if (aligned) _mm256_stream_si256(reinterpret_cast<__m256i*>(dst + (i >> 1)), pk);   // no read-for-ownership of the output
+        else _mm256_storeu_si256(reinterpret_cast<__m256i*>(dst + (i >> 1)), pk);
+    }
+    if (aligned) _mm_sfence();
+    pack_scalar(src + i, n - i, dst + (i >> 1), code);
+}
+
+class Pool {
+  public:
+    explicit Pool(int n) {
+        for (int t = 0; t < n; t++) workers_.emplace_back([this] { loop(); });
+    }
+    ~Pool() {
+        { std::lock_guard<std::mutex> lk(mu_); stop_ = true; }
+        cv_.notify_all();
+        for (auto& w : workers_) w.join();
+    }
+    // run fn(chunk) for chunk in [0, n_chunks) on the pool + the calling thread
+    void run(int n_chunks, const std::function<void(int)>& fn) {
+        std::unique_lock<std::mutex> call(call_mu_);              // one parallel region at a time
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            fn_ = &fn; next_.store(0); total_ = n_chunks; pending_ = n_chunks; gen_++;
+        }
+        cv_.notify_all();
+        work();
+        std::unique_lock<std::mutex> lk(mu_);
+        done_cv_.wait(lk, [&] { return pending_ == 0; });
+        fn_ = nullptr;
+    }
+    int size() const { return static_cast<int>(workers_.size()) + 1; }
+
+  private:
+    void work() {
+        for (;;) {
+            const int c = next_.fetch_add(1);
+            if (c >= total_) break;
+            (*fn_)(c);
+            std::lock_guard<std::mutex> lk(mu_);
+            if (--pending_ == 0) done_cv_.notify_all();
+        }
+    }
+    void loop() {
+        uint64_t seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return stop_ || gen_ != seen; });
+                if (stop_) return;
+                seen = gen_;
+            }
+            work();
+        }
+    }
+    std::vector<std::thread> workers_;
+    std::mutex mu_, call_mu_;
+    std::condition_variable cv_, done_cv_;
+    const std::function<void(int)>* fn_ = nullptr;
+    std::atomic<int> next_{0};
+    int total_ = 0, pending_ = 0;
+    uint64_t gen_ = 0;
+    bool stop_ = false;
+};
+
+Pool& pool(int threads) {
+    static Pool p(std::max(0, threads - 1));
+    return p;
+}
+}  // namespace
+
+int pack_default_threads() {
+    const unsigned hc = std::thread::hardware_concurrency();
+    return static_cast<int>(std::min(64u, std::max(1u, hc)));
+}
+
+void pack_nibbles(const uint8_t* src, size_t n, uint8_t* dst, const uint8_t* code, int threads) {
+    static const bool avx2 = __builtin_cpu_supports("avx2");
+    auto one = [&](const uint8_t* s, size_t len, uint8_t* d) { if (avx2) pack_avx2(s, len, d, code); else pack_scalar(s, len, d, code); };
+    const size_t kChunk = 4u << 20;                              // bases per work item (even, so chunks start on a byte boundary)
+    const int n_chunks = static_cast<int>((n + kChunk - 1) / kChunk);
+    if (threads <= 1 || n_chunks <= 1) { one(src, n, dst); return; }
+    pool(threads).run(n_chunks, [&](int c) {
+        const size_t lo = static_cast<size_t>(c) * kChunk, len = std::min(kChunk, n - lo);
+        one(src + lo, len, dst + (lo >> 1));
+    });
+}
+}  // namespace bb

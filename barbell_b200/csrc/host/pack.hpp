@@ -1,0 +1,11 @@
+// Host-side nibble packing of read bases for the host->device copy (see pack.cpp).
+#pragma once
+#include <cstddef>
+#include <cstdint>
+
+namespace bb {
+// code[256]: byte -> 4-bit IUPAC base set (the only property of a text byte the search depends on).
+// Packs n bases into (n+1)/2 bytes: out[i] = code[src[2i]] | code[src[2i+1]] << 4, using up to `threads` host threads.
+void pack_nibbles(const uint8_t* src, size_t n, uint8_t* dst, const uint8_t* code, int threads);
+int pack_default_threads();
+}  // namespace bb

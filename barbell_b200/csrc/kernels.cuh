@@ -1156,6 +1156,32 @@ __global__ void k_collapse(const Hit* __restrict__ hits, uint32_t n_hits, bb_row
     if (out > 0) atomicAdd(kept_reads, 1ull);
 }
 
+// Expands the nibble-packed wire format of the host->device copy (host/pack.cpp) back to one representative letter per
+// 4-bit IUPAC base set; 16 bases per thread (8 bytes in, 16 bytes out).  The search only sees a text byte through its
+// base set, so the round trip is lossless for this path.
+__global__ void k_unpack_nibbles(const uint8_t* __restrict__ packed, uint8_t* __restrict__ bases, uint64_t n_bases) {
+    const uint64_t g = (blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x) * 16;
+    if (g >= n_bases) return;
+    // code -> letter: A=1 C=2 G=4 T=8 and their unions; the empty set (non-IUPAC byte) -> 'X' (matches nothing)
+    const uint64_t lut_lo = 0x565352474d434158ull;   // codes 0..7 : X A C M G R S V   (little endian bytes)
+    const uint64_t lut_hi = 0x4e42444b48595754ull;   // codes 8..15: T W Y H K D B N
+    const uint2 in = *reinterpret_cast<const uint2*>(packed + (g >> 1));
+    uint32_t out[4];
+#pragma unroll
+    for (int w = 0; w < 4; w++) {
+        const uint32_t src = (w < 2 ? in.x : in.y) >> ((w & 1) * 16);
+        uint32_t v = 0;
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+            const uint32_t c = (src >> (4 * t)) & 15u;
+            const uint32_t ch = static_cast<uint32_t>(((c & 8u) ? lut_hi : lut_lo) >> ((c & 7u) * 8)) & 0xffu;
+            v |= ch << (8 * t);
+        }
+        out[w] = v;
+    }
+    *reinterpret_cast<uint4*>(bases + g) = make_uint4(out[0], out[1], out[2], out[3]);
+}
+
 // flank hit list for parity checks of the flank stage alone
 __global__ void k_export_hits(const Hit* __restrict__ hits, uint32_t n_hits, int32_t* __restrict__ out6) {
     const uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;

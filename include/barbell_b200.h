@@ -72,7 +72,8 @@ typedef struct {
     double  min_score_diff;     /* --min-score-diff, bin/main.rs:102-105 (default 0.1) */
     uint64_t max_batch_bytes;   /* capacity of the staging buffers for bb_annotate (0 = 256 MiB) */
     uint32_t max_batch_reads;   /* (0 = 4 Mi reads) */
-    uint32_t flags;             /* bit 0: disable the lossless pre-filter (exact full-length scan everywhere); else 0 */
+    uint32_t flags;             /* bit 0: disable the lossless pre-filter (exact full-length scan everywhere);
+                                   bit 1: nibble-pack the bases on the host cores before the PCIe copy (bb_annotate / bb_submit) */
 } bb_opts;
 
 typedef struct bb_ctx bb_ctx;
@@ -138,6 +139,10 @@ int  bb_fetch_flank_hits(bb_ctx *ctx, int32_t *out6, uint64_t cap, uint64_t *n_h
 /* page-locked host memory for the batch buffers handed to bb_submit / bb_annotate (NULL on failure) */
 void *bb_host_alloc(size_t bytes);
 void bb_host_free(void *p);
+
+/* the wire format of flags bit 1, exposed for hosts that want to pack while parsing: dst[i] = set(src[2i]) | set(src[2i+1]) << 4,
+   set() = 4-bit IUPAC base set (A=1, C=2, G=4, T=8; non-IUPAC bytes 0); dst holds (n+1)/2 bytes */
+int  bb_pack_nibbles(const uint8_t *src, uint64_t n, uint8_t *dst);
 
 int  bb_abi_version(void);
 

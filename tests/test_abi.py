@@ -58,3 +58,21 @@ def test_product_does_not_reference_oracle():
     assert not bad, bad
     out = os.popen(f"ldd {bb.lib_path()}").read()
     assert "oracle" not in out
+
+
+def test_pack_nibbles_matches_numpy():
+    """bb_pack_nibbles (AVX2 + thread pool) against a numpy restatement, all 256 byte values, odd lengths."""
+    import numpy as np
+    code = np.zeros(256, np.uint8)
+    for ch, v in zip(b"ACGTURYSWKMBDHVN", [1, 2, 4, 8, 8, 5, 10, 6, 9, 12, 3, 14, 13, 11, 7, 15]):
+        code[ch] = v; code[ch | 0x20] = v
+    rnd = np.random.default_rng(9)
+    for n in (0, 1, 63, 64, 65, 1000, 5_000_001):
+        src = rnd.integers(0, 256, n, dtype=np.uint8)
+        c = code[src]
+        if n & 1:
+            c = np.concatenate([c, [0]]).astype(np.uint8)
+        want = (c[0::2] | (c[1::2] << 4)).astype(np.uint8)
+        dst = np.zeros((n + 1) // 2 + 1, np.uint8)
+        assert bb.lib().bb_pack_nibbles(src.ctypes.data, n, dst.ctypes.data) == 0
+        assert (dst[:(n + 1) // 2] == want).all()

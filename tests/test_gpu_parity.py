@@ -251,3 +251,22 @@ def test_long_barcodes_unpacked_history_and_odd_counts():
     b, o, _ = synth.make_reads(G, 300, (150, 1500), seed=34)
     rows = _check(gs, b, o)
     assert (rows["match_type"] < 2).sum() > 50
+
+
+def test_nibble_packed_host_to_device_copy_is_lossless():
+    """bb_opts.flags bit 1: bases are packed two per byte on the host and expanded on the device; rows must not change
+    (lower case, IUPAC codes, non-IUPAC bytes included)."""
+    gs = bb.GroupSet.from_kit("SQK-NBD114-96")
+    b, o, _ = synth.make_reads(gs.as_dicts(), 3000, (200, 3000), seed=41, n_frac=0.01)
+    b = b.copy()
+    rnd = np.random.default_rng(5)
+    idx = rnd.integers(0, len(b), 3000)
+    b[idx] = rnd.choice(np.frombuffer(b"acgtnRYKMSWBDHVryU-*.@x", np.uint8), len(idx))
+    want = O.demux_batch(gs.as_dicts(), b, o)
+    an = _annotator(gs, pack_h2d=True)
+    got = an.annotate(b, o)
+    # pipelined calls take the same path
+    an.submit(b.ctypes.data, o.ctypes.data, len(o) - 1, tag=7)
+    tag, got2 = an.collect()
+    an.close()
+    assert got.tobytes() == want.tobytes() and got2.tobytes() == want.tobytes() and tag == 7
