@@ -4,6 +4,10 @@
 //                   bit-vector edit distance of the N-masked flank against every text position; emits every end
 //                   position whose cost is <= k ("sub-threshold entries").  Text tiles arrive in shared memory by one
 //                   TMA bulk copy per CTA; one lane owns one text chunk; match masks are staged once in shared memory.
+//  K1f filter       the same search as a LOSSLESS pre-filter: only the flank's longest N-free run (<= 15 rows) of both
+//  K1p precheck     strands is advanced per base (one 32-bit word, branch-free), candidate runs are re-scored together
+//  K1v verify       with the second N-free run, and the surviving windows (+ the read ends, where the overhang rule
+//                   applies) are verified with the exact full-length DP.  Default whenever 3k <= rows of the run.
 //  K2a resolve      sassy's local-minimum reporting rule applied to the sorted entries.
 //  K2b trace        traceback of every reported flank match -> text_start and the barcode text region
 //                   (reference cigar_parse.rs:71-82, searcher.rs:442-456).
@@ -11,7 +15,8 @@
 //                   match, barcodes across lanes), fallback pass, traceback, Lodhi score, thresholds, row assembly.
 //  K4  collapse     reference interval.rs:4-79, one thread per read.
 //
-// The arithmetic mirrors oracle/barbell_oracle.c bit for bit (policies S1-S7 there).
+// The arithmetic mirrors the CPU oracle's policies S1-S7 bit for bit (the oracle is test infrastructure: nothing here
+// includes, links or calls it).
 #pragma once
 #include <cuda_runtime.h>
 
