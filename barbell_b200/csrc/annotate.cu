@@ -303,7 +303,7 @@ struct Engine {
             BarArgs B{};
             B.bases = bases; B.offsets = offsets; B.hits = d_hits.as<Hit>(); B.n_hits = n_hits; B.groups = d_groups();
             B.code = gt->d_code.as<uint8_t>(); B.prm = prm; B.rows = d_rows.as<bb_row>(); B.row_valid = d_valid.as<uint8_t>();
-            B.hist_cols = gt->max_region + 1;
+            B.hist_cols = gt->max_region;
             const bool packed = gt->max_bar_len <= 48;
             const size_t smem = barcode_smem_bytes(B.hist_cols, packed);
             const unsigned blocks = std::min<unsigned>((n_hits + kBarWarps - 1) / kBarWarps, 148 * 32);

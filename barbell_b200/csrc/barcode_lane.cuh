@@ -1,0 +1,203 @@
+// Per-lane body of the barcode stage (K3): ONE padded barcode pattern against the barcode text region of one flank
+// match -- reference searcher.rs:282-301 (best match per pattern), sassy's traceback, cigar-lodhi-rs' score and
+// cigar_parse.rs:6-68 (map_pat_to_text_with_cost).  The function is __host__ __device__ so that the CPU test-suite can
+// run the very same code lane by lane against the oracle (tests/test_barcode_lane.py); the product only runs it on the GPU.
+//
+//  forward pass  one top-aligned 64-bit bit-vector column step per region base; walks sassy's local-minimum rule (S1)
+//                online and stores, for EVERY column, the two bit-vectors the traceback needs:
+//                   diag[i] = the path may leave cell (i, j) diagonally (match, or D[i-1][j-1] + 1 == D[i][j])
+//                   stop[i] = diag[i] or it may leave horizontally (D[i][j-1] + 1 == D[i][j])
+//                ([column][word][lane] in shared memory, 12 bytes per column when the pattern has <= 48 rows).
+//  traceback     (S2: match > substitution > text-only > pattern-only) ONE COLUMN per iteration and branch-free: the
+//                highest set bit of stop at or below the current row (count-leading-zeros) is the row at which the path
+//                leaves the column, the rows skipped on the way are pattern-only steps; no cost value is materialised
+//                and nothing is recomputed -- three LDS for the column plus the match mask of its base.
+//  Lodhi score   S_3(C, 1/2) is accumulated INSIDE the traceback loop in reversed op order.  The score is a sum of
+//                powers of two over triples of match ops, symmetric under reversal; with at most 48 ops every partial sum
+//                of either order is exactly representable in f64, so the reversed accumulation returns the same bits as
+//                the reference's forward recurrence.  Longer paths (>= 7 inserted bases; rare) replay the per-column
+//                records in path order with the forward recurrence.
+#pragma once
+#include <cstdint>
+#include <cstring>
+
+#if defined(__CUDACC__)
+#define BB_HD __host__ __device__ __forceinline__
+#else
+#define BB_HD inline
+#endif
+
+namespace bb {
+
+BB_HD int bb_clz64(uint64_t x) {
+#if defined(__CUDA_ARCH__)
+    return __clzll(static_cast<long long>(x));
+#else
+    return x ? __builtin_clzll(x) : 64;
+#endif
+}
+BB_HD double bb_bits_to_double(uint64_t x) {
+#if defined(__CUDA_ARCH__)
+    return __longlong_as_double(static_cast<long long>(x));
+#else
+    double d; std::memcpy(&d, &x, 8); return d;
+#endif
+}
+BB_HD double bb_fma(double a, double b, double c) {
+#if defined(__CUDA_ARCH__)
+    return __fma_rn(a, b, c);
+#else
+    return __builtin_fma(a, b, c);
+#endif
+}
+
+constexpr int kLodhiExactOps = 48;      // op count up to which every partial sum of the score is exact in f64
+
+template <bool PACKED>
+struct ColHist {                        // [column][word][lane] so that a warp's accesses are conflict-free
+    uint32_t* w;
+    int lane;
+    BB_HD void store(int col, uint64_t a, uint64_t b) const {
+        if constexpr (PACKED) {        // rows live in bits [16, 64): the low 16 bits are wildcard rows and never read
+            uint32_t* q = w + static_cast<size_t>(col) * 96 + lane;
+            q[0] = static_cast<uint32_t>(a >> 32); q[32] = static_cast<uint32_t>(b >> 32);
+            q[64] = (static_cast<uint32_t>(a) >> 16) | (static_cast<uint32_t>(b) & 0xffff0000u);
+        } else {
+            uint64_t* q = reinterpret_cast<uint64_t*>(w) + static_cast<size_t>(col) * 64 + lane;
+            q[0] = a; q[32] = b;
+        }
+    }
+    // One 32-bit traceback record per column, written over the first word of a column the traceback has already consumed.
+    BB_HD void store_rec(int col, uint32_t v) const {
+        if constexpr (PACKED) w[static_cast<size_t>(col) * 96 + lane] = v;
+        else w[(static_cast<size_t>(col) * 64 + lane) * 2] = v;
+    }
+    BB_HD uint32_t load_rec(int col) const {
+        if constexpr (PACKED) return w[static_cast<size_t>(col) * 96 + lane];
+        else return w[(static_cast<size_t>(col) * 64 + lane) * 2];
+    }
+    BB_HD void load(int col, uint64_t& a, uint64_t& b) const {
+        if constexpr (PACKED) {
+            const uint32_t* q = w + static_cast<size_t>(col) * 96 + lane;
+            const uint32_t lo = q[64];
+            a = (static_cast<uint64_t>(q[0]) << 32) | (lo << 16);
+            b = (static_cast<uint64_t>(q[32]) << 32) | (lo & 0xffff0000u);
+        } else {
+            const uint64_t* q = reinterpret_cast<const uint64_t*>(w) + static_cast<size_t>(col) * 64 + lane;
+            a = q[0]; b = q[32];
+        }
+    }
+};
+
+struct LaneAlign {
+    double s;                           // Lodhi S_3(path, 1/2), not normalised
+    int cbest, jend, ts;                // cost / end column of the first lowest-cost minimum; first text column of the path
+    int cnt, i_first, i_last, j_first, j_last, sub_cost;   // map_pat_to_text_with_cost over pattern rows [pb0, pb1)
+    int n_ops;
+};
+
+// Region bases are staged as one byte each: low nibble = 4-bit IUPAC base set, high nibble = slot of the set in the lane's
+// match-mask table (A, C, G, T, N -> 0..4; every other set -> kEqOther, resolved by OR-ing the masks of its bases).
+constexpr int kEqSlots = 5, kEqOther = 5;
+BB_HD uint8_t region_byte(uint8_t code) {
+    const int slot = code == 1 ? 0 : code == 2 ? 1 : code == 4 ? 2 : code == 8 ? 3 : code == 15 ? 4 : kEqOther;
+    return static_cast<uint8_t>(code | (slot << 4));
+}
+BB_HD uint64_t region_mask(const uint64_t* eq, uint32_t v, uint64_t wild) {
+    const uint32_t slot = v >> 4;
+    if (slot < static_cast<uint32_t>(kEqOther)) return eq[slot * 32];
+    uint64_t e = wild;                                       // rare: an ambiguity code other than N, or a non-IUPAC byte (empty set)
+    for (int b = 0; b < 4; b++) if ((v >> b) & 1u) e |= eq[b * 32];
+    return e;
+}
+
+// eq      : this lane's match masks of the sets {A}, {C}, {G}, {T}, {ACGT}, top-aligned with wildcard rows below: eq[slot * 32]
+// txt     : the region's bases as region_byte() values (shared by the warp), rn of them
+// hist    : this lane's column history; a consumed column's first word is reused for the column's traceback record
+template <bool PACKED>
+BB_HD void barcode_lane(const uint64_t* eq, const uint8_t* txt, int rn, int L, int pb0, int pb1,
+                        const ColHist<PACKED>& hist, LaneAlign& O) {
+    const int sh = 64 - L;                                   // row i of the pattern is bit i + sh
+    const uint64_t wild = sh ? ((1ull << sh) - 1ull) : 0ull;
+    // ---- forward pass: column history + the minima of the bottom row (S1) ----
+    uint64_t pv = (L >= 64 ? ~0ull : ((1ull << L) - 1ull)) << sh, mv = 0;
+    // S1 with every minimum reported (k = len) and "lowest cost, first seen" (searcher.rs:294-300) picks the right end of
+    // the FIRST plateau that reaches the global minimum of the bottom row: `open` = still on that plateau.
+    int cur = L, cbest = L, jend = 0, open = 1;
+    uint64_t e_next = rn > 0 ? region_mask(eq, txt[0], wild) : 0;
+    for (int p = 1; p <= rn; p++) {
+        const uint64_t e = e_next;
+        if (p < rn) e_next = region_mask(eq, txt[p], wild);
+        const uint64_t sum = (e & pv) + pv;
+        uint64_t ph = mv | ~(sum | pv | e);                  // horizontal deltas between columns p-1 and p
+        uint64_t mh = pv & ((sum ^ pv) | e);
+        const uint64_t diag = e | (ph & ~(pv | mv)) | (pv & ~(ph | mh));   // match, or D[i-1][p-1] + 1 == D[i][p]
+        hist.store(p - 1, diag, diag | ph);                                // ... else text-only if D[i][p-1] + 1 == D[i][p]
+        cur += static_cast<int>(ph >> 63) - static_cast<int>(mh >> 63);
+        ph <<= 1; mh <<= 1;
+        pv = mh | ~(e | mv | ph);
+        mv = ph & (e | mv);
+        open = cur < cbest ? 1 : (cur == cbest ? open : 0);
+        cbest = cur < cbest ? cur : cbest;
+        jend = open ? p : jend;
+    }
+    // ---- traceback (S2) from (L, jend), one column per iteration; column 0 is walked with pattern-only steps ----
+    int i = L, j = jend, nrec = 0, n_ops = 0;
+    int cnt = 0, i_first = 0, i_last = 0, j_first = 0, j_last = 0, sub_cost = 0;
+    double a1 = 0.0, a2 = 0.0, s = 0.0;                      // Lodhi accumulators over the REVERSED op sequence
+    uint64_t n_e = 0, n_diag = 0, n_stop = 0;                // the next column's vectors are fetched one iteration ahead
+    if (j > 0) { hist.load(j - 1, n_diag, n_stop); n_e = region_mask(eq, txt[j - 1], wild); }
+    while (i > 0 && j > 0) {
+        const uint64_t e = n_e, diag = n_diag, stop = n_stop;
+        const int jp = j - 1;
+        if (jp > 0) { hist.load(jp - 1, n_diag, n_stop); n_e = region_mask(eq, txt[jp - 1], wild); }
+        // move row i (bit i-1+sh) to bit 63: the leading zeros of stop are the pattern-only steps taken in this column
+        const int d = bb_clz64(stop << (L - i));
+        if (d >= i) break;                                   // no row at or below i lets the path out: pattern-only to row 0
+        const int il = i - d;                                // the path leaves the column at row il ...
+        const int t = il - 1 + sh;                           // ... whose bit this is
+        {
+            const int lo = il > pb0 ? il : pb0, hi = (i - 1) < (pb1 - 1) ? (i - 1) : (pb1 - 1);
+            if (hi >= lo) { if (cnt == 0) { i_last = hi; j_last = j; } i_first = lo; j_first = j; sub_cost += hi - lo + 1; cnt += hi - lo + 1; }
+        }
+        const int is_diag = static_cast<int>((diag >> t) & 1ull), is_match = static_cast<int>((e >> t) & 1ull);
+        i = il - is_diag; j = jp;                            // pre-op position of the leaving op
+        if (i >= pb0 && i < pb1) {                           // map_pat_to_text_with_cost range (cigar_parse.rs:22-30)
+            if (cnt == 0) { i_last = i; j_last = j; }
+            i_first = i; j_first = j; sub_cost += 1 - is_match; cnt++;
+        }
+        hist.store_rec(j, static_cast<uint32_t>((d << 1) | is_match));   // column j (0-based history slot) was consumed above
+        nrec++;
+        n_ops += d + 1;
+        // reversed op order: d non-match ops, then the leaving op; g = 2^-(d+1)
+        const double g = bb_bits_to_double(static_cast<uint64_t>(1022 - d) << 52);
+        const double mm = is_match ? 1.0 : 0.0;
+        s = bb_fma(is_match ? g : 0.0, a2, s);
+        a2 = g * bb_fma(mm, a1, a2);
+        a1 = bb_fma(g, a1, 0.5 * mm);
+    }
+    if (i > 0) {                                             // leading pattern-only steps at column j (first ops of the path)
+        const int lo = 0 > pb0 ? 0 : pb0, hi = (i - 1) < (pb1 - 1) ? (i - 1) : (pb1 - 1);
+        if (hi >= lo) { if (cnt == 0) { i_last = hi; j_last = j; } i_first = lo; j_first = j; sub_cost += hi - lo + 1; cnt += hi - lo + 1; }
+        n_ops += i;
+    }
+    if (n_ops > kLodhiExactOps) {
+        // same recurrence and op order as the reference's forward pass (leading non-match ops act on zeros)
+        a1 = 0.0; a2 = 0.0; s = 0.0;
+        for (int q = nrec - 1; q >= 0; q--) {
+            const int r = static_cast<int>(hist.load_rec(jend - 1 - q));
+            if (r & 1) { s = s + 0.5 * a2; a2 = 0.5 * (a2 + a1); a1 = 0.5 * (a1 + 1.0); }
+            else { a2 = 0.5 * a2; a1 = 0.5 * a1; }
+            const int d = r >> 1;
+            if (d) {                                         // d non-match ops = exact scaling by 2^-d
+                const double f = bb_bits_to_double(static_cast<uint64_t>(1023 - d) << 52);
+                a2 = a2 * f; a1 = a1 * f;
+            }
+        }
+    }
+    O.s = s; O.cbest = cbest; O.jend = jend; O.ts = j;
+    O.cnt = cnt; O.i_first = i_first; O.i_last = i_last; O.j_first = j_first; O.j_last = j_last; O.sub_cost = sub_cost;
+    O.n_ops = n_ops;
+}
+
+}  // namespace bb

@@ -24,6 +24,7 @@
 
 #include "../../include/barbell_b200.h"
 #include "device_types.cuh"
+#include "barcode_lane.cuh"
 
 namespace bb {
 
@@ -838,7 +839,7 @@ struct BarArgs {
     Params prm;
     bb_row* rows;             // one slot per hit
     uint8_t* row_valid;
-    int hist_cols;            // history columns per lane in shared memory (longest region + 1)
+    int hist_cols;            // history columns per lane in shared memory (longest region)
 };
 
 constexpr int kBarWarps = 1;
@@ -871,52 +872,16 @@ struct TopTwo {
     int ok = 0, pi = 0, ei = 0, pj = 0, ej = 0, cost = 0, ts = 0, te = 0;   // map_pat_to_text_with_cost of the top
 };
 
-// Shared-memory size of k_barcode for `cols` DP columns per lane: every column (Pv, Mv) of the lane's current pattern
-// (12 bytes when the pattern has <= 48 rows: the low 16 bits of both words are wildcard rows and always zero, so the two
-// low halves share one 32-bit word; 16 bytes otherwise), its 16 match masks, one traceback record per column, and the
-// region's base codes.
+// Shared-memory size of k_barcode for `cols` DP columns per lane: the lane's 5 match masks, the (diag, stop) bit-vectors
+// of every column (12 bytes when the pattern has <= 48 rows: rows live in bits [16, 64), so the two low halves share one
+// 32-bit word; 16 bytes otherwise; consumed columns are reused for the traceback records), and the region's bases.
 __host__ __device__ inline size_t barcode_warp_bytes(int cols, bool packed) {
-    const size_t c = static_cast<size_t>(cols) + 1, ch = c / 2 + 1;      // only the even columns are kept
-    return ch * 32 * (packed ? 12 : 16) + 16 * 32 * sizeof(uint64_t) + ((c * 32 + 15) & ~static_cast<size_t>(15)) + kCodesPad;
+    return kEqSlots * 32 * sizeof(uint64_t) + static_cast<size_t>(cols) * 32 * (packed ? 12 : 16) + kCodesPad;
 }
 __host__ __device__ inline size_t barcode_smem_bytes(int cols, bool packed) { return kBarWarps * barcode_warp_bytes(cols, packed); }
 
-template <bool PACKED>
-struct ColHist {                        // [column][word][lane] so that a warp's accesses are conflict-free
-    uint32_t* w;
-    int lane;
-    __device__ __forceinline__ void store(int col, uint64_t pv, uint64_t mv) const {
-        if constexpr (PACKED) {
-            uint32_t* q = w + static_cast<size_t>(col) * 96 + lane;
-            q[0] = static_cast<uint32_t>(pv >> 32); q[32] = static_cast<uint32_t>(mv >> 32);
-            q[64] = (static_cast<uint32_t>(pv) >> 16) | (static_cast<uint32_t>(mv) & 0xffff0000u);
-        } else {
-            uint64_t* q = reinterpret_cast<uint64_t*>(w) + static_cast<size_t>(col) * 64 + lane;
-            q[0] = pv; q[32] = mv;
-        }
-    }
-    __device__ __forceinline__ void load(int col, uint64_t& pv, uint64_t& mv) const {
-        if constexpr (PACKED) {
-            const uint32_t* q = w + static_cast<size_t>(col) * 96 + lane;
-            const uint32_t lo = q[64];
-            pv = (static_cast<uint64_t>(q[0]) << 32) | (lo << 16);
-            mv = (static_cast<uint64_t>(q[32]) << 32) | (lo & 0xffff0000u);
-        } else {
-            const uint64_t* q = reinterpret_cast<const uint64_t*>(w) + static_cast<size_t>(col) * 64 + lane;
-            pv = q[0]; mv = q[32];
-        }
-    }
-};
-
-// One warp per flank match; lane = barcode pattern (rounds of 32).  Per pattern:
-//  * one top-aligned bit-vector pass over the region that records every column (Pv, Mv) in shared memory
-//    ([column][lane], conflict-free) and walks the S1 minima online;
-//  * the S2 traceback from the best minimum, one COLUMN per iteration and branch-free: the horizontal deltas of the
-//    column pair are re-derived from the stored vertical deltas, the rows at which the path may leave the column
-//    (match/substitution first, then text-only) form a bit-vector, and the highest such row at or below the current one
-//    (count-leading-zeros) gives the number of pattern-only steps and the leaving op -- no cost value is materialised;
-//  * the Lodhi recurrence over the per-column records (leaving op + run of non-match ops; a run of d non-match ops is
-//    the exact scaling by 2^-d), in the oracle's op order.
+// One warp per flank match; lane = barcode pattern (rounds of 32); the per-pattern work is barcode_lane()
+// (barcode_lane.cuh: forward pass with column history, column-per-iteration traceback, Lodhi score).
 // The per-pattern best minimum is the same with k = floor(0.4*len) and with the fallback k = len (the first
 // lowest-cost minimum); the threshold only decides WHICH patterns are candidates, so both candidate sets are reduced
 // side by side and the fallback rule (searcher.rs:303-306) picks one at the end.
@@ -924,12 +889,11 @@ template <bool PACKED>
 __global__ void __launch_bounds__(kBarWarps * 32) k_barcode(const BarArgs A) {
     extern __shared__ __align__(16) unsigned char bar_smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const size_t ncol = static_cast<size_t>(A.hist_cols) + 1;
+    const size_t ncol = static_cast<size_t>(A.hist_cols);
     unsigned char* wbase = bar_smem + static_cast<size_t>(wib) * barcode_warp_bytes(A.hist_cols, PACKED);
-    uint64_t* eqs_s = reinterpret_cast<uint64_t*>(wbase);                    // [16 codes][32 lanes]
-    const ColHist<PACKED> hist{reinterpret_cast<uint32_t*>(eqs_s + 16 * 32), lane};
-    uint8_t* rec = wbase + 16 * 32 * sizeof(uint64_t) + (ncol / 2 + 1) * 32 * (PACKED ? 12 : 16);   // [column][lane]
-    uint8_t* codes = rec + ((ncol * 32 + 15) & ~static_cast<size_t>(15));
+    uint64_t* eqs_s = reinterpret_cast<uint64_t*>(wbase);                    // [5 base sets][32 lanes]
+    const ColHist<PACKED> hist{reinterpret_cast<uint32_t*>(eqs_s + kEqSlots * 32), lane};
+    uint8_t* txt = wbase + kEqSlots * 32 * sizeof(uint64_t) + ncol * 32 * (PACKED ? 12 : 16);   // region bases (region_byte)
     const uint32_t n_warps = gridDim.x * kBarWarps;
     for (uint32_t h = blockIdx.x * kBarWarps + wib; h < A.n_hits; h += n_warps) {
         const Hit H = A.hits[h];
@@ -939,12 +903,10 @@ __global__ void __launch_bounds__(kBarWarps * 32) k_barcode(const BarArgs A) {
         const int n = static_cast<int>(A.offsets[H.read + 1] - rs0);
         const int rn = H.re - H.rs;
         const int L = G.bar_len, nb = G.n_barcodes, k1 = G.k_bar;
-        const int pb0 = G.pbar0, pb1 = G.pbar1;
         const int sh = 64 - L;                                  // patterns are top-aligned like the flank scan
         __syncwarp();
-        for (int q = lane; q < rn; q += 32) codes[q] = __ldg(A.code + A.bases[rs0 + H.rs + q]);
+        for (int q = lane; q < rn; q += 32) txt[q] = region_byte(__ldg(A.code + A.bases[rs0 + H.rs + q]));
         const uint64_t* eqs = G.bar_eq + static_cast<size_t>(H.strand) * nb * 16;
-        const uint64_t pv_init = (L >= 64 ? ~0ull : ((1ull << L) - 1ull)) << sh;
         const uint64_t wild = sh ? ((1ull << sh) - 1ull) : 0ull;
 
         TopTwo all, strict;          // candidates under the fallback k = len / under k1
@@ -956,93 +918,15 @@ __global__ void __launch_bounds__(kBarWarps * 32) k_barcode(const BarArgs A) {
             __syncwarp();
             if (b < nb) {
 #pragma unroll
-                for (int cde = 0; cde < 16; cde++) eqs_s[cde * 32 + lane] = (__ldg(eqs + static_cast<size_t>(b) * 16 + cde) << sh) | wild;
+                for (int sl = 0; sl < kEqSlots; sl++)       // base sets {A}, {C}, {G}, {T}, {ACGT} = codes 1, 2, 4, 8, 15
+                    eqs_s[sl * 32 + lane] = (__ldg(eqs + static_cast<size_t>(b) * 16 + (sl < 4 ? (1 << sl) : 15)) << sh) | wild;
             }
             __syncwarp();
             if (b < nb) {
-                const uint64_t* eq = eqs_s + lane;
-                // ---- forward pass: record the columns, walk the minima (S1) ----
-                Col<1> col; col.pv[0] = pv_init; col.mv[0] = 0;
-                hist.store(0, pv_init, 0);
-                int prev = L, dec = 1, jend = -1, cbest = 1 << 20;
-                uint64_t e_next = rn > 0 ? eq[codes[0] * 32] : 0;
-                for (int p = 1; p <= rn; p++) {
-                    const uint64_t e = e_next;
-                    if (p < rn) e_next = eq[codes[p] * 32];
-                    const int cur = prev + col_step_top<1>(col, &e);
-                    if ((p & 1) == 0) hist.store(p >> 1, col.pv[0], col.mv[0]);       // even columns only; odd ones are re-derived
-                    if (cur > prev && dec && prev < cbest) { cbest = prev; jend = p - 1; }
-                    if (cur < prev) dec = 1; else if (cur > prev) dec = 0;
-                    prev = cur;
-                }
-                if (dec && prev < cbest) { cbest = prev; jend = rn; }
-                has1 = cbest <= k1;
-                // ---- traceback (S2), one column per iteration; no overhang: column 0 is walked with pattern-only steps ----
-                int i = L, j = jend, nrec = 0;
-                int cnt = 0, i_first = 0, i_last = 0, j_first = 0, j_last = 0, sub_cost = 0;
-                // the bit-vectors of a column pair do not depend on the path, so the pair for the NEXT iteration is
-                // prepared while the current one resolves its row (software pipelining of the LDS + vector work)
-                uint64_t n_e = 0, n_diag = 0, n_stop = 0;
-                auto prepare = [&](int jj) {                    // pair (jj-1, jj), jj >= 1
-                    uint64_t pvp, mvp;
-                    const int jp = jj - 1;
-                    hist.load(jp >> 1, pvp, mvp);               // even column at or below jj-1
-                    {                                           // odd jj-1: one column step from the stored even column (branch-free)
-                        Col<1> c2; c2.pv[0] = pvp; c2.mv[0] = mvp;
-                        const uint64_t e2 = eq[codes[jp > 0 ? jp - 1 : 0] * 32];
-                        col_step_top<1>(c2, &e2);
-                        if (jp & 1) { pvp = c2.pv[0]; mvp = c2.mv[0]; }
-                    }
-                    const uint64_t e = eq[codes[jj - 1] * 32];
-                    const uint64_t sum = (e & pvp) + pvp;
-                    const uint64_t ph = mvp | ~(sum | pvp | e), mh = pvp & ((sum ^ pvp) | e);   // deltas between columns jj-1 and jj
-                    n_e = e;
-                    n_diag = e | (ph & ~(pvp | mvp)) | (pvp & ~(ph | mh));   // match, or D[i-1][j-1] + 1 == D[i][j]
-                    n_stop = n_diag | ph;                                      // ... else text-only if D[i][j-1] + 1 == D[i][j]
-                };
-                if (j > 0) prepare(j);
-                while (i > 0 && j > 0) {
-                    const uint64_t e = n_e, diag = n_diag, stop = n_stop;
-                    const int jp = j - 1;
-                    if (jp > 0) prepare(jp);
-                    const int sbit = i - 1 + sh;
-                    const uint64_t below = (sbit >= 63 ? ~0ull : ((2ull << sbit) - 1ull)) & ~wild;
-                    const uint64_t cand = stop & below;
-                    if (cand == 0) break;                       // only pattern-only steps remain in this column
-                    const int t = 63 - __clzll(static_cast<long long>(cand));
-                    const int il = t - sh + 1;                  // the path leaves the column at row il
-                    const int d = i - il;                       // after d pattern-only steps (pre-op rows i-1 .. il)
-                    {
-                        const int lo = max(il, pb0), hi = min(i - 1, pb1 - 1);
-                        if (hi >= lo) { if (cnt == 0) { i_last = hi; j_last = j; } i_first = lo; j_first = j; sub_cost += hi - lo + 1; cnt += hi - lo + 1; }
-                    }
-                    const int is_diag = static_cast<int>((diag >> t) & 1ull), is_match = static_cast<int>((e >> t) & 1ull);
-                    i = il - is_diag; j = jp;                   // pre-op position of the leaving op
-                    if (i >= pb0 && i < pb1) {                  // map_pat_to_text_with_cost range (cigar_parse.rs:22-30)
-                        if (cnt == 0) { i_last = i; j_last = j; }
-                        i_first = i; j_first = j; sub_cost += 1 - is_match; cnt++;
-                    }
-                    rec[nrec * 32 + lane] = static_cast<uint8_t>((d << 1) | is_match);
-                    nrec++;
-                }
-                if (i > 0) {                                    // leading pattern-only steps at column j (first ops of the path)
-                    const int lo = max(0, pb0), hi = min(i - 1, pb1 - 1);
-                    if (hi >= lo) { if (cnt == 0) { i_last = hi; j_last = j; } i_first = lo; j_first = j; sub_cost += hi - lo + 1; cnt += hi - lo + 1; }
-                }
-                const int ts = j;
-                // ---- Lodhi S_3(C, 1/2) in path order (same recurrence and order as orc_lodhi; leading non-match ops act on zeros) ----
-                double a1 = 0.0, a2 = 0.0, s = 0.0;
-                for (int q = nrec - 1; q >= 0; q--) {
-                    const int r = rec[q * 32 + lane];
-                    if (r & 1) { s = s + 0.5 * a2; a2 = 0.5 * (a2 + a1); a1 = 0.5 * (a1 + 1.0); }
-                    else { a2 = 0.5 * a2; a1 = 0.5 * a1; }
-                    const int d = r >> 1;
-                    if (d) {                                    // d non-match ops = exact scaling by 2^-d
-                        const double f = __longlong_as_double(static_cast<long long>(1023 - d) << 52);
-                        a2 = a2 * f; a1 = a1 * f;
-                    }
-                }
-                const double sn = G.perfect > 0.0 ? s / G.perfect : 0.0;
+                LaneAlign R;
+                barcode_lane<PACKED>(eqs_s + lane, txt, rn, L, G.pbar0, G.pbar1, hist, R);
+                has1 = R.cbest <= k1;
+                const double sn = G.perfect > 0.0 ? R.s / G.perfect : 0.0;
 #pragma unroll
                 for (int set = 0; set < 2; set++) {
                     TopTwo& T = set == 0 ? all : strict;
@@ -1050,8 +934,8 @@ __global__ void __launch_bounds__(kBarWarps * 32) k_barcode(const BarArgs A) {
                     if (sn > T.top_s) {                       // ascending b within a lane: strict > keeps the lower index
                         T.sec_s = T.top_s;
                         T.top_s = sn; T.top_b = b;
-                        T.ok = cnt > 0; T.pi = i_first; T.ei = i_last; T.pj = j_first; T.ej = j_last; T.cost = sub_cost;
-                        T.ts = ts; T.te = jend;
+                        T.ok = R.cnt > 0; T.pi = R.i_first; T.ei = R.i_last; T.pj = R.j_first; T.ej = R.j_last; T.cost = R.sub_cost;
+                        T.ts = R.ts; T.te = R.jend;
                     } else if (sn > T.sec_s) T.sec_s = sn;
                 }
             }

@@ -1,0 +1,54 @@
+// Host build of the barcode stage's per-lane routine (barbell_b200/csrc/barcode_lane.cuh) for the CPU test-suite:
+// the SAME source the GPU kernel compiles, run for one lane of an emulated warp, so that its results can be compared
+// with the oracle without a GPU.  Test infrastructure only.
+#include <cstdint>
+#include <cstdlib>
+#include <vector>
+
+#include "../../barbell_b200/csrc/barcode_lane.cuh"
+
+namespace {
+uint8_t g_code[256];
+bool g_ready = false;
+void init_codes() {
+    if (g_ready) return;
+    const char* L = "ACGTURYSWKMBDHVN";
+    const uint8_t V[] = {1, 2, 4, 8, 8, 5, 10, 6, 9, 12, 3, 14, 13, 11, 7, 15};
+    for (int i = 0; L[i]; i++) { g_code[static_cast<uint8_t>(L[i])] = V[i]; g_code[static_cast<uint8_t>(L[i] | 0x20)] = V[i]; }
+    g_ready = true;
+}
+}  // namespace
+
+extern "C" {
+// out[12] = {cbest, jend, ts, cnt, i_first, i_last, j_first, j_last, sub_cost, n_ops, packed_used, 0}; score = Lodhi S_3
+int emu_barcode_lane(const uint8_t* pattern, int L, const uint8_t* region, int rn, int pb0, int pb1, int lane, int hist_cols,
+                     int32_t* out, double* score) {
+    init_codes();
+    if (L < 1 || L > 64 || rn < 0 || rn > hist_cols || lane < 0 || lane > 31) return -1;
+    const int sh = 64 - L;
+    const uint64_t wild = sh ? ((1ull << sh) - 1ull) : 0ull;
+    std::vector<uint64_t> eqs(bb::kEqSlots * 32, 0xdeadbeefdeadbeefull);
+    for (int sl = 0; sl < bb::kEqSlots; sl++) {
+        const int code = sl < 4 ? (1 << sl) : 15;
+        uint64_t v = 0;
+        for (int i = 0; i < L; i++) if (g_code[pattern[i]] & code) v |= 1ull << i;
+        eqs[sl * 32 + lane] = (v << sh) | wild;
+    }
+    std::vector<uint8_t> txt(rn + 16, 0);
+    for (int q = 0; q < rn; q++) txt[q] = bb::region_byte(g_code[region[q]]);
+    std::vector<uint32_t> hist(static_cast<size_t>(hist_cols) * 32 * 4 + 64, 0xabababab);
+    bb::LaneAlign R;
+    const bool packed = L <= 48;
+    if (packed) {
+        bb::ColHist<true> H{hist.data(), lane};
+        bb::barcode_lane<true>(eqs.data() + lane, txt.data(), rn, L, pb0, pb1, H, R);
+    } else {
+        bb::ColHist<false> H{hist.data(), lane};
+        bb::barcode_lane<false>(eqs.data() + lane, txt.data(), rn, L, pb0, pb1, H, R);
+    }
+    out[0] = R.cbest; out[1] = R.jend; out[2] = R.ts; out[3] = R.cnt; out[4] = R.i_first; out[5] = R.i_last;
+    out[6] = R.j_first; out[7] = R.j_last; out[8] = R.sub_cost; out[9] = R.n_ops; out[10] = packed; out[11] = 0;
+    *score = R.s;
+    return 0;
+}
+}
