@@ -37,6 +37,7 @@ EXPORTS = ["bb_groups_from_kit", "bb_groups_from_fasta", "bb_groups_add", "bb_gr
            "bb_lookup_barcode_seq", "bb_create",
            "bb_destroy", "bb_last_error", "bb_set_groups", "bb_annotate", "bb_annotate_device", "bb_fetch_rows",
            "bb_submit", "bb_collect", "bb_counters", "bb_host_alloc", "bb_host_free", "bb_pack_nibbles", "bb_last_stage_ms", "bb_kernel_launches", "bb_fetch_flank_hits",
+           "bb_kit_info", "bb_kit_filter_patterns", "bb_pattern_parse", "bb_filter", "bb_inspect", "bb_trim",
            "bb_abi_version"]
 
 _lib = None

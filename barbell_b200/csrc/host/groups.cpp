@@ -280,5 +280,19 @@ int bb_label_range(const char* from, const char* to, int use_12a, char* out, siz
     return static_cast<int>(labels.size());
 }
 const char* bb_lookup_barcode_seq(const char* label) { return label ? bb::barcode_seq(label) : nullptr; }
+int bb_kit_info(const char* kit, char* name, size_t namelen, char* ranges, size_t rangeslen, int* double_label, char* err, size_t errlen) {
+    if (!kit) return BB_ERR_INVALID;
+    std::string note;
+    const bb::KitPreset* p = bb::find_kit(kit, note);
+    if (!p) { bb::set_err(err, errlen, std::string("Unknown or unsupported kit: ") + kit + ", please raise an issue"); return BB_ERR_KIT; }
+    if (name && namelen) std::snprintf(name, namelen, "%s", p->name);
+    if (ranges && rangeslen) {
+        std::string r;
+        for (int t = 0; t < p->n_templates; t++) r += std::string(t ? "; " : "") + p->templates[t].label_from + " - " + p->templates[t].label_to;
+        std::snprintf(ranges, rangeslen, "%s", r.c_str());
+    }
+    if (double_label) *double_label = p->double_label_patterns ? 1 : 0;
+    return BB_OK;
+}
 int bb_abi_version(void) { return BB_ABI_VERSION; }
 }

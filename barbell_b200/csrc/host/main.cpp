@@ -3,7 +3,8 @@
 // (two batches in flight per GPU); rows are written as annotation.tsv in input order (reference column order,
 // src/annotate/searcher.rs:31-64; the header is written with the first row, so a run without hits leaves an empty
 // file exactly like the reference's csv writer, annotator.rs:20-24).
-// Not part of this build: inspect / filter / trim; `kit` runs the annotate stage only.
+// `filter`, `inspect` and `trim` (bin/main.rs:113-209, 340-395) are thin wrappers over bb_filter / bb_inspect / bb_trim, and
+// `kit` chains annotate -> inspect -> filter -> trim with the reference's fixed file names (src/kits/use_kit.rs:11-109).
 #include <sys/stat.h>
 #include <zlib.h>
 
@@ -20,6 +21,7 @@
 #include <vector>
 
 #include "../../../include/barbell_b200.h"
+#include "fastq.hpp"
 
 namespace {
 
@@ -28,6 +30,12 @@ struct Args {
     std::vector<std::string> input, queries, barcode_types{"Ftag"};
     int threads = 10, flank_max_errors = -1, gpus = 1;
     bool verbose = false, use_extended = false, maximize = false, gzip = false;
+    // filter / trim / inspect
+    std::vector<std::string> pattern_files, reads;
+    std::string dropped, failed_out, only_side, read_pattern_out;
+    bool no_label = false, no_orientation = false, no_flanks = false, sort_labels = false, skip_trim = false, flip = false;
+    int top_n = 10, bucket_size = 250;
+    bool output_given = false;
     double min_score = 0.2, min_score_diff = 0.1;
     float alpha = 0.4f;
     size_t batch_mb = 256;
@@ -40,7 +48,11 @@ struct Args {
         "  barbell annotate -i <fastq>... [-o output.tsv] (--kit <KIT> | -q <fasta>... [-b Ftag|Rtag ...])\n"
         "                   [-t N] [--flank-max-errors INT] [--min-score F] [--min-score-diff F] [--alpha F]\n"
         "                   [--use-extended] [--verbose] [--gpus N] [--batch-mb MB]\n"
-        "  barbell kit -k <KIT> -i <fastq>... -o <folder> [same options]   (annotate stage only)\n");
+        "  barbell kit -k <KIT> -i <fastq>... -o <folder> [--maximize] [--failed-out FILE] [--gzip] [annotate options]\n"
+        "  barbell filter -i annotation.tsv -o filtered.tsv -f <pattern file>... [--dropped FILE]\n"
+        "  barbell trim -i filtered.tsv -r <fastq>... -o <folder> [--no-label] [--no-orientation] [--no-flanks] [--sort-labels]\n"
+        "               [--only-side left|right] [--failed-out FILE] [--skip-trim] [--flip] [--gzip]\n"
+        "  barbell inspect -i annotation.tsv [-n 10] [-o read_patterns.tsv] [-s 250]\n");
     std::exit(msg ? 2 : 0);
 }
 
@@ -51,7 +63,8 @@ Args parse(int argc, char** argv) {
     if (argc < 2) usage(nullptr);
     a.cmd = argv[1];
     if (a.cmd == "-h" || a.cmd == "--help") usage(nullptr);
-    if (a.cmd != "annotate" && a.cmd != "kit" && a.cmd != "fastq-stats") usage("only the `annotate` and `kit` subcommands exist in this build");
+    if (a.cmd != "annotate" && a.cmd != "kit" && a.cmd != "filter" && a.cmd != "trim" && a.cmd != "inspect" && a.cmd != "fastq-stats")
+        usage("subcommands: annotate, kit, filter, trim, inspect");
     bool types_given = false;
     for (int i = 2; i < argc; i++) {
         std::string f = argv[i];
@@ -60,7 +73,20 @@ Args parse(int argc, char** argv) {
         if (f == "-i" || f == "--input") many(a.input);
         else if (f == "-q" || f == "--queries") many(a.queries);
         else if (f == "-b" || f == "--barcode-types") { if (!types_given) a.barcode_types.clear(); types_given = true; many(a.barcode_types); }
-        else if (f == "-o" || f == "--output") a.output = one();
+        else if ((f == "-o" || f == "--read-pattern-out") && a.cmd == "inspect") a.read_pattern_out = one();
+        else if (f == "-o" || f == "--output") { a.output = one(); a.output_given = true; }
+        else if (f == "-f" || f == "--file") many(a.pattern_files);
+        else if (f == "-r" || f == "--reads") many(a.reads);
+        else if (f == "--dropped") a.dropped = one();
+        else if (f == "--no-label") a.no_label = true;
+        else if (f == "--no-orientation") a.no_orientation = true;
+        else if (f == "--no-flanks") a.no_flanks = true;
+        else if (f == "--sort-labels") a.sort_labels = true;
+        else if (f == "--only-side") a.only_side = one();
+        else if (f == "--skip-trim") a.skip_trim = true;
+        else if (f == "--flip") a.flip = true;
+        else if ((f == "-n" || f == "--top-n") && a.cmd == "inspect") a.top_n = std::atoi(one().c_str());
+        else if ((f == "-s" || f == "--bucket-size") && a.cmd == "inspect") a.bucket_size = std::atoi(one().c_str());
         else if (f == "-t" || f == "--threads") a.threads = std::atoi(one().c_str());
         else if (f == "--kit" || f == "-k") a.kit = one();
         else if (f == "--flank-max-errors") a.flank_max_errors = std::atoi(one().c_str());
@@ -69,7 +95,7 @@ Args parse(int argc, char** argv) {
         else if (f == "--alpha") a.alpha = static_cast<float>(std::atof(one().c_str()));
         else if (f == "--gpus") a.gpus = std::atoi(one().c_str());
         else if (f == "--batch-mb") a.batch_mb = static_cast<size_t>(std::atol(one().c_str()));
-        else if (f == "--failed-out") (void)one();
+        else if (f == "--failed-out") a.failed_out = one();
         else if (f == "--verbose") a.verbose = true;
         else if (f == "--use-extended") a.use_extended = true;
         else if (f == "--maximize") a.maximize = true;
@@ -80,77 +106,7 @@ Args parse(int argc, char** argv) {
     return a;
 }
 
-// FASTQ(.gz) reader over several files (reference io.rs:27-32: one paraseq Collection over all paths).  Records are
-// parsed in place from a large read buffer (memchr per line) and handed out as views; the caller copies the bases
-// straight into the page-locked batch buffer, so every base is copied exactly once on the host.
-class FastqReader {
-  public:
-    explicit FastqReader(std::vector<std::string> paths) : paths_(std::move(paths)), buf_(kBuf) {}
-    ~FastqReader() { if (gz_) gzclose(gz_); }
-    struct View { const char* id; size_t id_len; const char* seq; size_t seq_len; };
-    // next record; false at the end of the last file or on error (err non-empty)
-    bool next(View& v, std::string& err) {
-        for (;;) {
-            if (!gz_) {
-                if (file_ >= paths_.size()) return false;
-                gz_ = gzopen(paths_[file_].c_str(), "rb");
-                if (!gz_) { err = "Failed to open FASTQ input: " + paths_[file_]; return false; }
-                gzbuffer(gz_, 1 << 20);
-                pos_ = len_ = 0; eof_ = false;
-            }
-            size_t p = pos_;
-            const char *l0, *l1, *l2, *l3; size_t n0, n1, n2, n3;
-            if (line(p, l0, n0) && line(p, l1, n1) && line(p, l2, n2) && line(p, l3, n3)) {
-                pos_ = p;
-                if (n0 == 0 && n1 == 0) continue;                 // blank lines between records
-                if (l0[0] != '@' || n2 == 0 || l2[0] != '+') { err = "malformed FASTQ record in " + paths_[file_]; return false; }
-                if (n3 != n1) { err = "truncated FASTQ record (quality length differs from sequence length) in " + paths_[file_]; return false; }
-                (void)l3;
-                size_t idl = 0;                                    // split_fastq_header, io.rs:5-16: id = header up to whitespace
-                while (idl < n0 - 1 && l0[1 + idl] != ' ' && l0[1 + idl] != '\t') idl++;
-                v.id = l0 + 1; v.id_len = idl; v.seq = l1; v.seq_len = n1;
-                return true;
-            }
-            // incomplete record in the buffer: compact and refill
-            if (eof_) {
-                bool only_ws = true;
-                for (size_t i = pos_; i < len_; i++) if (buf_[i] != '\n' && buf_[i] != '\r') { only_ws = false; break; }
-                if (!only_ws) {
-                    // last record without a trailing newline: terminate it and parse once more
-                    if (len_ < buf_.size() && !patched_) { buf_[len_++] = '\n'; patched_ = true; continue; }
-                    err = "truncated FASTQ record in " + paths_[file_]; return false;
-                }
-                gzclose(gz_); gz_ = nullptr; file_++; patched_ = false;
-                continue;
-            }
-            if (pos_ > 0) { std::memmove(buf_.data(), buf_.data() + pos_, len_ - pos_); len_ -= pos_; pos_ = 0; }
-            if (len_ + 1 >= buf_.size()) buf_.resize(buf_.size() * 2);       // a single record longer than the buffer
-            const int n = gzread(gz_, buf_.data() + len_, static_cast<unsigned>(std::min<size_t>(buf_.size() - 1 - len_, 1u << 30)));
-            if (n < 0) { err = "read error in " + paths_[file_]; return false; }
-            if (n == 0) eof_ = true;
-            len_ += static_cast<size_t>(n);
-        }
-    }
-
-  private:
-    static constexpr size_t kBuf = 8u << 20;
-    // one line starting at p (without the terminator); false if the buffer holds no complete line
-    bool line(size_t& p, const char*& s, size_t& n) {
-        if (p >= len_) return false;
-        const char* e = static_cast<const char*>(std::memchr(buf_.data() + p, '\n', len_ - p));
-        if (!e) return false;
-        s = buf_.data() + p; n = static_cast<size_t>(e - s);
-        p += n + 1;
-        if (n && s[n - 1] == '\r') n--;
-        return true;
-    }
-    std::vector<std::string> paths_;
-    size_t file_ = 0;
-    gzFile gz_ = nullptr;
-    std::vector<char> buf_;
-    size_t pos_ = 0, len_ = 0;
-    bool eof_ = false, patched_ = false;
-};
+using bb::FastqReader;
 
 struct Batch {
     uint8_t* bases = nullptr;
@@ -344,6 +300,109 @@ int run_fastq_stats(const Args& a) {
     return 0;
 }
 
+// `barbell filter` (bin/main.rs:340-354, filter_from_text_file filter.rs:137-181)
+int run_filter_cmd(const Args& a) {
+    std::printf("Starting filtering...\n");
+    char err[1024] = {0};
+    std::string msg;
+    std::vector<std::string> pats;
+    if (a.input.size() != 1 || !a.output_given || a.pattern_files.empty()) usage("filter needs -i <annotation.tsv> -o <output> -f <pattern file>...");
+    for (const auto& pf : a.pattern_files) {
+        FILE* f = std::fopen(pf.c_str(), "r");
+        if (!f) { msg = pf + ": cannot read pattern file"; break; }
+        char line[8192];
+        while (std::fgets(line, sizeof line, f)) {
+            std::string l(line);
+            size_t b = 0, e = l.size();
+            while (b < e && std::isspace(static_cast<unsigned char>(l[b]))) b++;
+            while (e > b && std::isspace(static_cast<unsigned char>(l[e - 1]))) e--;
+            if (e > b) pats.push_back(l.substr(b, e - b));
+        }
+        std::fclose(f);
+    }
+    if (msg.empty() && pats.empty()) msg = "No filter patterns found";
+    if (msg.empty()) {
+        std::vector<const char*> pp;
+        for (const auto& s : pats) pp.push_back(s.c_str());
+        uint64_t counts[3] = {0, 0, 0};
+        const int rc = bb_filter(a.input[0].c_str(), a.output.c_str(), a.dropped.empty() ? nullptr : a.dropped.c_str(), pp.data(),
+                                 static_cast<int32_t>(pp.size()), counts, err, sizeof err);
+        if (rc == BB_OK) {
+            std::printf("Total: %llu  Kept: %llu  Dropped: %llu reads\n", static_cast<unsigned long long>(counts[0]),
+                        static_cast<unsigned long long>(counts[1]), static_cast<unsigned long long>(counts[2]));
+            std::printf("Filtering successful!\n");
+            return 0;
+        }
+        msg = err;
+        if (msg.rfind("Pattern parse error", 0) == 0 || msg.rfind("Flank is not valid", 0) == 0) { std::fprintf(stderr, "%s\n", msg.c_str()); return 101; }   // the reference panics here
+    }
+    std::printf("Filtering failed: %s\n", msg.c_str());
+    return 0;
+}
+
+bb_trim_opts trim_opts_from(const Args& a, bool kit_defaults) {
+    bb_trim_opts o{};
+    if (kit_defaults) {                                   // use_kit.rs:87-99
+        o.add_labels = 1; o.add_orientation = 0; o.add_flank = 0; o.sort_labels = 0; o.only_side = 1;
+        o.write_full_header = 1; o.skip_trim = 0; o.flip = 0;
+    } else {                                              // bin/main.rs:372-384
+        o.add_labels = !a.no_label; o.add_orientation = !a.no_orientation; o.add_flank = !a.no_flanks; o.sort_labels = a.sort_labels;
+        o.only_side = a.only_side == "left" ? 1 : a.only_side == "right" ? 2 : 0;
+        o.write_full_header = 1; o.skip_trim = a.skip_trim; o.flip = a.flip;
+    }
+    o.gzip = a.gzip;
+    o.failed_out = a.failed_out.empty() ? nullptr : a.failed_out.c_str();
+    return o;
+}
+
+int run_trim(const std::string& filtered, const std::vector<std::string>& reads, const std::string& out_dir, const bb_trim_opts& o, std::string& msg) {
+    std::vector<const char*> rp;
+    for (const auto& r : reads) rp.push_back(r.c_str());
+    uint64_t counts[4] = {0, 0, 0, 0};
+    char err[1024] = {0};
+    const int rc = bb_trim(filtered.c_str(), rp.data(), static_cast<int32_t>(rp.size()), out_dir.c_str(), &o, counts, err, sizeof err);
+    if (rc != BB_OK) { msg = err; return rc; }
+    std::printf("Total: %llu  Trimmed: %llu  Trimmed split: %llu  Failed trims: %llu reads\n", static_cast<unsigned long long>(counts[0]),
+                static_cast<unsigned long long>(counts[1]), static_cast<unsigned long long>(counts[2]), static_cast<unsigned long long>(counts[3]));
+    return BB_OK;
+}
+
+// `barbell kit` (use_kit.rs:11-109): annotate -> inspect -> filter -> trim with fixed file names in the output folder
+int run_kit(const Args& a) {
+    char err[1024] = {0}, name[64] = {0}, ranges[256] = {0};
+    int dbl = 0;
+    ::mkdir(a.output.c_str(), 0755);
+    if (bb_kit_info(a.kit.c_str(), name, sizeof name, ranges, sizeof ranges, &dbl, err, sizeof err) != BB_OK) {
+        std::fprintf(stderr, "%s\n", err);               // get_kit_info panics on an unknown kit (kits.rs:704)
+        return 101;
+    }
+    std::printf("\nKit info\nKit name: %s\nKit type: %s\n", name, a.maximize ? "Maximize" : "Safe");
+    std::string r(ranges);
+    for (size_t p = 0; p < r.size();) { size_t q = r.find("; ", p); if (q == std::string::npos) q = r.size(); std::printf("Barcodes: %s\n", r.substr(p, q - p).c_str()); p = q + 2; }
+    std::printf("\nAnnotating reads...\n");
+    const std::string anno = a.output + "/annotation.tsv", filtered = a.output + "/filtered.tsv";
+    int rc = run_annotate(a, anno);
+    if (rc != BB_OK) { std::printf("Demultiplexing failed: annotate stage\n"); return 0; }
+    std::printf("\nTop 10 most common patterns\n");
+    rc = bb_inspect(anno.c_str(), 10, (a.output + "/pattern_per_read.tsv").c_str(), 250, err, sizeof err);
+    if (rc != BB_OK) { std::printf("Demultiplexing failed: %s\n", err); return 0; }
+    std::printf("Want to see more patterns? Run: `barbell inspect %s/annotation.tsv -n 100`\n", a.output.c_str());
+    std::printf("\nFiltering reads...\n");
+    const char* const* pats = nullptr; int32_t n_pats = 0;
+    bb_kit_filter_patterns(dbl, a.maximize, &pats, &n_pats);
+    uint64_t counts[3] = {0, 0, 0};
+    rc = bb_filter(anno.c_str(), filtered.c_str(), nullptr, pats, n_pats, counts, err, sizeof err);
+    if (rc != BB_OK) { std::printf("Demultiplexing failed: %s\n", err); return 0; }
+    std::printf("Total: %llu  Kept: %llu  Dropped: %llu reads\n", static_cast<unsigned long long>(counts[0]),
+                static_cast<unsigned long long>(counts[1]), static_cast<unsigned long long>(counts[2]));
+    std::printf("\nTrimming reads...\n");
+    std::string msg;
+    rc = run_trim(filtered, a.input, a.output, trim_opts_from(a, true), msg);
+    if (rc != BB_OK) { std::printf("Demultiplexing failed: %s\n", msg.c_str()); return 0; }
+    std::printf("\nDone!\n");
+    return 0;
+}
+
 }  // namespace
 
 int main(int argc, char** argv) {
@@ -354,11 +413,26 @@ int main(int argc, char** argv) {
         if (run_annotate(a, a.output) == BB_OK) std::printf("Annotation complete!\n");
         return 0;                                                   // the reference exits 0 even on errors (bin/main.rs:301-304)
     }
-    // kit: annotate -> <out>/annotation.tsv (use_kit.rs:43-48); the later stages are not part of this build
+    if (a.cmd == "filter") return run_filter_cmd(a);
+    if (a.cmd == "trim") {
+        std::printf("Starting trimming...\n");
+        if (a.input.size() != 1 || !a.output_given) usage("trim needs -i <filtered.tsv> -r <fastq>... -o <folder>");
+        if (!a.only_side.empty() && a.only_side != "left" && a.only_side != "right") usage("--only-side takes left or right");
+        if (!a.only_side.empty() && a.sort_labels) usage("--only-side cannot be used with --sort-labels");
+        std::string msg;
+        if (run_trim(a.input[0], a.reads, a.output, trim_opts_from(a, false), msg) == BB_OK) std::printf("Trimming complete!\n");
+        else std::printf("Trimming failed: %s\n", msg.c_str());
+        return 0;
+    }
+    if (a.cmd == "inspect") {
+        std::printf("Inspecting...\n");
+        if (a.input.size() != 1) usage("inspect needs -i <annotation.tsv>");
+        char err[1024] = {0};
+        if (bb_inspect(a.input[0].c_str(), a.top_n, a.read_pattern_out.empty() ? nullptr : a.read_pattern_out.c_str(), a.bucket_size, err, sizeof err) == BB_OK)
+            std::printf("Inspection complete!\n");
+        else std::printf("Inspection failed: %s\n", err);
+        return 0;
+    }
     if (a.kit.empty()) usage("kit needs -k <KIT>");
-    ::mkdir(a.output.c_str(), 0755);
-    std::printf("Running annotate...\n");
-    if (run_annotate(a, a.output + "/annotation.tsv") == BB_OK)
-        std::printf("Annotation complete: %s/annotation.tsv (inspect / filter / trim are not part of the B200 build)\n", a.output.c_str());
-    return 0;
+    return run_kit(a);
 }

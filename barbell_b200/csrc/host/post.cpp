@@ -1,0 +1,733 @@
+// The stages that consume annotation.tsv: `filter`, `inspect` and `trim`, host-side C++ behind the
+// C ABI so that `barbell kit` runs the reference's whole pipeline (src/kits/use_kit.rs:11-109).  They are sequential
+// text/IO stages in the reference as well (single-threaded csv + serde); nothing here touches the GPU.
+//
+//   pattern DSL + matching   src/filter/pattern.rs:8-383      parse_pattern(), match_pattern()
+//   filter                   src/filter/filter.rs:10-214       bb_filter()
+//   inspect                  src/inspect/inspect.rs:9-208      bb_inspect()
+//   trim                     src/trim/trim.rs:31-480           bb_trim()
+//   kit pattern sets         src/kits/kits.rs:175-236          bb_kit_filter_patterns()
+#include <sys/stat.h>
+#include <unistd.h>
+#include <zlib.h>
+
+#include <algorithm>
+#include <cerrno>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../../include/barbell_b200.h"
+#include "fastq.hpp"
+
+namespace {
+
+enum { FTAG = 0, RTAG = 1, FFLANK = 2, RFLANK = 3 };
+const char* const kTypeNames[] = {"Ftag", "Rtag", "Fflank", "Rflank"};
+
+struct Cut { uint64_t group_id; bool after; };   // pattern.rs:8-19: After = cut at match end (">>"), Before = at match start ("<<")
+
+// One annotation.tsv row (BarbellMatch, searcher.rs:31-64)
+struct Row {
+    std::string read_id, label;
+    uint64_t read_len = 0, read_start_bar = 0, read_end_bar = 0, read_start_flank = 0, read_end_flank = 0, bar_start = 0, bar_end = 0;
+    int64_t rel_dist_to_end = 0;
+    int match_type = FTAG, strand = 0;
+    int32_t flank_cost = 0, barcode_cost = 0;
+    std::vector<std::pair<Cut, uint64_t>> cuts;    // (cut, index of the annotation inside its read)
+};
+
+const char* const kHeader[15] = {"read_id", "read_len", "rel_dist_to_end", "read_start_bar", "read_end_bar", "read_start_flank", "read_end_flank",
+                                 "bar_start", "bar_end", "match_type", "flank_cost", "barcode_cost", "label", "strand", "cuts"};
+
+void set_err(char* err, size_t errlen, const std::string& msg) { if (err && errlen) std::snprintf(err, errlen, "%s", msg.c_str()); }
+
+std::string trim_ws(const std::string& s) {
+    size_t a = 0, b = s.size();
+    while (a < b && std::isspace(static_cast<unsigned char>(s[a]))) a++;
+    while (b > a && std::isspace(static_cast<unsigned char>(s[b - 1]))) b--;
+    return s.substr(a, b - a);
+}
+
+bool parse_u64(const std::string& s, uint64_t& v) {
+    if (s.empty()) return false;
+    size_t i = s[0] == '+' ? 1 : 0;
+    if (i >= s.size()) return false;
+    v = 0;
+    for (; i < s.size(); i++) { if (s[i] < '0' || s[i] > '9') return false; v = v * 10 + static_cast<uint64_t>(s[i] - '0'); }
+    return true;
+}
+bool parse_i64(const std::string& s, int64_t& v) {
+    if (s.empty()) return false;
+    const bool neg = s[0] == '-';
+    uint64_t u;
+    if (!parse_u64(neg ? s.substr(1) : s, u)) return false;
+    v = neg ? -static_cast<int64_t>(u) : static_cast<int64_t>(u);
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// TSV reader / writer (csv crate, tab delimiter, header row; fields of this format never need quoting)
+// ---------------------------------------------------------------------------------------------------------------
+class TsvReader {
+  public:
+    bool open(const std::string& path, std::string& err) {
+        f_ = std::fopen(path.c_str(), "r");
+        if (!f_) { err = path + ": " + std::strerror(errno); return false; }
+        std::string line;
+        if (!getline(line)) { empty_ = true; return true; }           // 0-byte file: a run without hits (annotator.rs:20-24)
+        std::vector<std::string> h = split(line);
+        for (int c = 0; c < 15; c++) {
+            col_[c] = -1;
+            for (size_t i = 0; i < h.size(); i++) if (h[i] == kHeader[c]) col_[c] = static_cast<int>(i);
+            if (col_[c] < 0) { err = "CSV deserialize error: missing field `" + std::string(kHeader[c]) + "`"; return false; }
+        }
+        return true;
+    }
+    ~TsvReader() { if (f_) std::fclose(f_); }
+    // 1 = row, 0 = end, -1 = error
+    int next(Row& r, std::string& err) {
+        if (empty_) return 0;
+        std::string line;
+        for (;;) {
+            if (!getline(line)) return 0;
+            if (!line.empty()) break;
+        }
+        lineno_++;
+        const std::vector<std::string> f = split(line);
+        auto get = [&](int c) -> const std::string& { static const std::string none; return col_[c] < static_cast<int>(f.size()) ? f[col_[c]] : none; };
+        auto bad = [&](int c) { err = "CSV deserialize error: record " + std::to_string(lineno_) + ": field `" + kHeader[c] + "`: invalid value `" + get(c) + "`"; return -1; };
+        r = Row();
+        r.read_id = get(0);
+        if (!parse_u64(get(1), r.read_len)) return bad(1);
+        if (!parse_i64(get(2), r.rel_dist_to_end)) return bad(2);
+        uint64_t* u[] = {&r.read_start_bar, &r.read_end_bar, &r.read_start_flank, &r.read_end_flank, &r.bar_start, &r.bar_end};
+        for (int c = 3; c <= 8; c++) if (!parse_u64(get(c), *u[c - 3])) return bad(c);
+        r.match_type = -1;
+        for (int t = 0; t < 4; t++) if (get(9) == kTypeNames[t]) r.match_type = t;
+        if (r.match_type < 0) return bad(9);
+        int64_t v;
+        if (!parse_i64(get(10), v)) return bad(10);
+        r.flank_cost = static_cast<int32_t>(v);
+        if (!parse_i64(get(11), v)) return bad(11);
+        r.barcode_cost = static_cast<int32_t>(v);
+        r.label = get(12);
+        if (get(13) == "Fwd") r.strand = 0; else if (get(13) == "Rc") r.strand = 1; else { err = "Invalid strand: " + get(13); return -1; }
+        // cuts: "After(0):1,Before(0):2" (searcher.rs:105-142)
+        const std::string& cs = get(14);
+        size_t p = 0;
+        while (p < cs.size()) {
+            size_t q = cs.find(',', p);
+            if (q == std::string::npos) q = cs.size();
+            const std::string part = cs.substr(p, q - p);
+            const size_t colon = part.find(':');
+            if (colon == std::string::npos) { err = "Invalid cut format: missing position part"; return -1; }
+            std::string cut_str = trim_ws(part.substr(0, colon)), pos_str = part.substr(colon + 1);
+            const size_t colon2 = pos_str.find(':');
+            if (colon2 != std::string::npos) pos_str = pos_str.substr(0, colon2);
+            Cut cut{0, false};
+            bool ok = false;
+            if (cut_str.rfind("Before(", 0) == 0 && cut_str.back() == ')') { cut.after = false; ok = parse_u64(cut_str.substr(7, cut_str.size() - 8), cut.group_id); }
+            else if (cut_str.rfind("After(", 0) == 0 && cut_str.back() == ')') { cut.after = true; ok = parse_u64(cut_str.substr(6, cut_str.size() - 7), cut.group_id); }
+            if (!ok) { err = "Invalid cut string: " + cut_str; return -1; }
+            uint64_t pos;
+            if (!parse_u64(pos_str, pos)) { err = "Invalid position: " + pos_str; return -1; }
+            r.cuts.push_back({cut, pos});
+            p = q + 1;
+        }
+        return 1;
+    }
+
+  private:
+    bool getline(std::string& out) {
+        out.clear();
+        char buf[4096];
+        bool any = false;
+        while (std::fgets(buf, sizeof buf, f_)) {
+            any = true;
+            const size_t n = std::strlen(buf);
+            out.append(buf, n);
+            if (n && buf[n - 1] == '\n') break;
+        }
+        while (!out.empty() && (out.back() == '\n' || out.back() == '\r')) out.pop_back();
+        return any;
+    }
+    static std::vector<std::string> split(const std::string& line) {
+        std::vector<std::string> f;
+        size_t p = 0;
+        for (;;) {
+            const size_t q = line.find('\t', p);
+            std::string v = line.substr(p, q == std::string::npos ? std::string::npos : q - p);
+            if (v.size() >= 2 && v.front() == '"' && v.back() == '"') v = v.substr(1, v.size() - 2);
+            f.push_back(v);
+            if (q == std::string::npos) break;
+            p = q + 1;
+        }
+        return f;
+    }
+    FILE* f_ = nullptr;
+    int col_[15];
+    bool empty_ = false;
+    uint64_t lineno_ = 0;
+};
+
+class TsvWriter {
+  public:
+    bool open(const std::string& path, std::string& err) {
+        f_ = std::fopen(path.c_str(), "w");
+        if (!f_) { err = path + ": " + std::strerror(errno); return false; }
+        std::setvbuf(f_, nullptr, _IOFBF, 1 << 20);
+        return true;
+    }
+    ~TsvWriter() { if (f_) std::fclose(f_); }
+    void write(const Row& r) {
+        if (!header_) {               // the csv writer emits the header with the first serialised row
+            for (int c = 0; c < 15; c++) std::fprintf(f_, "%s%s", kHeader[c], c == 14 ? "\n" : "\t");
+            header_ = true;
+        }
+        std::fprintf(f_, "%s\t%llu\t%lld\t%llu\t%llu\t%llu\t%llu\t%llu\t%llu\t%s\t%d\t%d\t%s\t%s\t", r.read_id.c_str(),
+                     static_cast<unsigned long long>(r.read_len), static_cast<long long>(r.rel_dist_to_end),
+                     static_cast<unsigned long long>(r.read_start_bar), static_cast<unsigned long long>(r.read_end_bar),
+                     static_cast<unsigned long long>(r.read_start_flank), static_cast<unsigned long long>(r.read_end_flank),
+                     static_cast<unsigned long long>(r.bar_start), static_cast<unsigned long long>(r.bar_end), kTypeNames[r.match_type],
+                     r.flank_cost, r.barcode_cost, r.label.c_str(), r.strand ? "Rc" : "Fwd");
+        for (size_t i = 0; i < r.cuts.size(); i++)
+            std::fprintf(f_, "%s%s(%llu):%llu", i ? "," : "", r.cuts[i].first.after ? "After" : "Before",
+                         static_cast<unsigned long long>(r.cuts[i].first.group_id), static_cast<unsigned long long>(r.cuts[i].second));
+        std::fputc('\n', f_);
+    }
+    bool close() { const bool ok = !f_ || std::fclose(f_) == 0; f_ = nullptr; return ok; }
+
+  private:
+    FILE* f_ = nullptr;
+    bool header_ = false;
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// pattern DSL (pattern.rs:242-383) and matching (pattern.rs:100-240)
+// ---------------------------------------------------------------------------------------------------------------
+enum RelPos { REL_NONE = 0, REL_LEFT, REL_RIGHT, REL_PREV_LEFT };
+
+struct PatternElement {
+    int match_type = FTAG;
+    int orientation = -1;                 // -1 any, 0 Fwd, 1 Rc
+    bool has_label = false; std::string label;
+    bool has_placeholder = false; uint64_t placeholder = 0;
+    int64_t range0 = 0, range1 = 0;
+    RelPos relative_to = REL_NONE;
+    std::vector<Cut> cuts;
+};
+struct Pattern { std::vector<PatternElement> elements; };
+
+bool parse_range(std::string s, int64_t& a, int64_t& b) {
+    size_t i = 0, j = s.size();
+    while (i < j && (s[i] == '(' || s[i] == ')')) i++;
+    while (j > i && (s[j - 1] == '(' || s[j - 1] == ')')) j--;
+    s = s.substr(i, j - i);
+    std::vector<std::string> parts;
+    size_t p = 0;
+    for (;;) {
+        const size_t q = s.find("..", p);
+        parts.push_back(s.substr(p, q == std::string::npos ? std::string::npos : q - p));
+        if (q == std::string::npos) break;
+        p = q + 2;
+    }
+    if (parts.size() != 2) return false;
+    return parse_i64(trim_ws(parts[0]), a) && parse_i64(trim_ws(parts[1]), b);
+}
+
+bool parse_position(const std::string& pos_str, RelPos& rel, int64_t& a, int64_t& b) {
+    if (std::count(pos_str.begin(), pos_str.end(), '(') != 1) return false;
+    const size_t paren = pos_str.find('(');
+    std::string name = pos_str.substr(0, paren);
+    size_t i = 0;
+    while (i < name.size() && name[i] == '@') i++;
+    name = name.substr(i);
+    if (name == "left") rel = REL_LEFT; else if (name == "right") rel = REL_RIGHT; else if (name == "prev_left") rel = REL_PREV_LEFT; else return false;
+    return parse_range(trim_ws(pos_str.substr(paren)), a, b);
+}
+
+// 1 = parsed, 0 = not an element (dropped, like the reference's filter_map), -1 = hard error (the reference panics)
+int parse_element(const std::string& element_str, PatternElement& el, std::string& err) {
+    const size_t br = element_str.find('[');
+    if (br == std::string::npos) return 0;
+    const std::string type = trim_ws(element_str.substr(0, br));
+    if (type == "Ftag") el.match_type = FTAG; else if (type == "Rtag") el.match_type = RTAG;
+    else if (type == "Fflank") el.match_type = FFLANK; else if (type == "Rflank") el.match_type = RFLANK;
+    else if (type == "Flank" || type == "flank") { err = "Flank is not valid, use Fflank or Rflank"; return -1; }
+    else return 0;
+    std::string params = element_str.substr(br + 1);
+    while (!params.empty() && params.back() == ']') params.pop_back();
+    size_t p = 0;
+    for (;;) {
+        const size_t q = params.find(',', p);
+        const std::string param = trim_ws(params.substr(p, q == std::string::npos ? std::string::npos : q - p));
+        if (param == "fw") el.orientation = 0;
+        else if (param == "rc") el.orientation = 1;
+        else if (!param.empty() && param[0] == '@') {
+            RelPos rel; int64_t a, b;
+            if (parse_position(param, rel, a, b)) { el.relative_to = rel; el.range0 = a; el.range1 = b; }
+        } else if (!param.empty() && param[0] == '?') {
+            uint64_t n;
+            if (parse_u64(param.substr(1), n)) { el.has_placeholder = true; el.placeholder = n; }
+        } else if (!param.empty() && (param[0] == '>' || param[0] == '<')) {
+            if (param.size() < 2) { err = "cut marker `" + param + "` is too short (use >> or <<)"; return -1; }   // the reference panics on the slice
+            const std::string pre = param.substr(0, 2);
+            uint64_t id = 0;
+            const bool id_ok = param.size() == 2 || parse_u64(param.substr(2), id);
+            if (id_ok && pre == ">>") el.cuts.push_back({id, true});
+            else if (id_ok && pre == "<<") el.cuts.push_back({id, false});
+        } else if (param == "*") {
+        } else {
+            std::string l = param;
+            while (!l.empty() && l.front() == '"') l.erase(l.begin());
+            while (!l.empty() && l.back() == '"') l.pop_back();
+            el.has_label = true; el.label = l;
+        }
+        if (q == std::string::npos) break;
+        p = q + 1;
+    }
+    return 1;
+}
+
+bool parse_pattern(const std::string& pattern_str, Pattern& pat, std::string& err) {
+    pat.elements.clear();
+    size_t p = 0, user_elems = 0;
+    for (;;) {
+        const size_t q = pattern_str.find("__", p);
+        PatternElement el;
+        const int rc = parse_element(trim_ws(pattern_str.substr(p, q == std::string::npos ? std::string::npos : q - p)), el, err);
+        if (rc < 0) return false;
+        if (rc > 0) pat.elements.push_back(el);
+        user_elems++;
+        if (q == std::string::npos) break;
+        p = q + 2;
+    }
+    if (user_elems != pat.elements.size()) { err = "Pattern parse error for: \"" + pattern_str + "\""; return false; }   // basic_verify
+    return true;
+}
+
+std::string describe_pattern(const Pattern& pat) {         // canonical text form (tests compare it with the reference's structs)
+    std::string s;
+    for (size_t i = 0; i < pat.elements.size(); i++) {
+        const PatternElement& e = pat.elements[i];
+        if (i) s += "__";
+        s += kTypeNames[e.match_type];
+        s += "[ori=" + std::string(e.orientation < 0 ? "any" : e.orientation ? "rc" : "fw");
+        s += ",label=" + (e.has_label ? e.label : std::string("*"));
+        s += ",ph=" + (e.has_placeholder ? std::to_string(e.placeholder) : std::string("-"));
+        s += ",rel=" + std::string(e.relative_to == REL_LEFT ? "left" : e.relative_to == REL_RIGHT ? "right" : e.relative_to == REL_PREV_LEFT ? "prev_left" : "none");
+        s += ",range=" + std::to_string(e.range0) + ".." + std::to_string(e.range1);
+        s += ",cuts=";
+        for (size_t c = 0; c < e.cuts.size(); c++) s += (c ? "|" : "") + std::string(e.cuts[c].after ? "After(" : "Before(") + std::to_string(e.cuts[c].group_id) + ")";
+        s += "]";
+    }
+    return s;
+}
+
+bool matches_element(const Row& m, const PatternElement& el, bool has_prev, int64_t prev_end, std::map<uint64_t, std::string>& labels) {
+    // check_match_type_and_label
+    if (m.match_type != el.match_type) return false;
+    if ((el.match_type == FTAG || el.match_type == RTAG) && el.has_label) {
+        if (!el.label.empty() && el.label[0] == '~') { if (m.label.find(el.label.substr(1)) == std::string::npos) return false; }
+        else if (el.label != m.label) return false;
+    }
+    // check_placeholder
+    if (el.has_placeholder) {
+        auto it = labels.find(el.placeholder);
+        if (it != labels.end()) { if (m.label != it->second) return false; }
+        else labels[el.placeholder] = m.label;
+    }
+    // check_orientation
+    if (el.orientation >= 0 && el.orientation != m.strand) return false;
+    // check_relative_position
+    const int64_t m_start = static_cast<int64_t>(m.read_start_bar), m_end = static_cast<int64_t>(m.read_end_bar), seq_len = static_cast<int64_t>(m.read_len);
+    switch (el.relative_to) {
+        case REL_LEFT: if (m_start < el.range0 || m_start > el.range1) return false; break;
+        case REL_RIGHT: if (m_end < seq_len - el.range1 || m_end > seq_len - el.range0) return false; break;
+        case REL_PREV_LEFT: if (has_prev && (m_start < prev_end + el.range0 || m_start > prev_end + el.range1)) return false; break;
+        case REL_NONE: break;
+    }
+    return true;
+}
+
+// pattern.rs:205-240: element q must match annotation q; returns the (annotation index, cut) list of the pattern
+bool match_pattern(const std::vector<Row>& matches, const Pattern& pat, std::vector<std::pair<size_t, Cut>>& cut_positions) {
+    cut_positions.clear();
+    if (matches.size() < pat.elements.size()) return false;
+    bool has_prev = false; int64_t prev_end = 0;
+    std::map<uint64_t, std::string> labels;
+    size_t idx = 0;
+    for (const PatternElement& el : pat.elements) {
+        if (idx >= matches.size()) { cut_positions.clear(); return false; }
+        const Row& m = matches[idx];
+        if (!matches_element(m, el, has_prev, prev_end, labels)) { cut_positions.clear(); return false; }
+        for (const Cut& c : el.cuts) cut_positions.push_back({idx, c});
+        has_prev = true; prev_end = static_cast<int64_t>(m.read_end_bar);
+        idx++;
+    }
+    return true;
+}
+
+// filter.rs:183-214: the longest matching pattern supplies the cuts; the read passes when that pattern covers every annotation
+bool check_filter_pass(std::vector<Row>& annotations, const std::vector<Pattern>& patterns) {
+    size_t max_matches = 0;
+    std::vector<std::pair<size_t, Cut>> best, cur;
+    for (const Pattern& p : patterns)
+        if (match_pattern(annotations, p, cur) && p.elements.size() > max_matches) { max_matches = p.elements.size(); best = cur; }
+    if (max_matches > 0)
+        for (const auto& pc : best) annotations[pc.first].cuts.push_back({pc.second, pc.first});
+    return max_matches == annotations.size();
+}
+
+// kits.rs:175-236
+const char* const kSingleSafe[] = {
+    "Ftag[fw, *, @left(0..250), >>]",
+    "Ftag[fw, ?1, @left(0..250)]__Ftag[fw, ?1, @prev_left(0..250), >>]",
+};
+const char* const kSingleMax[] = {
+    "Ftag[fw, *, @left(0..250), >>]",
+    "Ftag[fw, ?1, @left(0..250)]__Ftag[fw, ?1, @prev_left(0..250), >>]",
+    "Ftag[fw, *, @left(0..250)]__Ftag[fw, *, @prev_left(0..250), >>]",
+    "Ftag[fw, *, @left(0..250), >>]__Ftag[<<, fw, *, @right(0..250)]",
+    "Ftag[fw, *, @left(0..250)]__Ftag[fw, *, @prev_left(0..250), >>]__Ftag[<<, fw, *, @right(0..250)]",
+};
+const char* const kDoubleSafe[] = {
+    "Ftag[fw, *, @left(0..250), >>]",
+    "Ftag[<<, rc, *, @right(0..250)]",
+    "Ftag[fw, ?1, @left(0..250), >>]__Ftag[<<, rc, ?1, @right(0..250)]",
+};
+const char* const kDoubleMax[] = {
+    "Ftag[fw, *, @left(0..250), >>]",
+    "Ftag[<<, rc, *, @right(0..250)]",
+    "Ftag[fw, ?1, @left(0..250), >>]__Ftag[<<, rc, ?1, @right(0..250)]",
+    "Ftag[fw, *, @left(0..250)]__Ftag[fw, ?1, @prev_left(0..250), >>]__Ftag[<<, rc, ?1, @right(0..250)]",
+    "Ftag[fw, *, @left(0..250), >>]__Fflank[<<, rc, *, @right(0..250)]",
+    "Fflank[fw, *, @left(0..250), >>]__Ftag[<<, rc, *, @right(0..250)]",
+    "Ftag[fw, *, @left(0..250)]__Ftag[fw, *, @prev_left(0..250), >>]",
+    "Ftag[fw, ?1, @left(0..250), >>]__Ftag[<<, fw, ?1, @right(0..250)]__Ftag[rc, *, @right(0..250)]",
+    "Ftag[fw, *, @left(0..250)]__Ftag[rc, *, @prev_left(0..250)]__Ftag[fw, ?1, @prev_left(0..250), >>]__Ftag[<<, rc, ?1, @right(0..250)]",
+};
+
+// groups of consecutive rows with the same read_id (filter.rs:50-82, inspect.rs:159-178)
+template <class F>
+int for_each_read(const char* path, F&& fn, std::string& err) {
+    TsvReader rd;
+    if (!rd.open(path, err)) return BB_ERR_IO;
+    std::vector<Row> group;
+    Row r;
+    for (;;) {
+        const int rc = rd.next(r, err);
+        if (rc < 0) return BB_ERR_INVALID;
+        if (rc == 0) break;
+        if (!group.empty() && group.front().read_id != r.read_id) { fn(group); group.clear(); }
+        group.push_back(std::move(r));
+    }
+    if (!group.empty()) fn(group);
+    return BB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// inspect (inspect.rs:9-117)
+// ---------------------------------------------------------------------------------------------------------------
+uint64_t bucket_position(uint64_t pos, uint64_t bucket) { return ((pos ? pos - 1 : 0) / bucket) * bucket; }
+uint64_t sat_sub(uint64_t a, uint64_t b) { return a > b ? a - b : 0; }
+
+std::string group_structure(const std::vector<Row>& group, uint64_t bucket) {
+    std::string out;
+    bool has_prev = false; uint64_t prev_end = 0;
+    for (const Row& a : group) {
+        const uint64_t start = a.read_start_bar, end = a.read_end_bar;
+        char tag[96];
+        auto right_tag = [&] {
+            std::snprintf(tag, sizeof tag, "@right(%llu..%llu)", static_cast<unsigned long long>(bucket_position(sat_sub(a.read_len, end), bucket)),
+                          static_cast<unsigned long long>(bucket_position(sat_sub(a.read_len, start), bucket) + bucket));
+        };
+        if (has_prev) {
+            const uint64_t d_prev = sat_sub(start, prev_end), d_right = sat_sub(a.read_len, end);
+            if (d_prev <= d_right) {
+                const uint64_t g0 = bucket_position(d_prev, bucket);
+                std::snprintf(tag, sizeof tag, "@prev_left(%llu..%llu)", static_cast<unsigned long long>(g0), static_cast<unsigned long long>(g0 + bucket));
+            } else right_tag();
+        } else if (a.rel_dist_to_end > 0) {
+            const uint64_t s0 = bucket_position(start, bucket);
+            std::snprintf(tag, sizeof tag, "@left(%llu..%llu)", static_cast<unsigned long long>(s0), static_cast<unsigned long long>(s0 + bucket));
+        } else right_tag();
+        const char* cut = a.cuts.empty() ? "" : (a.strand == 0 ? ", <<" : ", >>");
+        if (!out.empty()) out += "__";
+        out += std::string(kTypeNames[a.match_type]) + "[" + (a.strand == 0 ? "fw" : "rc") + ", *" + cut + ", " + tag + "]";
+        has_prev = true; prev_end = end;
+    }
+    return out;
+}
+
+std::string colorize(std::string s) {                       // inspect.rs:120-131 (truecolor escapes of the `colored` crate)
+    const struct { const char* word; int r, g, b; } C[] = {{"Fflank", 255, 182, 193}, {"Ftag", 231, 84, 128}, {"Rflank", 173, 216, 230}, {"Rtag", 0, 0, 139}};
+    for (const auto& c : C) {
+        char rep[64];
+        std::snprintf(rep, sizeof rep, "\x1b[38;2;%d;%d;%dm%s\x1b[0m", c.r, c.g, c.b, c.word);
+        size_t p = 0;
+        while ((p = s.find(c.word, p)) != std::string::npos) { s.replace(p, std::strlen(c.word), rep); p += std::strlen(rep); }
+    }
+    return s;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// trim (trim.rs:31-315)
+// ---------------------------------------------------------------------------------------------------------------
+std::string create_label(const bb_trim_opts& o, const std::vector<const Row*>& annos) {       // trim.rs:56-106
+    if (!o.add_labels) return "none";
+    std::vector<std::string> parts;
+    for (const Row* m : annos) {
+        if (!o.add_flank && m->label.find("flank") != std::string::npos) continue;
+        std::string s = m->label;
+        if (o.add_orientation) s += m->strand == 0 ? "_fw" : "_rc";
+        parts.push_back(s);
+    }
+    if (parts.empty()) return "none";
+    if (o.sort_labels) std::sort(parts.begin(), parts.end());
+    else if (o.only_side == 1) return parts.front();
+    else if (o.only_side == 2) return parts.back();
+    std::string out;
+    for (size_t i = 0; i < parts.size(); i++) out += (i ? "__" : "") + parts[i];
+    return out;
+}
+
+struct Slice { uint64_t start, end; std::vector<const Row*> annos; };
+
+// trim.rs:127-248.  The reference collects the cut groups in a HashMap and orders them with a stable sort on the first
+// member's flank start; groups that tie on that key keep HashMap order there (arbitrary) and group-id order here.
+std::vector<Slice> preprocess_cuts(const std::vector<Row>& annotations, uint64_t seq_len) {
+    struct Member { uint64_t start, end; const Cut* cut; const Row* anno; };
+    std::map<uint64_t, std::vector<Member>> groups;
+    for (const Row& a : annotations)
+        for (const auto& c : a.cuts) groups[c.first.group_id].push_back({a.read_start_flank, a.read_end_flank, &c.first, &a});
+    std::vector<const std::vector<Member>*> sorted;
+    for (const auto& kv : groups) sorted.push_back(&kv.second);
+    std::stable_sort(sorted.begin(), sorted.end(), [](const std::vector<Member>* a, const std::vector<Member>* b) { return a->front().start < b->front().start; });
+    std::vector<Slice> slices;
+    for (size_t i = 0; i < sorted.size(); i++) {
+        const std::vector<Member>& g = *sorted[i];
+        if (g.size() == 2) {
+            const uint64_t start = g[0].cut->after ? g[0].end : g[0].start;
+            const uint64_t end = g[1].cut->after ? g[1].end : g[1].start;
+            slices.push_back({start, end, {g[0].anno, g[1].anno}});
+        } else if (g.size() == 1) {
+            const Member& m = g[0];
+            if (!m.cut->after) {                       // Before: look left for the start
+                uint64_t s = 0; const Row* left = nullptr;
+                if (i > 0) {
+                    const std::vector<Member>& pg = *sorted[i - 1];
+                    size_t best = 0;                    // max_by_key keeps the LAST maximum
+                    for (size_t q = 0; q < pg.size(); q++) if (pg[q].end >= pg[best].end) best = q;
+                    s = pg[best].end; left = pg[best].anno;
+                }
+                Slice sl{s, m.start, {}};
+                if (left) sl.annos.push_back(left);
+                sl.annos.push_back(m.anno);
+                slices.push_back(sl);
+            } else {                                   // After: look right for the end
+                uint64_t e = seq_len; const Row* right = nullptr;
+                if (i + 1 < sorted.size()) {
+                    const std::vector<Member>& ng = *sorted[i + 1];
+                    size_t best = 0;                    // min_by_key keeps the FIRST minimum
+                    for (size_t q = 1; q < ng.size(); q++) if (ng[q].start < ng[best].start) best = q;
+                    e = ng[best].start; right = ng[best].anno;
+                }
+                Slice sl{m.end, e, {m.anno}};
+                if (right) sl.annos.push_back(right);
+                slices.push_back(sl);
+            }
+        }
+    }
+    return slices;
+}
+
+struct RcTable {                                        // trim.rs:486-530
+    uint8_t t[256];
+    RcTable() {
+        for (int i = 0; i < 256; i++) t[i] = static_cast<uint8_t>(i);
+        const char *a = "ACTGRYSWKMBDHVNX", *b = "TGACYRSWMKVHDBNX";
+        for (int i = 0; a[i]; i++) { t[static_cast<uint8_t>(a[i])] = static_cast<uint8_t>(b[i]); t[static_cast<uint8_t>(a[i] | 0x20)] = static_cast<uint8_t>(b[i] | 0x20); }
+    }
+};
+const RcTable kRc;
+
+struct TrimmedRead { std::string seq, qual, label, suffix; };
+
+// trim.rs:250-300
+std::vector<TrimmedRead> process_read_and_anno(const char* seq, const char* qual, uint64_t seq_len, const std::vector<Row>& annotations, const bb_trim_opts& o) {
+    std::vector<TrimmedRead> out;
+    const std::vector<Slice> slices = preprocess_cuts(annotations, seq_len);
+    for (size_t sc = 0; sc < slices.size(); sc++) {
+        const Slice& s = slices[sc];
+        if (s.start >= s.end) continue;
+        TrimmedRead t;
+        if (o.skip_trim) { t.seq.assign(seq, seq_len); t.qual.assign(qual, seq_len); }
+        else {
+            const uint64_t e = std::min<uint64_t>(s.end, seq_len), b = std::min<uint64_t>(s.start, e);   // the reference would panic on an out-of-range slice
+            t.seq.assign(seq + b, e - b); t.qual.assign(qual + b, e - b);
+        }
+        bool flip = false;
+        if (o.flip) for (const Row* a : s.annos) if (a->match_type == FTAG && a->strand == 1) flip = true;      // should_flip
+        if (flip) {
+            std::reverse(t.seq.begin(), t.seq.end());
+            for (char& c : t.seq) c = static_cast<char>(kRc.t[static_cast<uint8_t>(c)]);
+            std::reverse(t.qual.begin(), t.qual.end());
+        }
+        t.label = create_label(o, s.annos);
+        t.suffix = sc == 0 ? "" : "_" + std::to_string(sc);
+        out.push_back(std::move(t));
+    }
+    return out;
+}
+
+class FastqOut {                                         // plain or gzip writer per label (trim.rs:420-445)
+  public:
+    bool open(const std::string& path, bool gz, std::string& err) {
+        gz_mode_ = gz;
+        if (gz) { g_ = gzopen(path.c_str(), "wb"); if (!g_) { err = "Failed to create output file '" + path + "': " + std::strerror(errno); return false; } gzbuffer(g_, 1 << 18); }
+        else { f_ = std::fopen(path.c_str(), "w"); if (!f_) { err = "Failed to create output file '" + path + "': " + std::strerror(errno) + (errno == EMFILE ? "\nTry setting ulimit higher: \"ulimit -n 65000\"" : ""); return false; } std::setvbuf(f_, nullptr, _IOFBF, 1 << 18); }
+        return true;
+    }
+    void write(const std::string& s) { if (gz_mode_) gzwrite(g_, s.data(), static_cast<unsigned>(s.size())); else std::fwrite(s.data(), 1, s.size(), f_); }
+    ~FastqOut() { if (g_) gzclose(g_); if (f_) std::fclose(f_); }
+  private:
+    bool gz_mode_ = false; gzFile g_ = nullptr; FILE* f_ = nullptr;
+};
+
+}  // namespace
+
+extern "C" {
+
+int bb_kit_filter_patterns(int double_label, int maximize, const char* const** patterns, int32_t* n) {
+    if (!patterns || !n) return BB_ERR_INVALID;
+    if (double_label) { *patterns = maximize ? kDoubleMax : kDoubleSafe; *n = maximize ? 9 : 3; }
+    else { *patterns = maximize ? kSingleMax : kSingleSafe; *n = maximize ? 5 : 2; }
+    return BB_OK;
+}
+
+int bb_pattern_parse(const char* pattern, char* canonical, size_t canonical_len, char* err, size_t errlen) {
+    if (!pattern) return BB_ERR_INVALID;
+    Pattern p; std::string e;
+    if (!parse_pattern(pattern, p, e)) { set_err(err, errlen, e); return BB_ERR_INVALID; }
+    if (canonical && canonical_len) std::snprintf(canonical, canonical_len, "%s", describe_pattern(p).c_str());
+    return BB_OK;
+}
+
+int bb_filter(const char* annotated, const char* output, const char* dropped, const char* const* patterns, int32_t n_patterns,
+              uint64_t counts[3], char* err, size_t errlen) {
+    if (!annotated || !output || (n_patterns > 0 && !patterns)) return BB_ERR_INVALID;
+    std::string e;
+    std::vector<Pattern> pats(static_cast<size_t>(std::max(0, n_patterns)));
+    for (int i = 0; i < n_patterns; i++) if (!parse_pattern(patterns[i], pats[i], e)) { set_err(err, errlen, e); return BB_ERR_INVALID; }
+    TsvWriter out, drop;
+    if (!out.open(output, e)) { set_err(err, errlen, e); return BB_ERR_IO; }
+    if (dropped && !drop.open(dropped, e)) { set_err(err, errlen, e); return BB_ERR_IO; }
+    uint64_t total = 0, kept = 0, dropped_n = 0;
+    const int rc = for_each_read(annotated, [&](std::vector<Row>& group) {
+        total++;
+        if (check_filter_pass(group, pats)) { kept++; for (const Row& r : group) out.write(r); }
+        else { dropped_n++; if (dropped) for (const Row& r : group) drop.write(r); }
+    }, e);
+    if (rc != BB_OK) { set_err(err, errlen, e); return rc; }
+    if (!out.close() || !drop.close()) { set_err(err, errlen, "write error"); return BB_ERR_IO; }
+    if (counts) { counts[0] = total; counts[1] = kept; counts[2] = dropped_n; }
+    return BB_OK;
+}
+
+int bb_inspect(const char* annotated, int32_t top_n, const char* read_pattern_out, int32_t bucket_size, char* err, size_t errlen) {
+    if (!annotated || bucket_size <= 0) return BB_ERR_INVALID;
+    std::string e;
+    FILE* rp = nullptr;
+    if (read_pattern_out) { rp = std::fopen(read_pattern_out, "w"); if (!rp) { set_err(err, errlen, std::string(read_pattern_out) + ": " + std::strerror(errno)); return BB_ERR_IO; } }
+    std::unordered_map<std::string, size_t> index;
+    std::vector<std::pair<std::string, uint64_t>> counts;          // first-seen order (the reference's HashMap order is arbitrary)
+    const int rc = for_each_read(annotated, [&](std::vector<Row>& group) {
+        const std::string label = group_structure(group, static_cast<uint64_t>(bucket_size));
+        if (rp) std::fprintf(rp, "%s\t%s\n", group.front().read_id.c_str(), label.c_str());
+        auto it = index.find(label);
+        if (it == index.end()) { index[label] = counts.size(); counts.push_back({label, 1}); } else counts[it->second].second++;
+    }, e);
+    if (rp) std::fclose(rp);
+    if (rc != BB_OK) { set_err(err, errlen, e); return rc; }
+    std::printf("Found %zu unique patterns\n", counts.size());
+    std::stable_sort(counts.begin(), counts.end(), [](const auto& a, const auto& b) { return a.second > b.second; });
+    const bool color = isatty(1) && !std::getenv("NO_COLOR");
+    for (size_t i = 0; i < counts.size() && i < static_cast<size_t>(std::max(0, top_n)); i++) {
+        std::printf("\tPattern %zu: %llu occurrences\n", i + 1, static_cast<unsigned long long>(counts[i].second));
+        std::printf("\t\t%s\n", (color ? colorize(counts[i].first) : counts[i].first).c_str());
+    }
+    std::printf("Showed %d / %zu patterns\n", top_n, counts.size());
+    return BB_OK;
+}
+
+int bb_trim(const char* filtered, const char* const* fastq, int32_t n_fastq, const char* out_dir, const bb_trim_opts* opts, uint64_t counts[4],
+            char* err, size_t errlen) {
+    if (!filtered || !out_dir || !opts) return BB_ERR_INVALID;
+    const bb_trim_opts& o = *opts;
+    struct stat st;
+    if (stat(out_dir, &st) != 0) {                         // create_dir_all
+        std::string path(out_dir);
+        for (size_t p = 1; p <= path.size(); p++) if (p == path.size() || path[p] == '/') ::mkdir(path.substr(0, p).c_str(), 0755);
+    }
+    if (o.sort_labels && o.only_side) { set_err(err, errlen, "Cannot enable only keeping left/right label and sorting; this is ambiguous"); return BB_ERR_INVALID; }
+    std::string e;
+    std::unordered_map<std::string, std::vector<Row>> by_read;      // trim.rs:335-355: all annotations, grouped by read id
+    {
+        TsvReader rd;
+        if (!rd.open(filtered, e)) { set_err(err, errlen, e); return BB_ERR_IO; }
+        Row r;
+        for (;;) {
+            const int rc = rd.next(r, e);
+            if (rc < 0) { set_err(err, errlen, "Failed to parse annotation line: " + e); return BB_ERR_INVALID; }
+            if (rc == 0) break;
+            by_read[r.read_id].push_back(r);
+        }
+    }
+    FILE* failed = nullptr;
+    if (o.failed_out) { failed = std::fopen(o.failed_out, "w"); if (!failed) { set_err(err, errlen, std::string(o.failed_out) + ": " + std::strerror(errno)); return BB_ERR_IO; } }
+    if (n_fastq <= 0 || !fastq) { if (failed) std::fclose(failed); set_err(err, errlen, "No FASTQ input files provided"); return BB_ERR_IO; }
+    std::map<std::string, std::unique_ptr<FastqOut>> writers;
+    uint64_t total = 0, trimmed = 0, split = 0, failed_n = 0;
+    std::vector<std::string> paths(fastq, fastq + n_fastq);
+    bb::FastqReader reader(paths);
+    bb::FastqReader::View v;
+    int rc = BB_OK;
+    while (reader.next(v, e)) {
+        total++;
+        const std::string read_id(v.id, v.id_len);
+        auto it = by_read.find(read_id);
+        if (it == by_read.end()) continue;
+        const std::vector<TrimmedRead> results = process_read_and_anno(v.seq, v.qual, v.seq_len, it->second, o);
+        if (!results.empty()) trimmed++;
+        else { failed_n++; if (failed) std::fprintf(failed, "%s\n", read_id.c_str()); }
+        if (results.size() > 1) split++;
+        for (const TrimmedRead& t : results) {
+            auto w = writers.find(t.label);
+            if (w == writers.end()) {
+                auto fo = std::make_unique<FastqOut>();
+                const std::string path = std::string(out_dir) + "/" + t.label + (o.gzip ? ".trimmed.fastq.gz" : ".trimmed.fastq");
+                if (!fo->open(path, o.gzip != 0, e)) { rc = BB_ERR_IO; break; }
+                w = writers.emplace(t.label, std::move(fo)).first;
+            }
+            std::string rec = "@" + read_id + t.suffix;
+            if (o.write_full_header && v.desc_len) { rec += " "; rec.append(v.desc, v.desc_len); }
+            rec += "\n" + t.seq + "\n+\n" + t.qual + "\n";
+            w->second->write(rec);
+        }
+        if (rc != BB_OK) break;
+    }
+    if (failed) std::fclose(failed);
+    if (rc == BB_OK && !e.empty()) rc = BB_ERR_IO;
+    if (rc != BB_OK) { set_err(err, errlen, e); return rc; }
+    if (counts) { counts[0] = total; counts[1] = trimmed; counts[2] = split; counts[3] = failed_n; }
+    return BB_OK;
+}
+
+}  // extern "C"

@@ -101,6 +101,11 @@ int  bb_label_range(const char *from_label, const char *to_label, int use_12a, c
 /* lookup_barcode_seq, src/kits/kits.rs:1074-1103: NULL when unknown */
 const char *bb_lookup_barcode_seq(const char *label);
 
+/* get_kit_info, src/kits/kits.rs:635-708: preset name, its templates' label ranges ("BC01 - BC96; ...") and whether the kit
+ * uses the double-label filter pattern sets (safe_patterns / maximize_patterns of its KitConfig, kits.rs:466-633) */
+int  bb_kit_info(const char *kit, char *name, size_t namelen, char *ranges, size_t rangeslen, int *double_label, char *err,
+                 size_t errlen);
+
 /* ---- the operator (replaces Demuxer::{new,add_query_group,demux}, src/annotate/searcher.rs:202-227, 430-490) ---- */
 int  bb_create(const bb_opts *opts, bb_ctx **out, char *err, size_t errlen);
 void bb_destroy(bb_ctx *ctx);
@@ -143,6 +148,35 @@ void bb_host_free(void *p);
 /* the wire format of flags bit 1, exposed for hosts that want to pack while parsing: dst[i] = set(src[2i]) | set(src[2i+1]) << 4,
    set() = 4-bit IUPAC base set (A=1, C=2, G=4, T=8; non-IUPAC bytes 0); dst holds (n+1)/2 bytes */
 int  bb_pack_nibbles(const uint8_t *src, uint64_t n, uint8_t *dst);
+
+/* ---- the stages that consume annotation.tsv (host side, no GPU): filter, inspect, trim -- so that `barbell kit` runs the
+ *      reference's whole pipeline, src/kits/use_kit.rs:11-109 ---- */
+/* the kit pattern sets of src/kits/kits.rs:175-236 (single/double label x safe/maximize) as pattern strings */
+int  bb_kit_filter_patterns(int double_label, int maximize, const char *const **patterns, int32_t *n);
+/* pattern_from_str!, src/filter/pattern.rs:242-383: parses one pattern string; `canonical` receives a normalised dump
+ * of the parsed elements.  A string the reference's macro panics on returns BB_ERR_INVALID with the message in err. */
+int  bb_pattern_parse(const char *pattern, char *canonical, size_t canonical_len, char *err, size_t errlen);
+/* filter, src/filter/filter.rs:10-119 (+ check_filter_pass :183-214, match_pattern pattern.rs:205-240): reads
+ * annotation.tsv, writes the rows of every read whose annotations are covered by its longest matching pattern (cuts
+ * column filled in) to `output` and, when `dropped` is non-NULL, the other reads' rows there.
+ * counts = {total, kept, dropped} reads (progress counters, filter.rs:55-97). */
+int  bb_filter(const char *annotated, const char *output, const char *dropped, const char *const *patterns,
+               int32_t n_patterns, uint64_t counts[3], char *err, size_t errlen);
+/* inspect, src/inspect/inspect.rs:133-208: pattern string per read (get_group_structure :15-117) into
+ * read_pattern_out (nullable), histogram of the top_n patterns on stdout */
+int  bb_inspect(const char *annotated, int32_t top_n, const char *read_pattern_out, int32_t bucket_size, char *err,
+                size_t errlen);
+/* TrimConfig, src/config.rs:19-32 */
+typedef struct {
+    int32_t add_labels, add_orientation, add_flank, sort_labels;
+    int32_t only_side;          /* 0 = none, 1 = LabelSide::Left, 2 = LabelSide::Right (trim.rs:25-29) */
+    int32_t write_full_header, skip_trim, flip, gzip;
+    const char *failed_out;     /* ids of reads with annotations but no slice; NULL = not written */
+} bb_trim_opts;
+/* trim_matches, src/trim/trim.rs:317-480: cuts every read of the FASTQ files that has rows in filtered.tsv and writes
+ * <out_dir>/<label>.trimmed.fastq[.gz].  counts = {total, trimmed, trimmed_split, failed} reads (trim.rs:19-22). */
+int  bb_trim(const char *filtered, const char *const *fastq, int32_t n_fastq, const char *out_dir, const bb_trim_opts *opts,
+             uint64_t counts[4], char *err, size_t errlen);
 
 int  bb_abi_version(void);
 

@@ -214,8 +214,30 @@ def test_cli_fastq_to_annotation_tsv(tmp_path):
     assert open(out).read() == want
     outdir = tmp_path / "kit_out"
     r = subprocess.run([exe, "kit", "-k", "SQK-NBD114-96", "-i", str(fq1), str(fq2), "-o", str(outdir)], capture_output=True, text=True, timeout=120)
-    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.returncode == 0 and "Done!" in r.stdout, r.stdout + r.stderr
     assert open(outdir / "annotation.tsv").read() == want
+    # the later stages of `kit` (use_kit.rs:50-105) against the Python restatement of filter / inspect / trim
+    import copy
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(cases.GOLD), "..", "oracle"))
+    import post_oracle as P
+    from barbell_b200 import post
+    anno = P.parse_tsv(want)
+    assert open(outdir / "pattern_per_read.tsv").read() == "".join(f"{g[0].read_id}\t{P.group_structure(g, 250)}\n" for g in P.group_reads(anno))
+    kept, _ = P.filter_rows(copy.deepcopy(anno), [P.parse_pattern(x) for x in post.kit_patterns("SQK-NBD114-96")])
+    assert open(outdir / "filtered.tsv").read() == P.to_tsv(kept) and len(kept) > 100
+    by = {}
+    for row in kept:
+        by.setdefault(row.read_id, []).append(row)
+    files = {}
+    for i in range(n):
+        rid = f"read_{i}"
+        if rid in by:
+            s = bases[int(offsets[i]):int(offsets[i + 1])].tobytes()
+            for ts, tq, lab, suf in P.process_read_and_anno(s, b"I" * len(s), by[rid], add_orientation=False, add_flank=False, only_side="left"):
+                files.setdefault(lab + ".trimmed.fastq", []).append(f"@{rid}{suf} runid=abc ch=7\n{ts.decode()}\n+\n{tq.decode()}\n")
+    got = {f: open(outdir / f).read() for f in os.listdir(outdir) if f.endswith(".trimmed.fastq")}
+    assert got == {k: "".join(v) for k, v in files.items()} and len(got) > 20
     # unknown kit: message, exit code 0 (reference bin/main.rs:301-304), empty/no output
     r = subprocess.run([exe, "annotate", "--kit", "SQK-NOPE", "-i", str(fq1), "-o", str(tmp_path / "x.tsv")], capture_output=True, text=True)
     assert r.returncode == 0 and "Error during processing" in r.stdout
