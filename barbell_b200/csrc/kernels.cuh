@@ -562,18 +562,24 @@ __device__ __forceinline__ int block_min_cost(const uint8_t* __restrict__ text, 
     if (c0 < 0) c0 = 0;
     uint32_t pv = blk, mv = 0;
     int score = rows, best = rows;
-    uint32_t ch_next = __ldg(text + c0);
-    for (int c = c0; c < hi; c++) {
-        const uint32_t e = (eq[ch_next] >> shiftbits) & blk;
-        if (c + 1 < hi) ch_next = __ldg(text + c + 1);
-        const uint32_t sum = (e & pv) + pv;
-        uint32_t ph = mv | ~(sum | pv | e);
-        uint32_t mh = pv & ((sum ^ pv) | e);
-        score += static_cast<int>((ph >> (rows - 1)) & 1u) - static_cast<int>((mh >> (rows - 1)) & 1u);
-        ph <<= 1; mh <<= 1;
-        pv = (mh | ~(e | mv | ph)) & blk;
-        mv = ph & (e | mv) & blk;
-        if (c + 1 >= lo) best = min(best, score);
+    // the window's bytes are fetched eight at a time (independent loads in flight) -- this kernel is latency-bound
+    for (int c = c0; c < hi; c += 8) {
+        uint32_t ch[8];
+#pragma unroll
+        for (int t = 0; t < 8; t++) ch[t] = c + t < hi ? __ldg(text + c + t) : 0u;
+#pragma unroll
+        for (int t = 0; t < 8; t++) {
+            if (c + t >= hi) break;
+            const uint32_t e = (eq[ch[t]] >> shiftbits) & blk;
+            const uint32_t sum = (e & pv) + pv;
+            uint32_t ph = mv | ~(sum | pv | e);
+            uint32_t mh = pv & ((sum ^ pv) | e);
+            score += static_cast<int>((ph >> (rows - 1)) & 1u) - static_cast<int>((mh >> (rows - 1)) & 1u);
+            ph <<= 1; mh <<= 1;
+            pv = (mh | ~(e | mv | ph)) & blk;
+            mv = ph & (e | mv) & blk;
+            if (c + t + 1 >= lo) best = min(best, score);
+        }
     }
     return best;
 }
@@ -645,12 +651,16 @@ __device__ void verify_window(const ScanArgs& A, const DevGroup& G, const uint64
     int score = fresh ? m : G.ov_m;
     if (lo == 0 && score <= k) scan_emit(A, r, strand, 0u, score);
     const int64_t base = strand == BB_FWD ? 0 : static_cast<int64_t>(n) - 1, step = strand == BB_FWD ? 1 : -1;
-    uint32_t ch_next = c0 < c_end ? __ldg(text + base + step * c0) : 0u;
-    for (int c = c0; c < c_end; c++) {
-        const uint32_t ch = ch_next;
-        if (c + 1 < c_end) ch_next = __ldg(text + base + step * (c + 1));
-        score += col_step_top<NW>(col, eq + ch * NW);
-        if (score <= k && c + 1 >= lo) scan_emit(A, r, strand, static_cast<uint32_t>(c + 1), score);
+    for (int c = c0; c < c_end; c += 8) {                        // eight independent byte loads in flight per round
+        uint32_t chs[8];
+#pragma unroll
+        for (int t = 0; t < 8; t++) chs[t] = c + t < c_end ? __ldg(text + base + step * (c + t)) : 0u;
+#pragma unroll
+        for (int t = 0; t < 8; t++) {
+            if (c + t >= c_end) break;
+            score += col_step_top<NW>(col, eq + chs[t] * NW);
+            if (score <= k && c + t + 1 >= lo) scan_emit(A, r, strand, static_cast<uint32_t>(c + t + 1), score);
+        }
     }
     if (hi > n && c_end == n) {                                  // virtual end positions past the text end (oracle policy S3)
         const int tmax = min(hi - n, m);
