@@ -198,21 +198,18 @@ struct Engine {
                     const uint32_t win_cap = static_cast<uint32_t>(std::min<uint64_t>(total / 48 + (1u << 20), 1u << 30));
                     BB_CUDA(d_windows.ensure(static_cast<size_t>(win_cap) * 8));
                     BB_CUDA(cudaMemsetAsync(d_cnt + 6, 0, 4, st));          // [6] window count ([7] overflow flag is sticky per attempt)
-                    FilterArgs F{A, d_windows.as<uint64_t>(), d_cnt + 6, win_cap, d_cnt + 7};
-                    const int fw = ((G.f_q + G.k + kGroup - 1) / kGroup) * kGroup;
-                    const size_t smem = filter_smem_bytes(fw);
+                    int halo_l = 0, halo_r = 0;
+                    filter_halos(G, halo_l, halo_r);
+                    FilterArgs F{A, d_windows.as<uint64_t>(), d_cnt + 6, win_cap, d_cnt + 7, halo_l, halo_r};
+                    const size_t smem = filter_smem_bytes(halo_l, halo_r);
                     BB_CUDA(cudaFuncSetAttribute(k_flank_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+                    // scan + candidate runs + pre-check with the second N-free run (all on the shared text tile) -> windows
                     k_flank_filter<<<n_tiles, kScanThreads, smem, st>>>(F, G);
-                    // candidate runs -> (pre-check with the second N-free run) -> windows -> exact verification
-                    BB_CUDA(d_windows2.ensure(static_cast<size_t>(win_cap) * 8));
-                    BB_CUDA(cudaMemsetAsync(d_cnt + 8, 0, 4, st));
-                    PrecheckArgs P{A, d_windows.as<uint64_t>(), d_cnt + 6, d_windows2.as<uint64_t>(), d_cnt + 8, win_cap, d_cnt + 7};
-                    k_flank_precheck<<<148 * 16, 128, 0, st>>>(P, G);
                     launches++;
-                    VerifyArgs V{A, d_windows2.as<uint64_t>(), d_cnt + 8};
+                    VerifyArgs V{A, d_windows.as<uint64_t>(), d_cnt + 6};
                     if (G.nw == 1) k_flank_verify<1><<<148 * 16, 128, 0, st>>>(V, G);
                     else k_flank_verify<2><<<148 * 16, 128, 0, st>>>(V, G);
-                    launches += 2;
+                    launches++;
                     filtered = true;
                     BB_CUDA(cudaGetLastError());
                     continue;

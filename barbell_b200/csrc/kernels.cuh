@@ -5,9 +5,10 @@
 //                   position whose cost is <= k ("sub-threshold entries").  Text tiles arrive in shared memory by one
 //                   TMA bulk copy per CTA; one lane owns one text chunk; match masks are staged once in shared memory.
 //  K1f filter       the same search as a LOSSLESS pre-filter: only the flank's longest N-free run (<= 15 rows) of both
-//  K1p precheck     strands is advanced per base (one 32-bit word, branch-free), candidate runs are re-scored together
-//  K1v verify       with the second N-free run, and the surviving windows (+ the read ends, where the overhang rule
-//                   applies) are verified with the exact full-length DP.  Default whenever 3k <= rows of the run.
+//                   strands is advanced per base (one 32-bit word, branch-free); the candidate runs are re-scored
+//                   together with the second N-free run on the text tile still in shared memory, and
+//  K1v verify       the surviving windows (+ the read ends, where the overhang rule applies) are verified with the
+//                   exact full-length DP.  Default whenever 3k <= rows of the run.
 //  K2a resolve      sassy's local-minimum reporting rule applied to the sorted entries.
 //  K2b trace        traceback of every reported flank match -> text_start and the barcode text region
 //                   (reference cigar_parse.rs:71-82, searcher.rs:442-456).
@@ -20,6 +21,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdint>
 
 #include "../../include/barbell_b200.h"
@@ -367,14 +369,15 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_flank_scan(const ScanArgs A
 // which the filter does not model), so the first and last m+k end positions of every read and strand (and the virtual
 // positions past the end) are ALWAYS verified.  Windows may overlap: duplicates are removed after the sort.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int kFiltQueue = 1024;     // candidate windows a CTA can stage in shared memory
+constexpr int kRunQueue = 2048;      // candidate runs a CTA can stage in shared memory (~850 per CTA on random text)
 
 struct FilterArgs {
     ScanArgs S;
-    uint64_t* windows;           // global candidate queue
+    uint64_t* windows;           // global queue of windows to verify
     uint32_t* n_windows;
     uint32_t win_cap;
     uint32_t* overflow;          // set when a CTA queue or the global queue overflowed (host falls back to the exact scan)
+    int halo_l, halo_r;          // text kept in shared memory before / after the CTA's chunks (pre-check of the second run)
 };
 
 __device__ __forceinline__ uint64_t make_window(uint32_t read, int strand, int lo, int len) {
@@ -382,29 +385,75 @@ __device__ __forceinline__ uint64_t make_window(uint32_t read, int strand, int l
            (static_cast<uint64_t>(static_cast<uint32_t>(lo)) << kWinLoShift) | static_cast<uint64_t>(len);
 }
 
-constexpr int kFiltGroups = kChunk / kGroup;     // candidate-bitmap groups per chunk (17)
+constexpr int kFiltGroups = kChunk / kGroup;     // candidate-bitmap groups per chunk (15)
+constexpr int kFiltStage = kFiltGroups * kScanThreads * 5 / 8;   // windows a CTA can stage (the bitmap area is reused)
 
-// Shared memory of k_flank_filter for a filter warm-up of `fw` columns.
-__host__ __device__ inline size_t filter_smem_bytes(int fw) {
-    return 128 + 1024 + kFiltQueue * sizeof(uint64_t) + static_cast<size_t>(kFiltGroups) * kScanThreads * 5 +
-           static_cast<size_t>(kScanThreads) * kChunk + fw + 48;
+// Shared-memory halos of k_flank_filter: the filter's own warm-up, and the reach of the pre-check (the second run S ends
+// d rows after/before the first, is scanned over +-k positions and needs its own rows + k warm-up columns).
+__host__ inline void filter_halos(const DevGroup& G, int& halo_l, int& halo_r) {
+    const int W = ((G.f_q + G.k + kGroup - 1) / kGroup) * kGroup;
+    const int d_f = (G.f_s0 + G.f_qs) - (G.f_q0 + G.f_q), d_r = G.f_q0 - G.f_s0;
+    const int back = G.f_qs ? std::max(0, std::max(-d_f, -d_r)) + 2 * G.k + G.f_qs + 2 : 0;
+    const int fwd = G.f_qs ? std::max(0, std::max(d_f, d_r)) + G.k + 1 : 0;
+    halo_l = (std::max(W, back) + 15) & ~15;
+    halo_r = (fwd + 15) & ~15;
+}
+__host__ inline size_t filter_smem_bytes(int halo_l, int halo_r) {
+    return 128 + 2 * 1024 + kRunQueue * sizeof(uint32_t) + 3 * kScanThreads * sizeof(int32_t) +
+           static_cast<size_t>(kFiltGroups) * kScanThreads * 5 + static_cast<size_t>(kScanThreads) * kChunk + halo_l + halo_r + 64;
 }
 
-// The scan loop is branch-free: per base it advances both 15-row blocks (one 32-bit word), updates the two packed
-// costs and shifts the two "cost > k" flags into per-strand bit registers; after every group of 20 bases the 2 x 20
-// flags go to a per-lane bitmap in shared memory.  Only after the whole chunk is scanned does the lane turn its bitmap
-// into runs of candidate positions and the runs into windows (CTA queue in shared memory, ONE global atomic per CTA).
+// min over end positions [lo, hi] (1-based, <= n) of the semi-global cost of a <=15-row block against text[0, n)
+__device__ __forceinline__ int block_min_cost(const uint8_t* __restrict__ text, const uint32_t* __restrict__ eq, int shiftbits, int rows,
+                                              int k, int lo, int hi) {
+    const uint32_t blk = (1u << rows) - 1u;
+    int c0 = lo - 1 - (rows + k);                            // the cost at p depends on text[p-(rows+k), p) only
+    if (c0 < 0) c0 = 0;
+    uint32_t pv = blk, mv = 0;
+    int score = rows, best = rows;
+    for (int c = c0; c < hi; c++) {
+        const uint32_t e = (eq[text[c]] >> shiftbits) & blk;
+        const uint32_t sum = (e & pv) + pv;
+        uint32_t ph = mv | ~(sum | pv | e);
+        uint32_t mh = pv & ((sum ^ pv) | e);
+        score += static_cast<int>((ph >> (rows - 1)) & 1u) - static_cast<int>((mh >> (rows - 1)) & 1u);
+        ph <<= 1; mh <<= 1;
+        pv = (mh | ~(e | mv | ph)) & blk;
+        mv = ph & (e | mv) & blk;
+        if (c + 1 >= lo) best = min(best, score);
+    }
+    return best;
+}
+
+// Phase 1 (scan): branch-free; per base it advances both 15-row blocks (one 32-bit word), updates the two packed costs and
+// shifts the two "cost > k" flags into per-strand bit registers; after every group of 20 bases the 2 x 20 flags go to a
+// per-lane bitmap in shared memory.
+// Phase 2 (runs): each lane turns its bitmap into runs of consecutive candidate positions per strand (CTA queue).
+// Phase 3 (pre-check, all threads over the CTA queue): a run [ps, pe] says "the run Q ends here with <= k edits".  In a real
+// match the second N-free run S of the flank ends at pS with |pS - p - d| <= k (d = signed row distance of the two run ends)
+// and cost(Q) + cost(S) <= k (disjoint rows of one alignment), so Q is re-scored over [ps, pe] and S over
+// [ps + d - k, pe + d + k] with single 32-bit block DPs on the text ALREADY IN SHARED MEMORY, and the run is dropped when
+// min cost(Q) + min cost(S) > k: ~95 % of the random candidates disappear before the ~4000-instruction exact verification
+// without a second pass over HBM.  Survivors become windows of end positions (one global atomic per CTA):
+//   forward: the Df rows after Q are aligned to (p, j] with <= k edits               -> j   in [ps + Df - k, pe + Df + k]
+//   rc     : the match starts at s = p - Dr +- k (the run's own indels shift its end) -> n-s in [n - pe + Dr - k, n - ps + Dr + k]
 __global__ void __launch_bounds__(kScanThreads, 2) k_flank_filter(const FilterArgs F, const DevGroup G) {
     extern __shared__ __align__(128) unsigned char smem[];
     const ScanArgs& A = F.S;
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
     int64_t* s_origin = reinterpret_cast<int64_t*>(smem + 16);
     uint32_t* s_qn = reinterpret_cast<uint32_t*>(smem + 32);
-    uint32_t* s_qbase = reinterpret_cast<uint32_t*>(smem + 36);
-    uint32_t* s_eq = reinterpret_cast<uint32_t*>(smem + 128);                       // [256]
-    uint64_t* s_queue = reinterpret_cast<uint64_t*>(smem + 128 + 1024);             // [kFiltQueue]
-    uint32_t* s_bm32 = reinterpret_cast<uint32_t*>(smem + 128 + 1024 + kFiltQueue * sizeof(uint64_t));   // [group][lane]
-    uint8_t* s_bm8 = reinterpret_cast<uint8_t*>(s_bm32 + kFiltGroups * kScanThreads);                     // [group][lane]
+    uint32_t* s_wn = reinterpret_cast<uint32_t*>(smem + 36);
+    uint32_t* s_wbase = reinterpret_cast<uint32_t*>(smem + 40);
+    uint32_t* s_eq = reinterpret_cast<uint32_t*>(smem + 128);                       // [256] first run Q (both strands)
+    uint32_t* s_seq = s_eq + 256;                                                   // [256] second run S
+    uint32_t* s_runs = s_seq + 256;                                                 // [kRunQueue]
+    int32_t* s_lane_r = reinterpret_cast<int32_t*>(s_runs + kRunQueue);             // per lane: read, chunk start, text offset of the read
+    int32_t* s_lane_a = s_lane_r + kScanThreads;
+    int32_t* s_lane_t = s_lane_a + kScanThreads;
+    uint32_t* s_bm32 = reinterpret_cast<uint32_t*>(s_lane_t + kScanThreads);        // [group][lane]
+    uint8_t* s_bm8 = reinterpret_cast<uint8_t*>(s_bm32 + kFiltGroups * kScanThreads);   // [group][lane]
+    uint64_t* s_stage = reinterpret_cast<uint64_t*>(s_bm32);                        // phase 3: surviving windows (bitmaps are dead)
     unsigned char* s_text = s_bm8 + kFiltGroups * kScanThreads;
 
     const int tid = threadIdx.x;
@@ -416,7 +465,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_flank_filter(const FilterAr
     const uint32_t r_first = __ldg(A.tile_first + blockIdx.x);
 
     if (tid == 0) {
-        *s_qn = 0;
+        *s_qn = 0; *s_wn = 0;
         mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         const uint32_t c_last = min(c_first + kScanThreads, total_chunks) - 1;
@@ -425,16 +474,16 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_flank_filter(const FilterAr
         uint64_t g_hi = __ldg(A.offsets + r_last) + static_cast<uint64_t>(c_last - __ldg(A.chunk_base + r_last) + 1) * kChunk;
         const uint64_t r_end = __ldg(A.offsets + r_last + 1);
         if (g_hi > r_end) g_hi = r_end;
-        uint64_t lo = g_lo >= static_cast<uint64_t>(W) ? g_lo - W : 0;
+        uint64_t lo = g_lo >= static_cast<uint64_t>(F.halo_l) ? g_lo - F.halo_l : 0;
         lo &= ~15ull;
-        uint64_t hi = (g_hi + 15) & ~15ull;
+        uint64_t hi = (g_hi + F.halo_r + 15) & ~15ull;
         if (hi > A.total16) hi = A.total16;
         *s_origin = static_cast<int64_t>(lo);
         const uint32_t bytes = static_cast<uint32_t>(hi - lo);
         mbar_expect_tx(bar, bytes);
         tma_bulk_g2s(s_text, A.bases + lo, bytes, bar);
     }
-    for (int i = tid; i < 256; i += kScanThreads) s_eq[i] = __ldg(G.f_eq + i);
+    for (int i = tid; i < 256; i += kScanThreads) { s_eq[i] = __ldg(G.f_eq + i); s_seq[i] = G.f_qs ? __ldg(G.f_seq + i) : 0u; }
 
     const uint32_t c = c_first + tid;
     const bool active = c < total_chunks;
@@ -451,7 +500,9 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_flank_filter(const FilterAr
     __syncthreads();
     mbar_wait(bar, 0);
     if (active) {
-        const unsigned char* text = s_text + (static_cast<int64_t>(rs_g) - *s_origin);
+        const int tb = static_cast<int>(static_cast<int64_t>(rs_g) - *s_origin);    // text[x] of this lane's read = s_text[tb + x]
+        s_lane_r[tid] = static_cast<int32_t>(r); s_lane_a[tid] = a; s_lane_t[tid] = tb;
+        const unsigned char* text = s_text + tb;
         const uint32_t blk = (1u << q) - 1u;
         const uint32_t keep = ~(1u << 16);                      // the upper block's row 0 gets no horizontal input
         const uint32_t last2 = 0x00010001u;
@@ -494,10 +545,11 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_flank_filter(const FilterAr
             }
         }
 #undef BB_FSTEP
-        // ---- candidate positions -> runs of consecutive positions per strand (queued as {read, strand, first, length-1}) ----
+        // ---- phase 2: candidate positions -> runs per strand, queued as {lane:8 | strand:1 | first - a:9 | length - 1:9} ----
         auto push = [&](int strand, int ps, int pe) {
             const uint32_t idx = atomicAdd(s_qn, 1u);
-            if (idx < kFiltQueue) s_queue[idx] = make_window(r, strand, ps, pe - ps);
+            if (idx < kRunQueue) s_runs[idx] = (static_cast<uint32_t>(tid) << 19) | (static_cast<uint32_t>(strand) << 18) |
+                                               (static_cast<uint32_t>(ps - a) << 9) | static_cast<uint32_t>(pe - ps);
         };
         const int ng = (b - a + kGroup - 1) / kGroup;
         int f_s = 0, f_e = -2, r_s = 0, r_e = -2;               // run start / last position per strand (empty: e = -2)
@@ -526,103 +578,51 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_flank_filter(const FilterAr
         if (r_e >= 0) push(BB_RC, r_s, r_e);
     }
     __syncthreads();
-    // flush the CTA queue with one global atomic
     const uint32_t nq = *s_qn;
-    if (nq > kFiltQueue) { if (tid == 0) atomicExch(F.overflow, 1u); return; }
-    if (tid == 0) *s_qbase = nq ? atomicAdd(F.n_windows, nq) : 0u;
-    __syncthreads();
-    const uint32_t base = *s_qbase;
-    if (base + nq > F.win_cap) { if (tid == 0) atomicExch(F.overflow, 1u); return; }
-    for (uint32_t i = tid; i < nq; i += kScanThreads) F.windows[base + i] = s_queue[i];
-}
-
-// K1p: pre-check of the filter's candidate runs, then runs -> windows.
-// A candidate run [ps, pe] says "the run Q ends here with <= k edits".  In a real match the second N-free run S of the
-// flank ends at pS with |pS - p - d| <= k (d = signed row distance between the two run ends) and cost(Q) + cost(S) <= k.
-// One thread per run re-scores Q over [ps, pe] and S over [ps + d - k, pe + d + k] with single 32-bit block DPs (a few
-// hundred instructions) and drops the run when min cost(Q) + min cost(S) > k -- which removes ~95 % of the random
-// candidates before the ~4000-instruction exact verification.  Survivors become windows of end positions:
-//   forward: the Df rows after Q are aligned to (p, j] with <= k edits               -> j   in [ps + Df - k, pe + Df + k]
-//   rc     : the match starts at s = p - Dr +- k (the run's own indels shift its end) -> n-s in [n - pe + Dr - k, n - ps + Dr + k]
-struct PrecheckArgs {
-    ScanArgs S;
-    const uint64_t* runs;
-    const uint32_t* n_runs;
-    uint64_t* windows;
-    uint32_t* n_windows;
-    uint32_t win_cap;
-    uint32_t* overflow;
-};
-
-// min over end positions [lo, hi] (1-based, <= n) of the semi-global cost of a <=15-row block against text[0, n)
-__device__ __forceinline__ int block_min_cost(const uint8_t* __restrict__ text, const uint32_t* __restrict__ eq, int shiftbits, int rows,
-                                              int k, int lo, int hi) {
-    const uint32_t blk = (1u << rows) - 1u;
-    int c0 = lo - 1 - (rows + k);                            // the cost at p depends on text[p-(rows+k), p) only
-    if (c0 < 0) c0 = 0;
-    uint32_t pv = blk, mv = 0;
-    int score = rows, best = rows;
-    // the window's bytes are fetched eight at a time (independent loads in flight) -- this kernel is latency-bound
-    for (int c = c0; c < hi; c += 8) {
-        uint32_t ch[8];
-#pragma unroll
-        for (int t = 0; t < 8; t++) ch[t] = c + t < hi ? __ldg(text + c + t) : 0u;
-#pragma unroll
-        for (int t = 0; t < 8; t++) {
-            if (c + t >= hi) break;
-            const uint32_t e = (eq[ch[t]] >> shiftbits) & blk;
-            const uint32_t sum = (e & pv) + pv;
-            uint32_t ph = mv | ~(sum | pv | e);
-            uint32_t mh = pv & ((sum ^ pv) | e);
-            score += static_cast<int>((ph >> (rows - 1)) & 1u) - static_cast<int>((mh >> (rows - 1)) & 1u);
-            ph <<= 1; mh <<= 1;
-            pv = (mh | ~(e | mv | ph)) & blk;
-            mv = ph & (e | mv) & blk;
-            if (c + t + 1 >= lo) best = min(best, score);
-        }
-    }
-    return best;
-}
-
-__global__ void __launch_bounds__(128) k_flank_precheck(const PrecheckArgs P, const DevGroup G) {
-    __shared__ uint32_t s_q[256], s_s[256];
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) { s_q[i] = __ldg(G.f_eq + i); s_s[i] = G.f_qs ? __ldg(G.f_seq + i) : 0u; }
-    __syncthreads();
-    const ScanArgs& A = P.S;
-    const uint32_t total = __ldg(P.n_runs);
-    const int m = G.m, k = G.k, q = G.f_q, qs = G.f_qs;
-    const int Df = m - (G.f_q0 + q), Dr = m - G.f_q0;
-    const int d_f = (G.f_s0 + qs) - (G.f_q0 + q);            // end(S) - end(Q) in the flank (forward strand)
-    const int d_r = G.f_q0 - G.f_s0;                         // end(rc S) - end(rc Q) in rc(flank)
-    for (uint32_t it = blockIdx.x * blockDim.x + threadIdx.x; it < total; it += gridDim.x * blockDim.x) {
-        const uint64_t w = P.runs[it];
-        const uint32_t r = static_cast<uint32_t>(w >> kWinReadShift);
-        const int strand = static_cast<int>((w >> kWinStrandShift) & 1);
-        const int ps = static_cast<int>((w >> kWinLoShift) & ((1u << 28) - 1)), pe = ps + static_cast<int>(w & ((1u << kWinLoShift) - 1));
-        const uint64_t rs_g = __ldg(A.offsets + r);
-        const int n = static_cast<int>(__ldg(A.offsets + r + 1) - rs_g);
-        const uint8_t* text = A.bases + rs_g;
-        bool keep = true;
-        if (qs > 0) {
-            const int d = strand == BB_FWD ? d_f : d_r;
-            const int slo = ps + d - k, shi = pe + d + k;
-            if (slo >= 1 && shi <= n) {                      // S entirely inside the read (else the read-end windows decide)
-                const int sbits = strand == BB_FWD ? 0 : 16;
-                const int cq = block_min_cost(text, s_q, sbits, q, k, ps, pe);
-                if (cq > k) keep = false;                    // cannot happen for a genuine candidate; cheap guard
-                else keep = cq + block_min_cost(text, s_s, sbits, qs, k, slo, shi) <= k;
+    if (nq > kRunQueue) { if (tid == 0) atomicExch(F.overflow, 1u); return; }
+    // ---- phase 3: pre-check of the CTA's runs on the shared text, survivors -> windows ----
+    {
+        const int qs = G.f_qs;
+        const int Df = m - (G.f_q0 + q), Dr = m - G.f_q0;
+        const int d_f = (G.f_s0 + qs) - (G.f_q0 + q);            // end(S) - end(Q) in the flank (forward strand)
+        const int d_r = G.f_q0 - G.f_s0;                         // end(rc S) - end(rc Q) in rc(flank)
+        for (uint32_t it = tid; it < nq; it += kScanThreads) {
+            const uint32_t e = s_runs[it];
+            const int lt = static_cast<int>(e >> 19), strand = static_cast<int>((e >> 18) & 1u);
+            const int ps = s_lane_a[lt] + static_cast<int>((e >> 9) & 0x1ffu), pe = ps + static_cast<int>(e & 0x1ffu);
+            const uint32_t rr = static_cast<uint32_t>(s_lane_r[lt]);
+            const int nn = static_cast<int>(__ldg(A.offsets + rr + 1) - __ldg(A.offsets + rr));
+            const uint8_t* text = s_text + s_lane_t[lt];
+            bool keep_run = true;
+            if (qs > 0) {
+                const int d = strand == BB_FWD ? d_f : d_r;
+                const int slo = ps + d - k, shi = pe + d + k;
+                if (slo >= 1 && shi <= nn) {                     // S entirely inside the read (else the read-end windows decide)
+                    const int sbits = strand == BB_FWD ? 0 : 16;
+                    const int cq = block_min_cost(text, s_eq, sbits, q, k, ps, pe);
+                    if (cq > k) keep_run = false;                // cannot happen for a genuine candidate; cheap guard
+                    else keep_run = cq + block_min_cost(text, s_seq, sbits, qs, k, slo, shi) <= k;
+                }
             }
+            if (!keep_run) continue;
+            int lo, hi;
+            if (strand == BB_FWD) { lo = ps + Df - k; hi = pe + Df + k; }
+            else { lo = nn - pe + Dr - k; hi = nn - ps + Dr + k; }
+            lo = max(lo, 1); hi = min(hi, nn);
+            if (lo > hi) continue;
+            const uint32_t idx = atomicAdd(s_wn, 1u);
+            if (idx < kFiltStage) s_stage[idx] = make_window(rr, strand, lo, hi - lo);
         }
-        if (!keep) continue;
-        int lo, hi;
-        if (strand == BB_FWD) { lo = ps + Df - k; hi = pe + Df + k; }
-        else { lo = n - pe + Dr - k; hi = n - ps + Dr + k; }
-        lo = max(lo, 1); hi = min(hi, n);
-        if (lo > hi) continue;
-        const uint32_t idx = atomicAdd(P.n_windows, 1u);
-        if (idx < P.win_cap) P.windows[idx] = make_window(r, strand, lo, hi - lo);
-        else atomicExch(P.overflow, 1u);
     }
+    __syncthreads();
+    // flush the CTA's windows with one global atomic
+    const uint32_t nw = *s_wn;
+    if (nw > kFiltStage) { if (tid == 0) atomicExch(F.overflow, 1u); return; }
+    if (tid == 0) *s_wbase = nw ? atomicAdd(F.n_windows, nw) : 0u;
+    __syncthreads();
+    const uint32_t base = *s_wbase;
+    if (base + nw > F.win_cap) { if (tid == 0) atomicExch(F.overflow, 1u); return; }
+    for (uint32_t i = tid; i < nw; i += kScanThreads) F.windows[base + i] = s_stage[i];
 }
 
 // K1v: exact verification of windows; items [0, 4*n_reads) are the read-end windows, the rest come from the queue.
