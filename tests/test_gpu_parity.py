@@ -29,9 +29,10 @@ def _check(gs, bases, offsets, **kw):
     assert out[0][0].tobytes() == out[1][0].tobytes(), "pre-filter path differs from the exact scan"
     rows, hits = out[0]
     G = gs.as_dicts()
+    cap = max(16, int(len(bases) // 100 // max(1, len(offsets) - 1)))      # rows / hits per read the oracle buffers may hold
     want = O.demux_batch(G, bases, offsets, alpha=kw.get("alpha", 0.4), min_score=kw.get("min_score", 0.2),
-                         min_score_diff=kw.get("min_score_diff", 0.1))
-    want_h = O.flank_hits_batch(G, bases, offsets, alpha=kw.get("alpha", 0.4))
+                         min_score_diff=kw.get("min_score_diff", 0.1), cap_per_read=cap)
+    want_h = O.flank_hits_batch(G, bases, offsets, alpha=kw.get("alpha", 0.4), cap_per_read=2 * cap)
     assert hits.shape == want_h.shape and (hits == want_h).all(), "flank hit list differs"
     assert rows.tobytes() == want.tobytes(), "annotation rows differ"
     return rows
@@ -73,6 +74,38 @@ def test_unaligned_read_boundaries_and_long_read():
     bases = np.concatenate([b1, b2])
     offsets = np.concatenate([o1, o2[1:] + o1[-1]])
     _check(gs, bases, offsets)
+
+
+def test_tags_straddling_scan_tiles_and_chunks():
+    """Tags (both orientations, mutated) placed across the 300-base chunk and 76 800-base CTA tile boundaries of long reads:
+    the filter's candidate runs are re-scored against the second flank run on the shared text tile, whose halos must reach."""
+    for kit, kw in (("SQK-NBD114-96", {}), ("SQK-RBK114-96", dict(max_flank_errors=5))):
+        gs = bb.GroupSet.from_kit(kit, **kw)
+        g = gs.as_dicts()[0]
+        tags = synth.full_tags(g)
+        rng = np.random.default_rng(31)
+        reads = []
+        for rd in range(8):                                          # (the oracle's batch driver holds 64 rows per read)
+            body = rng.choice(np.frombuffer(b"ACGT", np.uint8), 400_000 + 17 * rd).copy()
+            for t, base in enumerate(range(300 * 256, 390_000, 300 * 256)):
+                for j, delta in enumerate(range(-150, 151, 50)):
+                    tag = tags[(7 * t + j + rd) % len(tags)]
+                    tag = synth.mutate(rng, tag, 0.04)
+                    if (t + j + rd) & 1:
+                        tag = synth.revcomp(tag)
+                    pos = base + delta * 7 + rd * 3 - len(tag) // 2
+                    body[pos:pos + len(tag)] = tag
+            for c in range(5, 20):                                   # ... and across plain chunk boundaries
+                tag = synth.mutate(rng, tags[(c + rd) % len(tags)], 0.05)
+                if c & 1:
+                    tag = synth.revcomp(tag)
+                pos = c * 300 * 3 + (c * 37) % 300 - 40
+                body[pos:pos + len(tag)] = tag
+            reads.append(body)
+        bases = np.concatenate(reads)
+        offsets = np.concatenate([[0], np.cumsum([len(r) for r in reads])]).astype(np.uint64)
+        rows = _check(gs, bases, offsets)
+        assert (rows["match_type"] < 2).sum() > 100
 
 
 def test_adversarial_text():
