@@ -285,10 +285,13 @@ def main():
                                batch_bytes=total, l2_policy="batch (1 GB) larger than the 126 MB L2; same batch every step",
                                parallelism=f"reads sharded over {world} GPU(s), no data-path collective"),
                    roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=traffic,
-                                 kernel="flank scan stage: k_flank_filter + k_flank_verify (+ chunk index)",
+                                 kernel="flank scan stage (the kernels that stream the bases): k_flank_filter [scan + candidate runs + pre-check] + k_flank_verify (+ chunk index)",
+                                 whole_step=dict(achieved=algo_bytes / (ms_max / args.steps / 1e3) / 1e9, frac=algo_bytes / (ms_max / args.steps / 1e3) / 1e9 / peak,
+                                                 note="same algorithmic bytes over the WHOLE step; the barcode stage (k_barcode, ~60 % of the step) touches < 1 % of the bytes: "
+                                                      "one warp per flank match aligns all 96 barcodes with traceback + Lodhi score, issue/ALU bound"),
                                  algorithmic_bytes_per_launch=algo_bytes, ms_per_launch=scan_avg, peak_source=peak_src,
-                                 note="integer-issue bound (bit-vector DP on the ALU pipe: 79 % ALU-pipe active, ncu), not DRAM bound; "
-                                      "see DESIGN.md section 3. The barcode stage (k_barcode) reads < 1 % of the bytes and is ALU/latency bound."),
+                                 note="integer-issue bound (bit-vector DP, 23 instructions per base for both strands, ALU pipe 77 % active: "
+                                      "profiles/r1_ncu_full_final_kernels.txt), not DRAM bound; see DESIGN.md section 3"),
                    stage_ms_per_step={k: v / args.steps for k, v in stage_acc.items()},
                    e2e=e2e, gpu_launches=int(launches), clocks=clocks, rows_per_step=int(n_rows), counters=summed)
         if not args.no_cpu_baseline:
