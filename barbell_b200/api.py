@@ -36,7 +36,7 @@ EXPORTS = ["bb_groups_from_kit", "bb_groups_from_fasta", "bb_groups_add", "bb_gr
            "bb_groups_count", "bb_groups_data", "bb_groups_label", "bb_groups_free", "bb_edit_cut_off", "bb_label_range",
            "bb_lookup_barcode_seq", "bb_create",
            "bb_destroy", "bb_last_error", "bb_set_groups", "bb_annotate", "bb_annotate_device", "bb_fetch_rows",
-           "bb_submit", "bb_collect", "bb_counters", "bb_host_alloc", "bb_host_free", "bb_pack_nibbles", "bb_last_stage_ms", "bb_kernel_launches", "bb_fetch_flank_hits",
+           "bb_submit", "bb_collect", "bb_counters", "bb_host_alloc", "bb_host_free", "bb_pack_nibbles", "bb_last_stage_ms", "bb_kernel_launches", "bb_h2d_bytes", "bb_fetch_flank_hits",
            "bb_kit_info", "bb_kit_filter_patterns", "bb_pattern_parse", "bb_filter", "bb_inspect", "bb_trim",
            "bb_abi_version"]
 
@@ -81,6 +81,7 @@ def lib():
     L.bb_counters.argtypes = [vp, C.POINTER(u64)]
     L.bb_last_stage_ms.argtypes = [vp, C.POINTER(C.c_float)]
     L.bb_kernel_launches.argtypes = [vp]; L.bb_kernel_launches.restype = u64
+    L.bb_h2d_bytes.argtypes = [vp]; L.bb_h2d_bytes.restype = u64
     L.bb_fetch_flank_hits.argtypes = [vp, vp, u64, C.POINTER(u64)]
     L.bb_host_alloc.argtypes = [C.c_size_t]; L.bb_host_alloc.restype = C.c_void_p
     L.bb_host_free.argtypes = [C.c_void_p]; L.bb_host_free.restype = None
@@ -278,6 +279,10 @@ class Annotator:
 
     def kernel_launches(self) -> int:
         return int(lib().bb_kernel_launches(self._ctx))
+
+    def h2d_bytes(self) -> int:
+        """Bytes copied host -> device by annotate() / submit() so far."""
+        return int(lib().bb_h2d_bytes(self._ctx))
 
     def close(self):
         if self._ctx:

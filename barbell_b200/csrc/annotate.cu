@@ -89,7 +89,7 @@ struct Engine {
     const GroupTables* gt = nullptr;
     Params prm{};
     std::string err;
-    uint64_t launches = 0;
+    uint64_t launches = 0, h2d_bytes = 0;   // kernels launched / bytes copied host -> device by this engine
     // device buffers
     DBuf d_bases, d_offsets, d_nch, d_chunk_base, d_tile_first, d_windows, d_windows2, d_entries, d_sorted, d_cub, d_flags, d_hitkeys, d_hits, d_hist, d_rows, d_valid, d_rows_out, d_hits6;
     DBuf d_counters;                     // [0] n_entries (u32) [2] n_selected (u32) [4..5] kept reads (u64)
@@ -103,6 +103,8 @@ struct Engine {
     uint32_t* h_counters = nullptr;      // pinned, 8 x u32
     bb_row* h_rows = nullptr; size_t h_rows_cap = 0;   // pinned
     cudaEvent_t ev[6] = {};
+    cudaEvent_t ev_copy[2] = {};
+    double pack_frac = 0.6, pack_rate = 60e9, link_rate = 50e9;   // head fraction packed on the host; bytes/s estimates (see run_host)
     float stage_ms[5] = {0, 0, 0, 0, 0};
     uint32_t last_hits = 0;
     uint64_t last_rows = 0, last_reads = 0, last_kept = 0;
@@ -119,6 +121,7 @@ struct Engine {
         BB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&h_counters), 64));
         BB_CUDA(d_counters.ensure(64));
         for (auto& e : ev) BB_CUDA(cudaEventCreate(&e));
+        for (auto& e : ev_copy) BB_CUDA(cudaEventCreate(&e));
         return BB_OK;
     }
     void destroy() {
@@ -131,6 +134,7 @@ struct Engine {
         if (h_pack) cudaFreeHost(h_pack);
         d_packed.release();
         for (auto& e : ev) if (e) cudaEventDestroy(e);
+        for (auto& e : ev_copy) if (e) cudaEventDestroy(e);
         if (stream) cudaStreamDestroy(stream);
     }
     int ensure_host_rows(size_t n) {
@@ -358,25 +362,46 @@ struct Engine {
         BB_CUDA(d_bases.ensure(((total + 15) & ~15ull) + 16));
         BB_CUDA(d_offsets.ensure(static_cast<size_t>(n_reads + 1) * 8));
         if (pack_h2d && total >= (1u << 20)) {
-            // two bases per byte over PCIe: pack on the host cores, expand on the device (lossless for this path)
-            const size_t pbytes = ((total + 15) & ~15ull) / 2 + 16;
+            // Two bases per byte over PCIe for the HEAD of the batch (packed on the host cores, expanded on the device; lossless
+            // for this path) while the TAIL goes over the link as it is: the plain copy is queued first, so the DMA engine moves
+            // it while the cores pack.  The split balances the two resources: with P = pack rate and B = link rate (both measured
+            // on every batch), head fraction x solves (1 - x/2) / B = x / P.
+            const uint64_t split = std::min<uint64_t>(total, static_cast<uint64_t>(pack_frac * static_cast<double>(total))) & ~63ull;
+            const size_t pbytes = static_cast<size_t>(split / 2 + 64);
             if (pbytes > h_pack_cap) {
                 if (h_pack) cudaFreeHost(h_pack);
                 h_pack = nullptr; h_pack_cap = 0;
-                BB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&h_pack), pbytes + pbytes / 4));
-                h_pack_cap = pbytes + pbytes / 4;
+                const size_t want = static_cast<size_t>(total / 2 + 64) + static_cast<size_t>(total / 8);
+                BB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&h_pack), want));
+                h_pack_cap = want;
             }
             BB_CUDA(d_packed.ensure(pbytes));
-            pack_nibbles(bases, total, h_pack, kAlpha.code, pack_threads);
-            BB_CUDA(cudaMemcpyAsync(d_packed.p, h_pack, (total + 1) / 2, cudaMemcpyHostToDevice, stream));
-            const uint64_t n16 = (total + 15) / 16;
-            k_unpack_nibbles<<<static_cast<unsigned>((n16 + 255) / 256), 256, 0, stream>>>(d_packed.as<uint8_t>(), d_bases.as<uint8_t>(), total);
-            launches++;
-            BB_CUDA(cudaGetLastError());
+            BB_CUDA(cudaEventRecord(ev_copy[0], stream));
+            if (total > split) BB_CUDA(cudaMemcpyAsync(d_bases.as<uint8_t>() + split, bases + split, total - split, cudaMemcpyHostToDevice, stream));
+            BB_CUDA(cudaEventRecord(ev_copy[1], stream));
+            const auto t0 = std::chrono::steady_clock::now();
+            if (split) pack_nibbles(bases, split, h_pack, kAlpha.code, pack_threads);
+            const double pack_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            if (split) {
+                BB_CUDA(cudaMemcpyAsync(d_packed.p, h_pack, split / 2, cudaMemcpyHostToDevice, stream));
+                k_unpack_nibbles<<<static_cast<unsigned>((split / 16 + 255) / 256), 256, 0, stream>>>(d_packed.as<uint8_t>(), d_bases.as<uint8_t>(), split);
+                launches++;
+                BB_CUDA(cudaGetLastError());
+            }
+            BB_CUDA(cudaMemcpyAsync(d_offsets.p, offsets, static_cast<size_t>(n_reads + 1) * 8, cudaMemcpyHostToDevice, stream));
+            BB_CUDA(cudaEventSynchronize(ev_copy[1]));            // run() synchronises the stream a few kernels later anyway
+            float copy_ms = 0.f;
+            if (total - split >= (1u << 20) && cudaEventElapsedTime(&copy_ms, ev_copy[0], ev_copy[1]) == cudaSuccess && copy_ms > 0.f)
+                link_rate = 0.5 * link_rate + 0.5 * (static_cast<double>(total - split) / (copy_ms * 1e-3));
+            if (split >= (1u << 20) && pack_s > 0.0) pack_rate = 0.5 * pack_rate + 0.5 * (static_cast<double>(split) / pack_s);
+            h2d_bytes += (total - split) + split / 2 + static_cast<uint64_t>(n_reads + 1) * 8;
+            const double x = pack_rate / (link_rate + 0.5 * pack_rate);
+            pack_frac = std::min(1.0, std::max(0.05, 0.5 * pack_frac + 0.5 * x));
         } else {
             BB_CUDA(cudaMemcpyAsync(d_bases.p, bases, total, cudaMemcpyHostToDevice, stream));
+            BB_CUDA(cudaMemcpyAsync(d_offsets.p, offsets, static_cast<size_t>(n_reads + 1) * 8, cudaMemcpyHostToDevice, stream));
+            h2d_bytes += total + static_cast<uint64_t>(n_reads + 1) * 8;
         }
-        BB_CUDA(cudaMemcpyAsync(d_offsets.p, offsets, static_cast<size_t>(n_reads + 1) * 8, cudaMemcpyHostToDevice, stream));
         int rc = run(d_bases.as<uint8_t>(), d_offsets.as<uint64_t>(), n_reads, total, stream, n_rows);
         if (rc != BB_OK) return rc;
         if (*n_rows) {
@@ -732,6 +757,12 @@ int bb_last_stage_ms(bb_ctx* c, float out[5]) {
     if (!c || !out) return BB_ERR_INVALID;
     for (int i = 0; i < 5; i++) out[i] = c->eng[c->last_engine].stage_ms[i];
     return BB_OK;
+}
+
+uint64_t bb_h2d_bytes(const bb_ctx* c) {
+    uint64_t n = 0;
+    if (c) for (const auto& e : c->eng) n += e.h2d_bytes;
+    return n;
 }
 
 uint64_t bb_kernel_launches(const bb_ctx* c) {

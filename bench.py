@@ -138,6 +138,8 @@ def main():
     ap.add_argument("--cpu-reads", type=int, default=40000, help="reads of the batch timed on the host cores for cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-sub", type=int, default=4, help="sub-batches per step of the end-to-end leg")
+    ap.add_argument("--e2e-depth", type=int, default=4, help="sub-batches in flight (<= BB_MAX_INFLIGHT = 4)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -207,7 +209,7 @@ def main():
     # ---- end to end: pinned host buffers through bb_submit / bb_collect (two streams), copies inside the timed region ----
     e2e = None
     if not args.no_e2e:
-        n_sub = 4
+        n_sub, depth = args.e2e_sub, args.e2e_depth
         cuts = np.linspace(0, n_reads, n_sub + 1).astype(int)
         subs = []
         for i in range(n_sub):
@@ -222,7 +224,7 @@ def main():
             jobs = [(s, i) for s in range(n_steps) for i in range(n_sub)]
             inflight = nxt = 0
             while nxt < len(jobs) or inflight:
-                while nxt < len(jobs) and inflight < 2:
+                while nxt < len(jobs) and inflight < depth:
                     hb, ho, nr = subs[jobs[nxt][1]]
                     an.submit(hb.data_ptr(), ho.data_ptr(), nr, tag=nxt)
                     nxt += 1; inflight += 1
@@ -234,34 +236,39 @@ def main():
             nonlocal an
             an_saved, an = an, annot
             try:
-                e2e_pass(1)
+                e2e_pass(2)                              # warm-up (the packed mode also settles its head/tail split here)
                 barrier()
+                b0 = annot.h2d_bytes()
                 t0 = time.perf_counter()
                 rows = e2e_pass(args.steps)
                 torch.cuda.synchronize()
                 dt = time.perf_counter() - t0
+                moved = (annot.h2d_bytes() - b0) // args.steps
             finally:
                 an = an_saved
             te = torch.tensor([dt], dtype=torch.float64, device="cuda")
             if world > 1:
                 dist.all_reduce(te, op=dist.ReduceOp.MAX)
-            return float(te.item()), rows
+            return float(te.item()), rows, int(moved)
 
-        dt_plain, rows_e2e = timed_e2e(an)
-        # same call with bb_opts.flags bit 1: the library nibble-packs the bases on the host cores, so PCIe moves half the bytes
+        dt_plain, rows_e2e, moved_plain = timed_e2e(an)
+        # same call with bb_opts.flags bit 1: the library nibble-packs the HEAD of every batch on the host cores while the tail is
+        # copied as it is (the split adapts to the measured pack and link rates), so PCIe moves fewer bytes
         an_pack = bb.Annotator(gs, device=local, pack_h2d=True)
-        dt_pack, rows_pack = timed_e2e(an_pack)
+        dt_pack, rows_pack, moved_pack = timed_e2e(an_pack)
         an_pack.close()
-        assert rows_pack == rows_e2e
-        modes = {"plain": (dt_plain, int(h2d)), "packed": (dt_pack, int(h2d - total + (total + 1) // 2))}
+        assert rows_pack == rows_e2e and moved_plain == h2d
+        modes = {"plain": (dt_plain, moved_plain), "packed": (dt_pack, moved_pack)}
         best = min(modes, key=lambda k: modes[k][0])
         dt = modes[best][0]
         e2e = dict(value=world * n_reads * args.steps / dt, unit="reads/s", h2d_bytes_per_step=modes[best][1],
                    d2h_bytes_per_step=int(rows_e2e // args.steps * 88),
-                   api="bb_submit/bb_collect, pinned host buffers, 2 streams; mode=" + best +
-                       (" (bases nibble-packed by the library on the host cores before the copy, expanded on the device)" if best == "packed" else ""),
+                   api=f"bb_submit/bb_collect, pinned host buffers, {n_sub} sub-batches per step, {depth} in flight; mode=" + best +
+                       (" (head of every batch nibble-packed by the library on the host cores and expanded on the device, tail copied as it is; "
+                        "bytes counted by the library: bb_h2d_bytes)" if best == "packed" else ""),
                    gbases_per_s=world * total * args.steps / dt / 1e9,
-                   by_mode={k: world * n_reads * args.steps / v[0] for k, v in modes.items()})
+                   by_mode={k: world * n_reads * args.steps / v[0] for k, v in modes.items()},
+                   h2d_bytes_by_mode={k: v[1] for k, v in modes.items()})
 
     counters = an.counters()
     summed = sharding.all_reduce_counters(counters["total"], counters["kept"]) if world > 1 else counters

@@ -73,7 +73,8 @@ typedef struct {
     uint64_t max_batch_bytes;   /* capacity of the staging buffers for bb_annotate (0 = 256 MiB) */
     uint32_t max_batch_reads;   /* (0 = 4 Mi reads) */
     uint32_t flags;             /* bit 0: disable the lossless pre-filter (exact full-length scan everywhere);
-                                   bit 1: nibble-pack the bases on the host cores before the PCIe copy (bb_annotate / bb_submit) */
+                                   bit 1: nibble-pack the head of every batch on the host cores before the PCIe copy while the tail is copied
+                                   as it is; the split adapts to the measured pack and link rates (bb_annotate / bb_submit) */
 } bb_opts;
 
 typedef struct bb_ctx bb_ctx;
@@ -123,11 +124,12 @@ int  bb_annotate_device(bb_ctx *ctx, const void *d_bases, const void *d_offsets,
                         void *stream, uint64_t *n_rows);
 int  bb_fetch_rows(bb_ctx *ctx, bb_row *rows, uint64_t rows_cap, uint64_t *n_rows);
 
-/* Pipelined form: up to BB_MAX_INFLIGHT batches may be submitted before the first collect; batches alternate between
-   two CUDA streams so the host->device copy of one overlaps the kernels of the other.  The caller owns `bases` and
+/* Pipelined form: up to BB_MAX_INFLIGHT batches may be submitted before the first collect; batches rotate over that many
+   CUDA streams (each with its own worker thread and device buffers) so that the host-side packing, the host->device copy
+   and the kernels of different batches overlap.  The caller owns `bases` and
    `offsets` until bb_collect has returned that batch_tag (they are read by the DMA engine in place: use pinned memory
    for full PCIe speed).  `rows` returned by bb_collect stay valid until the next bb_submit / bb_collect on the ctx. */
-#define BB_MAX_INFLIGHT 2
+#define BB_MAX_INFLIGHT 4
 int  bb_submit(bb_ctx *ctx, const uint8_t *bases, const uint64_t *offsets, uint32_t n_reads, uint64_t batch_tag);
 int  bb_collect(bb_ctx *ctx, uint64_t *batch_tag, const bb_row **rows, uint64_t *n_rows);
 
@@ -137,6 +139,8 @@ int  bb_counters(const bb_ctx *ctx, uint64_t out[3]);
 int  bb_last_stage_ms(bb_ctx *ctx, float out[5]);
 /* number of kernels this library launched since bb_create */
 uint64_t bb_kernel_launches(const bb_ctx *ctx);
+/* bytes copied host -> device by bb_annotate / bb_submit so far (with flags bit 1 the head of every batch travels nibble-packed) */
+uint64_t bb_h2d_bytes(const bb_ctx *ctx);
 /* debugging / parity of the flank stage alone: the hit list after the flank search of the last bb_annotate_device call,
    6 int32 per hit {read_idx, group, strand, text_start, text_end, cost} in (read, group, Fwd-before-Rc, end) order */
 int  bb_fetch_flank_hits(bb_ctx *ctx, int32_t *out6, uint64_t cap, uint64_t *n_hits);
