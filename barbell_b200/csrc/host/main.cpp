@@ -5,8 +5,13 @@
 // file exactly like the reference's csv writer, annotator.rs:20-24).
 // `filter`, `inspect` and `trim` (bin/main.rs:113-209, 340-395) are thin wrappers over bb_filter / bb_inspect / bb_trim, and
 // `kit` chains annotate -> inspect -> filter -> trim with the reference's fixed file names (src/kits/use_kit.rs:11-109).
+#include <fcntl.h>
+#include <sys/mman.h>
 #include <sys/stat.h>
+#include <unistd.h>
 #include <zlib.h>
+
+#include <atomic>
 
 #include <chrono>
 #include <cstdio>
@@ -15,6 +20,7 @@
 #include <algorithm>
 #include <condition_variable>
 #include <deque>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -35,7 +41,8 @@ struct Args {
     std::string dropped, failed_out, only_side, read_pattern_out;
     bool no_label = false, no_orientation = false, no_flanks = false, sort_labels = false, skip_trim = false, flip = false;
     int top_n = 10, bucket_size = 250;
-    bool output_given = false;
+    bool output_given = false, single_reader = false;
+    size_t chunk_kb = 0;
     double min_score = 0.2, min_score_diff = 0.1;
     float alpha = 0.4f;
     size_t batch_mb = 256;
@@ -97,6 +104,8 @@ Args parse(int argc, char** argv) {
         else if (f == "--batch-mb") a.batch_mb = static_cast<size_t>(std::atol(one().c_str()));
         else if (f == "--failed-out") a.failed_out = one();
         else if (f == "--verbose") a.verbose = true;
+        else if (f == "--single-reader") a.single_reader = true;
+        else if (f == "--chunk-kb") a.chunk_kb = static_cast<size_t>(std::atol(one().c_str()));
         else if (f == "--use-extended") a.use_extended = true;
         else if (f == "--maximize") a.maximize = true;
         else if (f == "--gzip") a.gzip = true;
@@ -115,14 +124,25 @@ struct Batch {
     uint32_t n_reads = 0;
     std::vector<char> id_chars;          // read ids back to back
     std::vector<uint32_t> id_off;        // n_reads + 1
-    bool alloc(size_t cb, size_t cr) {
-        cap_bytes = cb; cap_reads = cr;
-        bases = static_cast<uint8_t*>(bb_host_alloc(cb + 64));
-        offsets = static_cast<uint64_t*>(bb_host_alloc((cr + 1) * sizeof(uint64_t)));
+    bool pinned = true;
+    bool alloc(size_t cb, size_t cr, bool pin = true) {
+        cap_bytes = cb; cap_reads = cr; pinned = pin;
+        bases = static_cast<uint8_t*>(pin ? bb_host_alloc(cb + 64) : std::malloc(cb + 64));
+        offsets = static_cast<uint64_t*>(pin ? bb_host_alloc((cr + 1) * sizeof(uint64_t)) : std::malloc((cr + 1) * sizeof(uint64_t)));
         return bases && offsets;
     }
     void clear() { bytes = 0; n_reads = 0; id_chars.clear(); id_off.assign(1, 0); if (offsets) offsets[0] = 0; }
-    void release() { bb_host_free(bases); bb_host_free(offsets); bases = nullptr; offsets = nullptr; }
+    void append(const char* id, size_t id_len, const char* seq, size_t seq_len) {
+        std::memcpy(bases + bytes, seq, seq_len);
+        bytes += seq_len;
+        offsets[++n_reads] = bytes;
+        id_chars.insert(id_chars.end(), id, id + id_len);
+        id_off.push_back(static_cast<uint32_t>(id_chars.size()));
+    }
+    void release() {
+        if (pinned) { bb_host_free(bases); bb_host_free(offsets); } else { std::free(bases); std::free(offsets); }
+        bases = nullptr; offsets = nullptr;
+    }
 };
 
 // hand-off between the reader thread and the GPU/writer thread
@@ -133,6 +153,257 @@ class Channel {
     T pop() { std::unique_lock<std::mutex> lk(mu_); cv_.wait(lk, [&] { return !q_.empty(); }); T v = q_.front(); q_.pop_front(); return v; }
   private:
     std::mutex mu_; std::condition_variable cv_; std::deque<T> q_;
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// Batch sources: FASTQ -> page-locked batches, delivered to the GPU/writer thread IN INPUT ORDER.
+//   SequentialSource  one reader thread over FastqReader (gzip or plain), like paraseq's reader thread (annotator.rs:278-280)
+//   ParallelSource    plain (uncompressed) files only: the files are mapped, cut into chunks at record boundaries and parsed
+//                     by several threads; chunk i always lands in slot i % n_slots, so batches come out in file order and a
+//                     parser only ever waits for EARLIER chunks to be collected (no deadlock).
+// ---------------------------------------------------------------------------------------------------------------
+class BatchSource {
+  public:
+    virtual ~BatchSource() {}
+    virtual int next_filled() = 0;          // slot index; -1 = end of input; -2 = error (see error())
+    virtual void release(int slot) = 0;     // the batch in `slot` has been collected
+    virtual void abort() = 0;               // consumer gives up: unblock the producers
+    virtual void join() = 0;
+    virtual const std::string& error() const = 0;
+};
+
+class SequentialSource : public BatchSource {
+  public:
+    SequentialSource(const std::vector<std::string>& paths, std::vector<Batch>& slots) : slots_(slots) {
+        for (size_t s = 0; s < slots.size(); s++) free_.push(static_cast<int>(s));
+        thread_ = std::thread([this, paths] { run(paths); });
+    }
+    int next_filled() override { return filled_.pop(); }
+    void release(int slot) override { free_.push(slot); }
+    void abort() override { for (size_t s = 0; s < slots_.size() + 2; s++) free_.push(-1); }
+    void join() override { if (thread_.joinable()) thread_.join(); }
+    const std::string& error() const override { return err_; }
+
+  private:
+    void run(const std::vector<std::string>& paths) {
+        FastqReader reader(paths);
+        FastqReader::View v;
+        int cur = free_.pop();
+        if (cur < 0) return;
+        slots_[cur].clear();
+        for (;;) {
+            std::string err;
+            const bool more = reader.next(v, err);
+            if (!more && !err.empty()) { err_ = err; filled_.push(-2); return; }
+            Batch* B = &slots_[cur];
+            if (more && v.seq_len > B->cap_bytes) { err_ = "read longer than the batch buffer (raise --batch-mb)"; filled_.push(-2); return; }
+            const bool full = more && (B->bytes + v.seq_len > B->cap_bytes || B->n_reads + 1 > B->cap_reads);
+            if ((full || !more) && B->n_reads > 0) {
+                filled_.push(cur);
+                if (!more) break;
+                cur = free_.pop();
+                if (cur < 0) return;                              // consumer aborted
+                B = &slots_[cur];
+                B->clear();
+            }
+            if (!more) break;
+            B->append(v.id, v.id_len, v.seq, v.seq_len);
+        }
+        filled_.push(-1);
+    }
+    std::vector<Batch>& slots_;
+    Channel<int> free_, filled_;
+    std::thread thread_;
+    std::string err_;
+};
+
+class ParallelSource : public BatchSource {
+  public:
+    // every path must be a plain (not gzip) regular file; chunk_bytes <= batch capacity
+    static bool usable(const std::vector<std::string>& paths) {
+        for (const auto& p : paths) {
+            FILE* f = std::fopen(p.c_str(), "rb");
+            if (!f) return false;
+            unsigned char m[2] = {0, 0};
+            const size_t n = std::fread(m, 1, 2, f);
+            std::fclose(f);
+            struct stat st;
+            if (stat(p.c_str(), &st) != 0 || !S_ISREG(st.st_mode)) return false;
+            if (n == 2 && m[0] == 0x1f && m[1] == 0x8b) return false;
+        }
+        return !paths.empty();
+    }
+    ParallelSource(const std::vector<std::string>& paths, std::vector<Batch>& slots, size_t chunk_bytes, int n_threads)
+        : slots_(slots), chunk_(chunk_bytes), round_(slots.size(), 0) {
+        for (const auto& p : paths) {
+            File f; f.path = p;
+            f.fd = ::open(p.c_str(), O_RDONLY);
+            struct stat st;
+            if (f.fd < 0 || fstat(f.fd, &st) != 0) { err_ = "Failed to open FASTQ input: " + p; failed_ = true; break; }
+            f.size = static_cast<size_t>(st.st_size);
+            if (f.size) {
+                void* m = mmap(nullptr, f.size, PROT_READ, MAP_PRIVATE, f.fd, 0);
+                if (m == MAP_FAILED) { err_ = "mmap failed: " + p; failed_ = true; ::close(f.fd); break; }
+                madvise(m, f.size, MADV_SEQUENTIAL);
+                f.map = static_cast<const char*>(m);
+            }
+            f.first_chunk = n_chunks_;
+            n_chunks_ += (f.size + chunk_ - 1) / chunk_;
+            files_.push_back(f);
+        }
+        done_.assign(n_chunks_, 0);
+        if (failed_) return;
+        for (int t = 0; t < std::max(1, n_threads); t++) workers_.emplace_back([this] { work(); });
+    }
+    ~ParallelSource() override {
+        join();
+        for (auto& f : files_) { if (f.map) munmap(const_cast<char*>(f.map), f.size); if (f.fd >= 0) ::close(f.fd); }
+    }
+    int next_filled() override {
+        if (failed_) return -2;
+        for (;;) {
+            std::unique_lock<std::mutex> lk(mu_);
+            if (deliver_ >= n_chunks_) return -1;
+            cv_.wait(lk, [&] { return done_[deliver_] != 0; });
+            if (done_[deliver_] == 2) return -2;
+            const int slot = static_cast<int>(deliver_ % slots_.size());
+            deliver_++;
+            if (slots_[slot].n_reads == 0) { round_[slot]++; cv_.notify_all(); continue; }   // chunk without a record start
+            return slot;
+        }
+    }
+    void release(int slot) override { { std::lock_guard<std::mutex> lk(mu_); round_[slot]++; } cv_.notify_all(); }
+    void abort() override { { std::lock_guard<std::mutex> lk(mu_); aborted_ = true; } cv_.notify_all(); }
+    void join() override { for (auto& w : workers_) if (w.joinable()) w.join(); workers_.clear(); }
+    const std::string& error() const override { return err_; }
+
+  private:
+    struct File { std::string path; int fd = -1; size_t size = 0; const char* map = nullptr; size_t first_chunk = 0; };
+
+    // one line [p, e) without its terminator; next = start of the following line
+    static void line_at(const char* m, size_t size, size_t p, size_t& e, size_t& next) {
+        const char* nl = static_cast<const char*>(std::memchr(m + p, '\n', size - p));
+        e = nl ? static_cast<size_t>(nl - m) : size;
+        next = nl ? e + 1 : size;
+        if (e > p && m[e - 1] == '\r') e--;
+    }
+    // first record start at or after pos: a line "@..." whose third line starts with '+' and whose fourth line is as long as
+    // its second (a quality line may start with '@' too, but then the line two below is a sequence, never a '+' line)
+    static size_t record_start(const char* m, size_t size, size_t pos) {
+        if (pos == 0) return 0;
+        if (pos >= size) return size;
+        size_t p = pos;
+        if (m[pos - 1] != '\n') {
+            const char* nl = static_cast<const char*>(std::memchr(m + pos, '\n', size - pos));
+            if (!nl) return size;
+            p = static_cast<size_t>(nl - m) + 1;
+        }
+        while (p < size) {
+            size_t e0, n0, e1, n1, e2, n2, e3, n3;
+            line_at(m, size, p, e0, n0);
+            if (m[p] == '@' && n0 < size) {
+                line_at(m, size, n0, e1, n1);
+                if (n1 < size) {
+                    line_at(m, size, n1, e2, n2);
+                    if (e2 > n1 && m[n1] == '+' && n2 <= size) {
+                        if (n2 < size) line_at(m, size, n2, e3, n3); else { e3 = n2; n3 = n2; }
+                        if (e3 - n2 == e1 - n0) return p;
+                    }
+                }
+            }
+            p = n0;
+        }
+        return size;
+    }
+    bool parse_chunk(const File& f, size_t k, Batch& B, std::string& err) {
+        const char* m = f.map;
+        const size_t begin = record_start(m, f.size, k * chunk_), end = record_start(m, f.size, std::min(f.size, (k + 1) * chunk_));
+        size_t p = begin;
+        while (p < end) {
+            size_t e0, n0, e1, n1, e2, n2, e3, n3;
+            line_at(m, f.size, p, e0, n0);
+            if (e0 == p) { p = n0; continue; }                     // blank line between records
+            if (n0 >= f.size) { err = "truncated FASTQ record in " + f.path; return false; }
+            line_at(m, f.size, n0, e1, n1);
+            if (n1 >= f.size) { err = "truncated FASTQ record in " + f.path; return false; }
+            line_at(m, f.size, n1, e2, n2);
+            if (n2 < f.size) line_at(m, f.size, n2, e3, n3); else { e3 = n2; n3 = n2; }
+            if (m[p] != '@' || e2 == n1 || m[n1] != '+') { err = "malformed FASTQ record in " + f.path; return false; }
+            if (e3 - n2 != e1 - n0) { err = "truncated FASTQ record (quality length differs from sequence length) in " + f.path; return false; }
+            const size_t seq_len = e1 - n0;
+            if (B.bytes + seq_len > B.cap_bytes || B.n_reads + 1 > B.cap_reads) { err = "read longer than the batch buffer (raise --batch-mb)"; return false; }
+            size_t idl = 0;
+            const char* id = m + p + 1;
+            auto ws = [](char c) { return c == ' ' || c == '\t' || c == '\v' || c == '\f' || c == '\r'; };
+            while (idl < e0 - p - 1 && !ws(id[idl])) idl++;
+            B.append(id, idl, m + n0, seq_len);
+            p = n3;
+        }
+        return true;
+    }
+    void work() {
+        for (;;) {
+            const size_t i = claim_.fetch_add(1);
+            if (i >= n_chunks_) return;
+            const size_t slot = i % slots_.size(), need = i / slots_.size();
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return aborted_ || round_[slot] == need; });
+                if (aborted_) return;
+            }
+            const File* f = &files_[0];
+            for (const auto& ff : files_) if (i >= ff.first_chunk) f = &ff;
+            Batch& B = slots_[slot];
+            B.clear();
+            std::string err;
+            const bool ok = parse_chunk(*f, i - f->first_chunk, B, err);
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                if (!ok && err_.empty()) err_ = err;
+                done_[i] = ok ? 1 : 2;
+            }
+            cv_.notify_all();
+            if (!ok) return;
+        }
+    }
+    std::vector<Batch>& slots_;
+    size_t chunk_, n_chunks_ = 0, deliver_ = 0;
+    std::vector<File> files_;
+    std::vector<uint64_t> round_;            // how often each slot has been released
+    std::vector<uint8_t> done_;              // per chunk: 0 pending, 1 parsed, 2 error
+    std::atomic<size_t> claim_{0};
+    std::mutex mu_;
+    std::condition_variable cv_;
+    std::vector<std::thread> workers_;
+    std::string err_;
+    bool failed_ = false, aborted_ = false;
+};
+
+// Slots + source for a run: plain files are cut into chunks of `chunk` FASTQ bytes (<= chunk/2 bases each) and parsed by up to
+// 8 of the -t threads; anything else (gzip, pipes, -t 1, --single-reader) goes through one reader thread.
+struct Ingest {
+    std::vector<Batch> slots;
+    std::unique_ptr<BatchSource> source;
+    bool parallel = false;
+    bool open(const Args& a, int in_flight, bool pinned, std::string& err) {
+        const size_t cap_bytes = a.batch_mb << 20, cap_reads = 1u << 22;
+        const int parse_threads = std::min(8, std::max(1, a.threads));
+        parallel = parse_threads > 1 && !a.single_reader && ParallelSource::usable(a.input);
+        size_t chunk = a.chunk_kb ? a.chunk_kb << 10 : cap_bytes, n_chunks = 0;
+        if (parallel) {
+            for (const auto& p : a.input) { struct stat st; if (stat(p.c_str(), &st) == 0) n_chunks += (static_cast<size_t>(st.st_size) + chunk - 1) / chunk; }
+        }
+        // sequential: in flight + one filled + the one being filled; parallel: in flight + one per parser (fewer for small inputs)
+        const size_t n_slots = parallel ? std::max<size_t>(2, std::min<size_t>(in_flight + parse_threads, n_chunks + 1)) : static_cast<size_t>(in_flight + 2);
+        // a chunk holds at most chunk/2 bases plus the tail of the record that straddles its end (16 MB covers the longest reads)
+        const size_t slot_bytes = parallel ? std::min(cap_bytes, chunk / 2) + (16u << 20) : cap_bytes;
+        slots.resize(n_slots);
+        for (auto& b : slots) if (!b.alloc(slot_bytes, cap_reads, pinned)) { err = pinned ? "pinned host allocation failed" : "host allocation failed"; return false; }
+        if (parallel) source.reset(new ParallelSource(a.input, slots, chunk, parse_threads));
+        else source.reset(new SequentialSource(a.input, slots));
+        return true;
+    }
+    void close() { if (source) { source->join(); source.reset(); } for (auto& b : slots) b.release(); slots.clear(); }
 };
 
 const char* kTypeNames[] = {"Ftag", "Rtag", "Fflank", "Rflank"};
@@ -181,51 +452,19 @@ int run_annotate(const Args& a, const std::string& out_path) {
     static char outbuf[1 << 22];
     std::setvbuf(out, outbuf, _IOFBF, sizeof outbuf);
 
-    const size_t cap_bytes = a.batch_mb << 20, cap_reads = 1u << 22;
-    const int n_slots = 2 * n_gpus + 2;                 // 2 in flight per GPU + one filled + the one being filled
-    std::vector<Batch> slots(n_slots);
-    for (auto& b : slots) if (!b.alloc(cap_bytes, cap_reads)) { std::printf("Error during processing: pinned host allocation failed\n"); return BB_ERR_CUDA; }
+    Ingest ingest;
+    {
+        std::string ierr;
+        if (!ingest.open(a, 2 * n_gpus, true, ierr)) { std::printf("Error during processing: %s\n", ierr.c_str()); return BB_ERR_CUDA; }
+    }
+    std::vector<Batch>& slots = ingest.slots;
+    BatchSource* source = ingest.source.get();
 
     struct Flight { int slot, dev; };
     std::deque<Flight> flight;
     uint64_t total_reads = 0, total_rows = 0, kept = 0, submitted = 0;
     bool header_written = false;
     auto t0 = std::chrono::steady_clock::now();
-    Channel<int> free_slots, filled;                 // slot indices; filled: -1 = end of input, -2 = reader error
-    for (int s2 = 0; s2 < n_slots; s2++) free_slots.push(s2);
-    std::string reader_err;
-
-    // reader thread: FASTQ -> page-locked batches (annotator.rs:278-280: paraseq's reader thread fills record batches)
-    std::thread reader_thread([&] {
-        FastqReader reader(a.input);
-        FastqReader::View v;
-        int cur = free_slots.pop();
-        slots[cur].clear();
-        for (;;) {
-            std::string err;
-            const bool more = reader.next(v, err);
-            if (!more && !err.empty()) { reader_err = err; filled.push(-2); return; }
-            Batch* B = &slots[cur];
-            if (more && v.seq_len > B->cap_bytes) { reader_err = "read longer than the batch buffer (raise --batch-mb)"; filled.push(-2); return; }
-            const bool full = more && (B->bytes + v.seq_len > B->cap_bytes || B->n_reads + 1 > B->cap_reads);
-            if ((full || !more) && B->n_reads > 0) {
-                filled.push(cur);
-                if (!more) break;
-                cur = free_slots.pop();
-                if (cur < 0) return;                              // consumer aborted
-                B = &slots[cur];
-                B->clear();
-            }
-            if (!more) break;
-            std::memcpy(B->bases + B->bytes, v.seq, v.seq_len);
-            B->bytes += v.seq_len;
-            B->offsets[++B->n_reads] = B->bytes;
-            B->id_chars.insert(B->id_chars.end(), v.id, v.id + v.id_len);
-            B->id_off.push_back(static_cast<uint32_t>(B->id_chars.size()));
-        }
-        filled.push(-1);
-    });
-
     auto collect_one = [&]() -> int {
         const Flight f = flight.front(); flight.pop_front();
         uint64_t tag = 0, n_rows = 0; const bb_row* rows = nullptr;
@@ -249,15 +488,15 @@ int run_annotate(const Args& a, const std::string& out_path) {
                          bb_groups_label(gs, w.group_idx, w.label_idx), w.strand ? "Rc" : "Fwd");
         }
         total_rows += n_rows;
-        free_slots.push(f.slot);
+        source->release(f.slot);
         return BB_OK;
     };
 
     rc = BB_OK;
     for (;;) {
-        const int cur = filled.pop();
+        const int cur = source->next_filled();
         if (cur == -1) break;
-        if (cur == -2) { std::printf("Error during processing: %s\n", reader_err.c_str()); rc = BB_ERR_IO; break; }
+        if (cur == -2) { std::printf("Error during processing: %s\n", source->error().c_str()); rc = BB_ERR_IO; break; }
         Batch& B = slots[cur];
         const int dev = static_cast<int>(submitted % n_gpus);
         size_t on_dev = 0; for (const auto& f : flight) on_dev += f.dev == dev;
@@ -270,8 +509,8 @@ int run_annotate(const Args& a, const std::string& out_path) {
         total_reads += B.n_reads;
     }
     while (!flight.empty() && rc == BB_OK) rc = collect_one();
-    if (rc != BB_OK) { for (int s2 = 0; s2 < n_slots + 2; s2++) free_slots.push(-1); }   // unblock the reader
-    reader_thread.join();
+    if (rc != BB_OK) source->abort();                // unblock the producers
+    source->join();
     std::fclose(out);
     const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     if (rc == BB_OK) {
@@ -279,7 +518,7 @@ int run_annotate(const Args& a, const std::string& out_path) {
                     static_cast<unsigned long long>(kept), static_cast<unsigned long long>(total_reads - kept),
                     static_cast<unsigned long long>(total_rows), secs, secs > 0 ? total_reads / secs : 0.0);
     }
-    for (auto& b : slots) b.release();
+    ingest.close();
     for (auto* c : ctx) bb_destroy(c);
     bb_groups_free(gs);
     return rc;
@@ -289,15 +528,29 @@ int run_annotate(const Args& a, const std::string& out_path) {
 
 // `barbell fastq-stats -i files...`: parse only (no GPU): records, bases, FNV-1a of ids and sequences (reader self-check)
 int run_fastq_stats(const Args& a) {
-    FastqReader reader(a.input);
-    FastqReader::View v;
+    Ingest ingest;
     std::string err;
-    uint64_t n = 0, bases = 0, h = 1469598103934665603ull;
+    if (!ingest.open(a, 1, false, err)) { std::printf("Error during processing: %s\n", err.c_str()); return 1; }
+    uint64_t n = 0, bases = 0, batches = 0, h = 1469598103934665603ull;
     auto mix = [&](const char* p, size_t len) { for (size_t i = 0; i < len; i++) { h ^= static_cast<unsigned char>(p[i]); h *= 1099511628211ull; } h ^= 0xff; h *= 1099511628211ull; };
-    while (reader.next(v, err)) { n++; bases += v.seq_len; mix(v.id, v.id_len); mix(v.seq, v.seq_len); }
-    if (!err.empty()) { std::printf("Error during processing: %s\n", err.c_str()); return 1; }
-    std::printf("records=%llu bases=%llu fnv=%016llx\n", static_cast<unsigned long long>(n), static_cast<unsigned long long>(bases), static_cast<unsigned long long>(h));
-    return 0;
+    int rc = 0;
+    for (;;) {
+        const int cur = ingest.source->next_filled();
+        if (cur == -1) break;
+        if (cur == -2) { std::printf("Error during processing: %s\n", ingest.source->error().c_str()); rc = 1; ingest.source->abort(); break; }
+        const Batch& B = ingest.slots[cur];
+        for (uint32_t r = 0; r < B.n_reads; r++) {
+            mix(B.id_chars.data() + B.id_off[r], B.id_off[r + 1] - B.id_off[r]);
+            mix(reinterpret_cast<const char*>(B.bases) + B.offsets[r], B.offsets[r + 1] - B.offsets[r]);
+        }
+        n += B.n_reads; bases += B.bytes; batches++;
+        ingest.source->release(cur);
+    }
+    const bool par = ingest.parallel;
+    ingest.close();
+    if (rc == 0) std::printf("records=%llu bases=%llu fnv=%016llx batches=%llu reader=%s\n", static_cast<unsigned long long>(n), static_cast<unsigned long long>(bases),
+                             static_cast<unsigned long long>(h), static_cast<unsigned long long>(batches), par ? "parallel" : "sequential");
+    return rc;
 }
 
 // `barbell filter` (bin/main.rs:340-354, filter_from_text_file filter.rs:137-181)

@@ -18,10 +18,12 @@ def fnv(records):
     return h
 
 
-def stats(paths):
-    r = subprocess.run([EXE, "fastq-stats", "-i"] + [str(p) for p in paths], capture_output=True, text=True, timeout=60)
+def stats(paths, *extra, want_reader=None):
+    r = subprocess.run([EXE, "fastq-stats", "-i"] + [str(p) for p in paths] + list(extra), capture_output=True, text=True, timeout=60)
     assert r.returncode == 0, r.stdout + r.stderr
     kv = dict(x.split("=") for x in r.stdout.split())
+    if want_reader:
+        assert kv["reader"] == want_reader, kv
     return int(kv["records"]), int(kv["bases"]), int(kv["fnv"], 16)
 
 
@@ -55,3 +57,37 @@ def test_reader_variants(tmp_path):
     assert r.returncode != 0 and "truncated" in r.stdout
     r = subprocess.run([EXE, "fastq-stats", "-i", str(tmp_path / "nope.fastq")], capture_output=True, text=True)
     assert r.returncode != 0 and "Failed to open" in r.stdout
+
+
+def test_parallel_chunked_reader_equals_sequential(tmp_path):
+    """Plain files are cut into chunks at record boundaries and parsed by several threads; batches must come out in input order
+    whatever the chunk size (records spanning chunks, chunks without a record start, '@' as the first quality character)."""
+    import random
+    rnd = random.Random(11)
+    recs = [(f"r{i}/x".encode(), bytes(rnd.choice(b"ACGTN") for _ in range(rnd.choice([0, 1, 3, 50, 700, 5000, 70000])))) for i in range(150)]
+
+    def text(rs, nl="\n", final_nl=True):
+        out = []
+        for i, (rid, seq) in enumerate(rs):
+            qual = "".join(rnd.choice("@+I5") for _ in seq)          # quality lines that LOOK like headers / separators
+            out.append(f"@{rid.decode()} ch={i}{nl}{seq.decode()}{nl}+{nl}{qual}{nl}")
+        t = "".join(out)
+        return t if final_nl else t[:-len(nl)]
+    want = (len(recs), sum(len(s) for _, s in recs), fnv(recs))
+    pa, pb, pc = tmp_path / "a.fastq", tmp_path / "b.fastq", tmp_path / "c.fastq"
+    pa.write_text(text(recs[:70])); pb.write_bytes(text(recs[70:110], nl="\r\n").encode()); pc.write_text(text(recs[110:], final_nl=False))
+    assert stats([pa, pb, pc], "--single-reader", want_reader="sequential") == want
+    for chunk_kb, threads in [(1, 8), (3, 4), (64, 8), (300, 3), (100000, 8)]:
+        assert stats([pa, pb, pc], "--chunk-kb", str(chunk_kb), "-t", str(threads), want_reader="parallel") == want, (chunk_kb, threads)
+    # -t 1 and gzip inputs fall back to the single reader thread
+    assert stats([pa, pb, pc], "-t", "1", want_reader="sequential") == want
+    pz = tmp_path / "z.fastq.gz"
+    with gzip.open(pz, "wt") as f:
+        f.write(text(recs[:5]))
+    stats([pa, pz], want_reader="sequential")
+    # errors surface from the parser threads too
+    bad = tmp_path / "bad.fastq"; bad.write_text(text(recs[:20]) + "@r1\nACGT\n+\nII\n" + text(recs[20:40]))
+    r = subprocess.run([EXE, "fastq-stats", "-i", str(bad), "--chunk-kb", "2", "-t", "4"], capture_output=True, text=True, timeout=60)
+    assert r.returncode != 0 and ("quality length" in r.stdout or "malformed" in r.stdout), r.stdout
+    empty = tmp_path / "empty.fastq"; empty.write_text("")
+    assert stats([empty, pa], "--chunk-kb", "4")[0] == 70
