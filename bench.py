@@ -200,6 +200,7 @@ def main():
     clocks = sampler.stop(t_mark0, sampler.mark())
     launches = an.kernel_launches() - l0
     ms = ev0.elapsed_time(ev1)
+    hist_local = sharding.label_histogram(an.fetch_rows(int(n_rows)), G)     # rows of the last timed step (outside the timed region)
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -272,6 +273,8 @@ def main():
 
     counters = an.counters()
     summed = sharding.all_reduce_counters(counters["total"], counters["kept"]) if world > 1 else counters
+    # per-barcode row counts of the last step, summed over the ranks (the one other collective of the path)
+    hist = sharding.all_reduce_label_counts(hist_local)
 
     if rank == 0:
         peak, peak_src = peaks()
@@ -300,7 +303,9 @@ def main():
                                  note="integer-issue bound (bit-vector DP, 23 instructions per base for both strands, ALU pipe 77 % active: "
                                       "profiles/r1_ncu_full_final_kernels.txt), not DRAM bound; see DESIGN.md section 3"),
                    stage_ms_per_step={k: v / args.steps for k, v in stage_acc.items()},
-                   e2e=e2e, gpu_launches=int(launches), clocks=clocks, rows_per_step=int(n_rows), counters=summed)
+                   e2e=e2e, gpu_launches=int(launches), clocks=clocks, rows_per_step=int(n_rows), counters=summed,
+                   label_counts=dict(labels_seen=int((hist[1:] > 0).sum()), rows=int(hist.sum()), flank_only_rows=int(hist[0]),
+                                     note="rows per barcode of the last step, all ranks (all_reduce of %d int64)" % len(hist)))
         if not args.no_cpu_baseline:
             import oracle_lib as O
             threads = O.lib().orc_max_threads()

@@ -25,7 +25,8 @@ def _worker(rank, world, port, q):
     mine["read_idx"] += np.uint32(lo)
     kept = len(np.unique(mine["read_idx"]))
     counters = sharding.all_reduce_counters(hi - lo, kept, backend_device="cpu")
-    q.put((rank, mine.tobytes(), counters))
+    hist = sharding.all_reduce_label_counts(sharding.label_histogram(mine, gs.as_dicts()), backend_device="cpu")
+    q.put((rank, mine.tobytes(), counters, hist.tolist()))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -45,8 +46,11 @@ def test_two_rank_sharding_matches_single_rank():
     assert merged == rows.tobytes()
     n = len(offsets) - 1
     kept = len(np.unique(rows["read_idx"]))
+    want_hist = sharding.label_histogram(rows, gs.as_dicts())
+    assert want_hist.sum() == len(rows) and (want_hist[1:] > 0).sum() > 10
     for g in got:
         assert g[2] == dict(total=n, kept=kept, dropped=n - kept)
+        assert g[3] == want_hist.tolist()
 
 
 def test_shard_ranges_cover_everything():
