@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <condition_variable>
 #include <cstdarg>
@@ -91,7 +92,7 @@ struct Engine {
     std::string err;
     uint64_t launches = 0, h2d_bytes = 0;   // kernels launched / bytes copied host -> device by this engine
     // device buffers
-    DBuf d_bases, d_offsets, d_nch, d_chunk_base, d_tile_first, d_windows, d_windows2, d_entries, d_sorted, d_cub, d_flags, d_hitkeys, d_hits, d_hist, d_rows, d_valid, d_rows_out, d_hits6;
+    DBuf d_bases, d_offsets, d_nch, d_chunk_base, d_tile_first, d_windows, d_entries, d_sorted, d_cub, d_flags, d_hitkeys, d_hits, d_hist, d_rows, d_valid, d_rows_out, d_hits6;
     DBuf d_counters;                     // [0] n_entries (u32) [2] n_selected (u32) [4..5] kept reads (u64)
     uint32_t entries_cap = 0;
     bool use_filter = true;              // bb_opts.flags bit 0 disables the pre-filter (exact scan everywhere)
@@ -126,7 +127,7 @@ struct Engine {
     }
     void destroy() {
         cudaSetDevice(device);
-        for (DBuf* b : {&d_bases, &d_offsets, &d_nch, &d_chunk_base, &d_tile_first, &d_windows, &d_windows2, &d_entries, &d_sorted, &d_cub, &d_flags, &d_hitkeys, &d_hits, &d_hist, &d_rows,
+        for (DBuf* b : {&d_bases, &d_offsets, &d_nch, &d_chunk_base, &d_tile_first, &d_windows, &d_entries, &d_sorted, &d_cub, &d_flags, &d_hitkeys, &d_hits, &d_hist, &d_rows,
                         &d_valid, &d_rows_out, &d_hits6, &d_counters})
             b->release();
         if (h_counters) cudaFreeHost(h_counters);

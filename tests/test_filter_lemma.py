@@ -1,8 +1,8 @@
-"""CPU check of the lemma behind the GPU pre-filter (DESIGN.md, K1f/K1p/K1v), using only the oracle's exact cost rows:
+"""CPU check of the lemma behind the GPU pre-filter (DESIGN.md, K1f / K1v), using only the oracle's exact cost rows:
 
 every end position whose full-flank cost is <= k must lie inside (a) a read-end window or (b) a window derived from a
 candidate run of the N-free run Q that also survives the second-run pre-check.  This is a restatement in numpy of what
-k_flank_filter / k_flank_precheck compute, so a flaw in the argument shows up here without a GPU."""
+k_flank_filter computes (scan phase and pre-check phase), so a flaw in the argument shows up here without a GPU."""
 import numpy as np
 import pytest
 
