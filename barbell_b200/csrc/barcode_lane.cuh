@@ -12,6 +12,9 @@
 //                highest set bit of stop at or below the current row (count-leading-zeros) is the row at which the path
 //                leaves the column, the rows skipped on the way are pattern-only steps; no cost value is materialised
 //                and nothing is recomputed -- three LDS for the column plus the match mask of its base.
+//  history       shared memory per alignment bounds the warps in flight, so only HALF of the columns are resident at a time
+//                (meet in the middle: the upper half is stored by the forward pass, the lower half by a replay of the forward
+//                recurrence when the traceback arrives there).
 //  Lodhi score   S_3(C, 1/2) is accumulated INSIDE the traceback loop in reversed op order.  The score is a sum of
 //                powers of two over triples of match ops, symmetric under reversal; with at most 48 ops every partial sum
 //                of either order is exactly representable in f64, so the reversed accumulation returns the same bits as
@@ -67,15 +70,6 @@ struct ColHist {                        // [column][word][lane] so that a warp's
             q[0] = a; q[32] = b;
         }
     }
-    // One 32-bit traceback record per column, written over the first word of a column the traceback has already consumed.
-    BB_HD void store_rec(int col, uint32_t v) const {
-        if constexpr (PACKED) w[static_cast<size_t>(col) * 96 + lane] = v;
-        else w[(static_cast<size_t>(col) * 64 + lane) * 2] = v;
-    }
-    BB_HD uint32_t load_rec(int col) const {
-        if constexpr (PACKED) return w[static_cast<size_t>(col) * 96 + lane];
-        else return w[(static_cast<size_t>(col) * 64 + lane) * 2];
-    }
     BB_HD void load(int col, uint64_t& a, uint64_t& b) const {
         if constexpr (PACKED) {
             const uint32_t* q = w + static_cast<size_t>(col) * 96 + lane;
@@ -113,69 +107,98 @@ BB_HD uint64_t region_mask(const uint64_t* eq, uint32_t v, uint64_t wild) {
 
 // eq      : this lane's match masks of the sets {A}, {C}, {G}, {T}, {ACGT}, top-aligned with wildcard rows below: eq[slot * 32]
 // txt     : the region's bases as region_byte() values (shared by the warp), rn of them
-// hist    : this lane's column history; a consumed column's first word is reused for the column's traceback record
+// hist    : this lane's column history, (rn + 1) / 2 columns: shared memory per alignment is what bounds the warps in flight,
+//           so only HALF of the columns are ever resident (see below)
+// rec     : this lane's per-column traceback records, rec[q * 32]
+//
+// Meet-in-the-middle history.  With H = rn / 2: the forward pass runs over all columns (it needs the whole bottom row for the
+// minima) but stores (diag, stop) for the columns > H only; the traceback walks those; when it arrives at column H the forward
+// recurrence is replayed over columns 1..H -- this time storing -- and the traceback continues.  Half the shared memory for
+// ~0.5 extra forward columns per column: the kernel is bound by warps in flight, not by instructions.
 template <bool PACKED>
 BB_HD void barcode_lane(const uint64_t* eq, const uint8_t* txt, int rn, int L, int pb0, int pb1,
-                        const ColHist<PACKED>& hist, LaneAlign& O) {
+                        const ColHist<PACKED>& hist, uint8_t* rec, LaneAlign& O) {
     const int sh = 64 - L;                                   // row i of the pattern is bit i + sh
     const uint64_t wild = sh ? ((1ull << sh) - 1ull) : 0ull;
-    // ---- forward pass: column history + the minima of the bottom row (S1) ----
-    uint64_t pv = (L >= 64 ? ~0ull : ((1ull << L) - 1ull)) << sh, mv = 0;
+    const uint64_t pv0 = (L >= 64 ? ~0ull : ((1ull << L) - 1ull)) << sh;
+    const int H = rn >> 1;
+    // ---- forward pass: the minima of the bottom row (S1) + column history of the upper half ----
     // S1 with every minimum reported (k = len) and "lowest cost, first seen" (searcher.rs:294-300) picks the right end of
     // the FIRST plateau that reaches the global minimum of the bottom row: `open` = still on that plateau.
+    uint64_t pv = pv0, mv = 0;
     int cur = L, cbest = L, jend = 0, open = 1;
     uint64_t e_next = rn > 0 ? region_mask(eq, txt[0], wild) : 0;
-    for (int p = 1; p <= rn; p++) {
-        const uint64_t e = e_next;
-        if (p < rn) e_next = region_mask(eq, txt[p], wild);
-        const uint64_t sum = (e & pv) + pv;
-        uint64_t ph = mv | ~(sum | pv | e);                  // horizontal deltas between columns p-1 and p
-        uint64_t mh = pv & ((sum ^ pv) | e);
-        const uint64_t diag = e | (ph & ~(pv | mv)) | (pv & ~(ph | mh));   // match, or D[i-1][p-1] + 1 == D[i][p]
-        hist.store(p - 1, diag, diag | ph);                                // ... else text-only if D[i][p-1] + 1 == D[i][p]
-        cur += static_cast<int>(ph >> 63) - static_cast<int>(mh >> 63);
-        ph <<= 1; mh <<= 1;
-        pv = mh | ~(e | mv | ph);
-        mv = ph & (e | mv);
-        open = cur < cbest ? 1 : (cur == cbest ? open : 0);
-        cbest = cur < cbest ? cur : cbest;
-        jend = open ? p : jend;
+#define BB_COLUMN(P, STORE, SLOT, MINIMA)                                                                  \
+    {                                                                                                      \
+        const uint64_t e = e_next;                                                                         \
+        if ((P) < rn) e_next = region_mask(eq, txt[(P)], wild);                                            \
+        const uint64_t sum = (e & pv) + pv;                                                                \
+        uint64_t ph = mv | ~(sum | pv | e);                  /* horizontal deltas between columns P-1 and P */ \
+        uint64_t mh = pv & ((sum ^ pv) | e);                                                               \
+        if (STORE) {                                                                                       \
+            const uint64_t diag = e | (ph & ~(pv | mv)) | (pv & ~(ph | mh));   /* match, or D[i-1][P-1] + 1 == D[i][P] */ \
+            hist.store((SLOT), diag, diag | ph);                               /* ... else text-only if D[i][P-1] + 1 == D[i][P] */ \
+        }                                                                                                  \
+        if (MINIMA) cur += static_cast<int>(ph >> 63) - static_cast<int>(mh >> 63);                        \
+        ph <<= 1; mh <<= 1;                                                                                \
+        pv = mh | ~(e | mv | ph);                                                                          \
+        mv = ph & (e | mv);                                                                                \
+        if (MINIMA) {                                                                                      \
+            open = cur < cbest ? 1 : (cur == cbest ? open : 0);                                            \
+            cbest = cur < cbest ? cur : cbest;                                                             \
+            jend = open ? (P) : jend;                                                                      \
+        }                                                                                                  \
     }
+    for (int p = 1; p <= H; p++) BB_COLUMN(p, false, 0, true)
+    for (int p = H + 1; p <= rn; p++) BB_COLUMN(p, true, p - 1 - H, true)
     // ---- traceback (S2) from (L, jend), one column per iteration; column 0 is walked with pattern-only steps ----
     int i = L, j = jend, nrec = 0, n_ops = 0;
     int cnt = 0, i_first = 0, i_last = 0, j_first = 0, j_last = 0, sub_cost = 0;
     double a1 = 0.0, a2 = 0.0, s = 0.0;                      // Lodhi accumulators over the REVERSED op sequence
-    uint64_t n_e = 0, n_diag = 0, n_stop = 0;                // the next column's vectors are fetched one iteration ahead
-    if (j > 0) { hist.load(j - 1, n_diag, n_stop); n_e = region_mask(eq, txt[j - 1], wild); }
-    while (i > 0 && j > 0) {
-        const uint64_t e = n_e, diag = n_diag, stop = n_stop;
-        const int jp = j - 1;
-        if (jp > 0) { hist.load(jp - 1, n_diag, n_stop); n_e = region_mask(eq, txt[jp - 1], wild); }
-        // move row i (bit i-1+sh) to bit 63: the leading zeros of stop are the pattern-only steps taken in this column
-        const int d = bb_clz64(stop << (L - i));
-        if (d >= i) break;                                   // no row at or below i lets the path out: pattern-only to row 0
-        const int il = i - d;                                // the path leaves the column at row il ...
-        const int t = il - 1 + sh;                           // ... whose bit this is
-        {
-            const int lo = il > pb0 ? il : pb0, hi = (i - 1) < (pb1 - 1) ? (i - 1) : (pb1 - 1);
-            if (hi >= lo) { if (cnt == 0) { i_last = hi; j_last = j; } i_first = lo; j_first = j; sub_cost += hi - lo + 1; cnt += hi - lo + 1; }
+    bool to_row0 = false;                                    // the rest of the path is pattern-only steps in column j
+    // walks the columns j > j_lo whose vectors sit in history slots (column - 1 - off)
+    auto trace = [&](int j_lo, int off) {
+        uint64_t n_e = 0, n_diag = 0, n_stop = 0;            // the next column's vectors are fetched one iteration ahead
+        if (j > j_lo) { hist.load(j - 1 - off, n_diag, n_stop); n_e = region_mask(eq, txt[j - 1], wild); }
+        while (i > 0 && j > j_lo) {
+            const uint64_t e = n_e, diag = n_diag, stop = n_stop;
+            const int jp = j - 1;
+            if (jp > j_lo) { hist.load(jp - 1 - off, n_diag, n_stop); n_e = region_mask(eq, txt[jp - 1], wild); }
+            // move row i (bit i-1+sh) to bit 63: the leading zeros of stop are the pattern-only steps taken in this column
+            const int d = bb_clz64(stop << (L - i));
+            if (d >= i) { to_row0 = true; break; }           // no row at or below i lets the path out: pattern-only to row 0
+            const int il = i - d;                            // the path leaves the column at row il ...
+            const int t = il - 1 + sh;                       // ... whose bit this is
+            {
+                const int lo = il > pb0 ? il : pb0, hi = (i - 1) < (pb1 - 1) ? (i - 1) : (pb1 - 1);
+                if (hi >= lo) { if (cnt == 0) { i_last = hi; j_last = j; } i_first = lo; j_first = j; sub_cost += hi - lo + 1; cnt += hi - lo + 1; }
+            }
+            const int is_diag = static_cast<int>((diag >> t) & 1ull), is_match = static_cast<int>((e >> t) & 1ull);
+            i = il - is_diag; j = jp;                        // pre-op position of the leaving op
+            if (i >= pb0 && i < pb1) {                       // map_pat_to_text_with_cost range (cigar_parse.rs:22-30)
+                if (cnt == 0) { i_last = i; j_last = j; }
+                i_first = i; j_first = j; sub_cost += 1 - is_match; cnt++;
+            }
+            rec[nrec * 32] = static_cast<uint8_t>((d << 1) | is_match);
+            nrec++;
+            n_ops += d + 1;
+            // reversed op order: d non-match ops, then the leaving op; g = 2^-(d+1)
+            const double g = bb_bits_to_double(static_cast<uint64_t>(1022 - d) << 52);
+            const double mm = is_match ? 1.0 : 0.0;
+            s = bb_fma(is_match ? g : 0.0, a2, s);
+            a2 = g * bb_fma(mm, a1, a2);
+            a1 = bb_fma(g, a1, 0.5 * mm);
         }
-        const int is_diag = static_cast<int>((diag >> t) & 1ull), is_match = static_cast<int>((e >> t) & 1ull);
-        i = il - is_diag; j = jp;                            // pre-op position of the leaving op
-        if (i >= pb0 && i < pb1) {                           // map_pat_to_text_with_cost range (cigar_parse.rs:22-30)
-            if (cnt == 0) { i_last = i; j_last = j; }
-            i_first = i; j_first = j; sub_cost += 1 - is_match; cnt++;
-        }
-        hist.store_rec(j, static_cast<uint32_t>((d << 1) | is_match));   // column j (0-based history slot) was consumed above
-        nrec++;
-        n_ops += d + 1;
-        // reversed op order: d non-match ops, then the leaving op; g = 2^-(d+1)
-        const double g = bb_bits_to_double(static_cast<uint64_t>(1022 - d) << 52);
-        const double mm = is_match ? 1.0 : 0.0;
-        s = bb_fma(is_match ? g : 0.0, a2, s);
-        a2 = g * bb_fma(mm, a1, a2);
-        a1 = bb_fma(g, a1, 0.5 * mm);
+    };
+    trace(H, H);
+    if (!to_row0 && i > 0 && j > 0) {                        // arrived at column j <= H: replay the forward recurrence, storing
+        pv = pv0; mv = 0;
+        e_next = region_mask(eq, txt[0], wild);
+        const int jj = j;
+        for (int p = 1; p <= jj; p++) BB_COLUMN(p, true, p - 1, false)
+        trace(0, 0);
     }
+#undef BB_COLUMN
     if (i > 0) {                                             // leading pattern-only steps at column j (first ops of the path)
         const int lo = 0 > pb0 ? 0 : pb0, hi = (i - 1) < (pb1 - 1) ? (i - 1) : (pb1 - 1);
         if (hi >= lo) { if (cnt == 0) { i_last = hi; j_last = j; } i_first = lo; j_first = j; sub_cost += hi - lo + 1; cnt += hi - lo + 1; }
@@ -185,7 +208,7 @@ BB_HD void barcode_lane(const uint64_t* eq, const uint8_t* txt, int rn, int L, i
         // same recurrence and op order as the reference's forward pass (leading non-match ops act on zeros)
         a1 = 0.0; a2 = 0.0; s = 0.0;
         for (int q = nrec - 1; q >= 0; q--) {
-            const int r = static_cast<int>(hist.load_rec(jend - 1 - q));
+            const int r = rec[q * 32];
             if (r & 1) { s = s + 0.5 * a2; a2 = 0.5 * (a2 + a1); a1 = 0.5 * (a1 + 1.0); }
             else { a2 = 0.5 * a2; a1 = 0.5 * a1; }
             const int d = r >> 1;

@@ -882,11 +882,13 @@ struct TopTwo {
     int ok = 0, pi = 0, ei = 0, pj = 0, ej = 0, cost = 0, ts = 0, te = 0;   // map_pat_to_text_with_cost of the top
 };
 
-// Shared-memory size of k_barcode for `cols` DP columns per lane: the lane's 5 match masks, the (diag, stop) bit-vectors
-// of every column (12 bytes when the pattern has <= 48 rows: rows live in bits [16, 64), so the two low halves share one
-// 32-bit word; 16 bytes otherwise; consumed columns are reused for the traceback records), and the region's bases.
+// Shared-memory size of k_barcode for regions of up to `cols` bases: the lane's 5 match masks, the (diag, stop) bit-vectors of
+// HALF of the columns (barcode_lane() keeps the upper half, then the lower half resident; 12 bytes per column and lane when
+// the pattern has <= 48 rows: rows live in bits [16, 64), so the two low halves share one 32-bit word; 16 bytes otherwise),
+// one traceback record per column, and the region's bases.
+__host__ __device__ inline size_t barcode_hist_bytes(int cols, bool packed) { return static_cast<size_t>((cols + 1) / 2) * 32 * (packed ? 12 : 16); }
 __host__ __device__ inline size_t barcode_warp_bytes(int cols, bool packed) {
-    return kEqSlots * 32 * sizeof(uint64_t) + static_cast<size_t>(cols) * 32 * (packed ? 12 : 16) + kCodesPad;
+    return kEqSlots * 32 * sizeof(uint64_t) + barcode_hist_bytes(cols, packed) + ((static_cast<size_t>(cols) * 32 + 15) & ~static_cast<size_t>(15)) + kCodesPad;
 }
 __host__ __device__ inline size_t barcode_smem_bytes(int cols, bool packed) { return kBarWarps * barcode_warp_bytes(cols, packed); }
 
@@ -903,7 +905,8 @@ __global__ void __launch_bounds__(kBarWarps * 32) k_barcode(const BarArgs A) {
     unsigned char* wbase = bar_smem + static_cast<size_t>(wib) * barcode_warp_bytes(A.hist_cols, PACKED);
     uint64_t* eqs_s = reinterpret_cast<uint64_t*>(wbase);                    // [5 base sets][32 lanes]
     const ColHist<PACKED> hist{reinterpret_cast<uint32_t*>(eqs_s + kEqSlots * 32), lane};
-    uint8_t* txt = wbase + kEqSlots * 32 * sizeof(uint64_t) + ncol * 32 * (PACKED ? 12 : 16);   // region bases (region_byte)
+    uint8_t* rec = wbase + kEqSlots * 32 * sizeof(uint64_t) + barcode_hist_bytes(A.hist_cols, PACKED);   // [column][lane]
+    uint8_t* txt = rec + ((ncol * 32 + 15) & ~static_cast<size_t>(15));                                    // region bases (region_byte)
     const uint32_t n_warps = gridDim.x * kBarWarps;
     for (uint32_t h = blockIdx.x * kBarWarps + wib; h < A.n_hits; h += n_warps) {
         const Hit H = A.hits[h];
@@ -934,7 +937,7 @@ __global__ void __launch_bounds__(kBarWarps * 32) k_barcode(const BarArgs A) {
             __syncwarp();
             if (b < nb) {
                 LaneAlign R;
-                barcode_lane<PACKED>(eqs_s + lane, txt, rn, L, G.pbar0, G.pbar1, hist, R);
+                barcode_lane<PACKED>(eqs_s + lane, txt, rn, L, G.pbar0, G.pbar1, hist, rec + lane, R);
                 has1 = R.cbest <= k1;
                 const double sn = G.perfect > 0.0 ? R.s / G.perfect : 0.0;
 #pragma unroll

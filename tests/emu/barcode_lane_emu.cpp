@@ -36,16 +36,20 @@ int emu_barcode_lane(const uint8_t* pattern, int L, const uint8_t* region, int r
     }
     std::vector<uint8_t> txt(rn + 16, 0);
     for (int q = 0; q < rn; q++) txt[q] = bb::region_byte(g_code[region[q]]);
-    std::vector<uint32_t> hist(static_cast<size_t>(hist_cols) * 32 * 4 + 64, 0xabababab);
-    bb::LaneAlign R;
+    const int half = (hist_cols + 1) / 2;                     // the kernel keeps half of the columns resident
     const bool packed = L <= 48;
+    const size_t hist_words = static_cast<size_t>(half) * 32 * (packed ? 3 : 4);   // exactly what the kernel reserves per warp
+    std::vector<uint32_t> hist(hist_words + 256, 0xabababab);                        // + a guard zone that must stay untouched
+    std::vector<uint8_t> rec(static_cast<size_t>(hist_cols) * 32 + 64, 0xcd);
+    bb::LaneAlign R;
     if (packed) {
         bb::ColHist<true> H{hist.data(), lane};
-        bb::barcode_lane<true>(eqs.data() + lane, txt.data(), rn, L, pb0, pb1, H, R);
+        bb::barcode_lane<true>(eqs.data() + lane, txt.data(), rn, L, pb0, pb1, H, rec.data() + lane, R);
     } else {
         bb::ColHist<false> H{hist.data(), lane};
-        bb::barcode_lane<false>(eqs.data() + lane, txt.data(), rn, L, pb0, pb1, H, R);
+        bb::barcode_lane<false>(eqs.data() + lane, txt.data(), rn, L, pb0, pb1, H, rec.data() + lane, R);
     }
+    for (size_t q = hist_words; q < hist.size(); q++) if (hist[q] != 0xabababab) return -2;   // wrote past the reserved columns
     out[0] = R.cbest; out[1] = R.jend; out[2] = R.ts; out[3] = R.cnt; out[4] = R.i_first; out[5] = R.i_last;
     out[6] = R.j_first; out[7] = R.j_last; out[8] = R.sub_cost; out[9] = R.n_ops; out[10] = packed; out[11] = 0;
     *score = R.s;
