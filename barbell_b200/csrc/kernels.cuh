@@ -918,7 +918,13 @@ __global__ void __launch_bounds__(kBarWarps * 32) k_barcode(const BarArgs A) {
         const int L = G.bar_len, nb = G.n_barcodes, k1 = G.k_bar;
         const int sh = 64 - L;                                  // patterns are top-aligned like the flank scan
         __syncwarp();
-        for (int q = lane; q < rn; q += 32) txt[q] = region_byte(__ldg(A.code + A.bases[rs0 + H.rs + q]));
+        bool plain_l = true;                                     // every base of the region is A, C, G, T or N (the usual case)
+        for (int q = lane; q < rn; q += 32) {
+            const uint8_t v = region_byte(__ldg(A.code + A.bases[rs0 + H.rs + q]));
+            txt[q] = v;
+            plain_l = plain_l && (v >> 4) < kEqOther;
+        }
+        const bool plain = __all_sync(0xffffffffu, plain_l);
         const uint64_t* eqs = G.bar_eq + static_cast<size_t>(H.strand) * nb * 16;
         const uint64_t wild = sh ? ((1ull << sh) - 1ull) : 0ull;
 
@@ -937,7 +943,8 @@ __global__ void __launch_bounds__(kBarWarps * 32) k_barcode(const BarArgs A) {
             __syncwarp();
             if (b < nb) {
                 LaneAlign R;
-                barcode_lane<PACKED>(eqs_s + lane, txt, rn, L, G.pbar0, G.pbar1, hist, rec + lane, R);
+                if (plain) barcode_lane<PACKED, true>(eqs_s + lane, txt, rn, L, G.pbar0, G.pbar1, hist, rec + lane, R);
+                else barcode_lane<PACKED, false>(eqs_s + lane, txt, rn, L, G.pbar0, G.pbar1, hist, rec + lane, R);
                 has1 = R.cbest <= k1;
                 const double sn = G.perfect > 0.0 ? R.s / G.perfect : 0.0;
 #pragma unroll

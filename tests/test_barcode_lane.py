@@ -34,7 +34,7 @@ def run_lane(lib, pattern, region, pb0, pb1, lane=0, hist_cols=None):
     sc = C.c_double()
     rc = lib.emu_barcode_lane(pattern, len(pattern), region, len(region), pb0, pb1, lane, hist_cols or max(1, len(region)), out, C.byref(sc))
     assert rc == 0
-    keys = ["cbest", "jend", "ts", "cnt", "i_first", "i_last", "j_first", "j_last", "sub_cost", "n_ops", "packed"]
+    keys = ["cbest", "jend", "ts", "cnt", "i_first", "i_last", "j_first", "j_last", "sub_cost", "n_ops", "packed", "variant"]
     d = dict(zip(keys, list(out)))
     d["s"] = sc.value
     return d
@@ -92,7 +92,7 @@ def test_native_geometry_random(emu):
     """SQK-NBD114-96 geometry: 10 + 24 + 8 pattern rows, region = 10 + barcode + 9 bases around the mask."""
     rng = random.Random(1234)
     left, right = b"AAGGTTAA"[-10:].rjust(10, b"T"), b"CAGCACCT"
-    n_long = 0
+    n_long, variants = 0, set()
     for it in range(3000):
         bar = rand_seq(rng, 24)
         pattern = left + bar + right
@@ -121,7 +121,9 @@ def test_native_geometry_random(emu):
             continue
         got = check(emu, pattern, region, 10, 33, lane=it % 32)
         n_long += got["n_ops"] > 48
-    assert n_long > 50          # the replayed forward recurrence was exercised
+        variants.add(got["variant"])
+    assert n_long > 50
+    assert variants == {1, 2, 5, 6}   # FAST / general (other base sets), each with and without the replayed forward recurrence
 
 
 @pytest.mark.parametrize("L", [8, 24, 41, 42, 43, 44, 47, 48, 49, 56, 63, 64])
@@ -145,3 +147,26 @@ def test_degenerate_regions(emu):
     for pattern, region in [(b"ACGTACGTAC", b"A"), (b"ACGTACGTAC", b"T"), (b"AAAAAAAAAA", b"CCCCCCCCCCCC"), (b"ACGT" * 10, b"ACGT" * 10),
                             (b"N" * 42, b"ACGT" * 11), (b"ACGT" * 10 + b"AC", b"N" * 50), (b"A" * 42, b"A" * 64)]:
         check(emu, pattern, region, 3, len(pattern) - 2)
+
+
+def test_reversed_lodhi_is_exact_whenever_the_criterion_says_so(emu):
+    """lodhi_exact(s, n_ops) must imply bit-equality of the reversed accumulation with the reference's forward recurrence --
+    on adversarial op strings too (long match runs = large scores, lengths around the 53-bit budget)."""
+    emu.emu_lodhi_reversed.restype = C.c_int
+    emu.emu_lodhi_reversed.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_double)]
+    rng = random.Random(99)
+    n_ok = n_long_ok = n_rejected = 0
+    for it in range(60000):
+        n = rng.choice([3, 10, 30, 40, 44, 46, 47, 48, 49, 50, 51, 52, 53, 54, 56, 60, 64, 70])
+        p = rng.choice([0.3, 0.6, 0.8, 0.9, 0.97, 1.0])
+        ops = bytes(1 if rng.random() < p else 0 for _ in range(n))
+        sc = C.c_double()
+        ok = emu.emu_lodhi_reversed(ops, n, C.byref(sc))
+        want = O.lib().orc_lodhi(bytes(0 if o else 1 for o in ops), n)       # oracle op codes: 0 = match
+        if ok:
+            assert np.float64(sc.value).tobytes() == np.float64(want).tobytes(), (ops, sc.value, want)
+            n_ok += 1
+            n_long_ok += n > 48
+        else:
+            n_rejected += 1
+    assert n_ok > 20000 and n_long_ok > 1000 and n_rejected > 5000
