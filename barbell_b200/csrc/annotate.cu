@@ -308,7 +308,7 @@ struct Engine {
             B.hist_cols = gt->max_region;
             const bool packed = gt->max_bar_len <= 48;
             const size_t smem = barcode_smem_bytes(B.hist_cols, packed);
-            const unsigned blocks = std::min<unsigned>((n_hits + kBarWarps - 1) / kBarWarps, 148 * 32);
+            const unsigned blocks = std::min<unsigned>((n_hits + kBarWarps - 1) / kBarWarps, 148 * 32 / kBarWarps);
             if (packed) {
                 BB_CUDA(cudaFuncSetAttribute(k_barcode<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
                 k_barcode<true><<<blocks, kBarWarps * 32, smem, st>>>(B);
