@@ -406,6 +406,21 @@ struct Ingest {
     void close() { if (source) { source->join(); source.reset(); } for (auto& b : slots) b.release(); slots.clear(); }
 };
 
+// --verbose: `<dir>/<step>.<unix ms>.log` with the step's final counters, like ProgressTracker::finish (progress.rs:102-144, 188-201)
+void write_progress_log(const std::string& dir, const char* step, const std::vector<std::pair<const char*, unsigned long long>>& counts) {
+    const long long ms = std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::system_clock::now().time_since_epoch()).count();
+    const std::string path = (dir.empty() ? std::string(".") : dir) + "/" + step + "." + std::to_string(ms) + ".log";
+    FILE* f = std::fopen(path.c_str(), "w");
+    if (!f) { std::printf("Failed to create log file '%s'\n", path.c_str()); return; }
+    std::fprintf(f, "step\tmetric\tcount\n");
+    for (const auto& c : counts) std::fprintf(f, "%s\t%s\t%llu\n", step, c.first, c.second);
+    std::fclose(f);
+}
+std::string parent_dir(const std::string& path) {
+    const size_t p = path.find_last_of('/');
+    return p == std::string::npos ? std::string(".") : (p == 0 ? std::string("/") : path.substr(0, p));
+}
+
 const char* kTypeNames[] = {"Ftag", "Rtag", "Fflank", "Rflank"};
 
 int run_annotate(const Args& a, const std::string& out_path) {
@@ -513,6 +528,8 @@ int run_annotate(const Args& a, const std::string& out_path) {
     source->join();
     std::fclose(out);
     const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (rc == BB_OK && a.verbose)
+        write_progress_log(parent_dir(out_path), "annotate", {{"Total:", total_reads}, {"Kept:", kept}, {"Dropped:", total_reads - kept}});
     if (rc == BB_OK) {
         std::printf("Total: %llu  Kept: %llu  Dropped: %llu  (rows: %llu, %.2f s, %.0f reads/s)\n", static_cast<unsigned long long>(total_reads),
                     static_cast<unsigned long long>(kept), static_cast<unsigned long long>(total_reads - kept),
@@ -581,6 +598,7 @@ int run_filter_cmd(const Args& a) {
         const int rc = bb_filter(a.input[0].c_str(), a.output.c_str(), a.dropped.empty() ? nullptr : a.dropped.c_str(), pp.data(),
                                  static_cast<int32_t>(pp.size()), counts, err, sizeof err);
         if (rc == BB_OK) {
+            if (a.verbose) write_progress_log(parent_dir(a.output), "filter", {{"Total:", counts[0]}, {"Kept:", counts[1]}, {"Dropped:", counts[2]}});
             std::printf("Total: %llu  Kept: %llu  Dropped: %llu reads\n", static_cast<unsigned long long>(counts[0]),
                         static_cast<unsigned long long>(counts[1]), static_cast<unsigned long long>(counts[2]));
             std::printf("Filtering successful!\n");
@@ -608,13 +626,15 @@ bb_trim_opts trim_opts_from(const Args& a, bool kit_defaults) {
     return o;
 }
 
-int run_trim(const std::string& filtered, const std::vector<std::string>& reads, const std::string& out_dir, const bb_trim_opts& o, std::string& msg) {
+int run_trim(const std::string& filtered, const std::vector<std::string>& reads, const std::string& out_dir, const bb_trim_opts& o, std::string& msg,
+             bool verbose = false) {
     std::vector<const char*> rp;
     for (const auto& r : reads) rp.push_back(r.c_str());
     uint64_t counts[4] = {0, 0, 0, 0};
     char err[1024] = {0};
     const int rc = bb_trim(filtered.c_str(), rp.data(), static_cast<int32_t>(rp.size()), out_dir.c_str(), &o, counts, err, sizeof err);
     if (rc != BB_OK) { msg = err; return rc; }
+    if (verbose) write_progress_log(out_dir, "trim", {{"Total:", counts[0]}, {"Kept:", counts[1]}, {"Kept split:", counts[2]}, {"Failed:", counts[3]}});
     std::printf("Total: %llu  Trimmed: %llu  Trimmed split: %llu  Failed trims: %llu reads\n", static_cast<unsigned long long>(counts[0]),
                 static_cast<unsigned long long>(counts[1]), static_cast<unsigned long long>(counts[2]), static_cast<unsigned long long>(counts[3]));
     return BB_OK;
@@ -646,11 +666,12 @@ int run_kit(const Args& a) {
     uint64_t counts[3] = {0, 0, 0};
     rc = bb_filter(anno.c_str(), filtered.c_str(), nullptr, pats, n_pats, counts, err, sizeof err);
     if (rc != BB_OK) { std::printf("Demultiplexing failed: %s\n", err); return 0; }
+    if (a.verbose) write_progress_log(a.output, "filter", {{"Total:", counts[0]}, {"Kept:", counts[1]}, {"Dropped:", counts[2]}});
     std::printf("Total: %llu  Kept: %llu  Dropped: %llu reads\n", static_cast<unsigned long long>(counts[0]),
                 static_cast<unsigned long long>(counts[1]), static_cast<unsigned long long>(counts[2]));
     std::printf("\nTrimming reads...\n");
     std::string msg;
-    rc = run_trim(filtered, a.input, a.output, trim_opts_from(a, true), msg);
+    rc = run_trim(filtered, a.input, a.output, trim_opts_from(a, true), msg, a.verbose);
     if (rc != BB_OK) { std::printf("Demultiplexing failed: %s\n", msg.c_str()); return 0; }
     std::printf("\nDone!\n");
     return 0;
@@ -673,7 +694,7 @@ int main(int argc, char** argv) {
         if (!a.only_side.empty() && a.only_side != "left" && a.only_side != "right") usage("--only-side takes left or right");
         if (!a.only_side.empty() && a.sort_labels) usage("--only-side cannot be used with --sort-labels");
         std::string msg;
-        if (run_trim(a.input[0], a.reads, a.output, trim_opts_from(a, false), msg) == BB_OK) std::printf("Trimming complete!\n");
+        if (run_trim(a.input[0], a.reads, a.output, trim_opts_from(a, false), msg, a.verbose) == BB_OK) std::printf("Trimming complete!\n");
         else std::printf("Trimming failed: %s\n", msg.c_str());
         return 0;
     }

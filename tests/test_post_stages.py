@@ -323,9 +323,13 @@ def test_cli_filter_inspect_trim(tmp_path):
     rows = rand_rows(rng, 50)
     (tmp_path / "a.tsv").write_text(P.to_tsv(rows))
     (tmp_path / "pats.txt").write_text("Ftag[fw, *, @left(0..250), >>]\n\n  Ftag[<<, rc, *, @right(0..250)]  \n")
-    r = subprocess.run([exe, "filter", "-i", str(tmp_path / "a.tsv"), "-o", str(tmp_path / "f.tsv"), "-f", str(tmp_path / "pats.txt"), "--dropped", str(tmp_path / "d.tsv")],
-                       capture_output=True, text=True)
+    r = subprocess.run([exe, "filter", "-i", str(tmp_path / "a.tsv"), "-o", str(tmp_path / "f.tsv"), "-f", str(tmp_path / "pats.txt"), "--dropped", str(tmp_path / "d.tsv"),
+                        "--verbose"], capture_output=True, text=True)
     assert r.returncode == 0 and "Filtering successful!" in r.stdout, r.stdout + r.stderr
+    logs = [f for f in tmp_path.iterdir() if f.name.startswith("filter.") and f.name.endswith(".log")]     # progress.rs:102-144
+    assert len(logs) == 1
+    lines = logs[0].read_text().split("\n")
+    assert lines[0] == "step\tmetric\tcount" and lines[1].startswith("filter\tTotal:\t") and lines[3].startswith("filter\tDropped:\t")
     import copy
     kept, dropped = P.filter_rows(copy.deepcopy(rows), [P.parse_pattern("Ftag[fw, *, @left(0..250), >>]"), P.parse_pattern("Ftag[<<, rc, *, @right(0..250)]")])
     assert (tmp_path / "f.tsv").read_text() == P.to_tsv(kept) and (tmp_path / "d.tsv").read_text() == P.to_tsv(dropped)
