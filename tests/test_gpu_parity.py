@@ -108,6 +108,40 @@ def test_tags_straddling_scan_tiles_and_chunks():
         assert (rows["match_type"] < 2).sum() > 100
 
 
+def test_barcode_regions_with_ambiguity_codes_and_many_insertions():
+    """The barcode stage's general variant (base sets other than A/C/G/T/N resolved by OR-ing masks) and the replayed forward
+    Lodhi recurrence (paths too long for the exact reversed accumulation): tags whose barcode part carries IUPAC codes,
+    lower case, non-IUPAC bytes and runs of inserted bases."""
+    for kit, kw in (("SQK-NBD114-96", {}), ("SQK-RBK114-96", dict(max_flank_errors=5))):
+        gs = bb.GroupSet.from_kit(kit, **kw)
+        g = gs.as_dicts()[0]
+        tags = synth.full_tags(g)
+        b0, b1 = g["bar_region"]
+        rng = np.random.default_rng(77)
+        junk = np.frombuffer(b"RYKMSWBDHVNacgtn-*x", np.uint8)
+        reads = []
+        for r in range(600):
+            tag = tags[r % len(tags)].copy()
+            bar = tag[b0:b1 + 1].copy()
+            kind = r % 4
+            if kind in (0, 2):                                   # ambiguity codes / garbage inside the barcode
+                idx = rng.integers(0, len(bar), rng.integers(1, 5))
+                bar[idx] = rng.choice(junk, len(idx))
+            if kind in (1, 2):                                   # 6..14 inserted bases inside the barcode: long alignment paths
+                ins = rng.choice(np.frombuffer(b"ACGT", np.uint8), rng.integers(6, 15))
+                cut = rng.integers(3, len(bar) - 3)
+                bar = np.concatenate([bar[:cut], ins, bar[cut:]])
+            tag = np.concatenate([tag[:b0], bar, tag[b1 + 1:]])
+            if r & 1:
+                tag = synth.revcomp(tag)
+            body = rng.choice(np.frombuffer(b"ACGT", np.uint8), rng.integers(100, 400))
+            reads.append(np.concatenate([tag, body]) if (r >> 1) & 1 else np.concatenate([body, tag, body[:50]]))
+        bases = np.concatenate(reads)
+        offsets = np.concatenate([[0], np.cumsum([len(x) for x in reads])]).astype(np.uint64)
+        rows = _check(gs, bases, offsets)
+        assert len(rows) >= 250
+
+
 def test_adversarial_text():
     """poly-N (matches everything), homopolymers, lower case, non-IUPAC bytes, tags cut by the read ends."""
     gs = bb.GroupSet.from_kit("SQK-NBD114-96")
