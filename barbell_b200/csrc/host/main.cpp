@@ -379,12 +379,122 @@ class ParallelSource : public BatchSource {
     bool failed_ = false, aborted_ = false;
 };
 
+// Several input files, some of them gzip (the usual shape of a nanopore run: thousands of small .fastq.gz): every worker inflates
+// and parses ONE whole file into heap buffers; an assembler thread copies the parsed files, in input order, into the
+// page-locked batches.  A window bounds the files parsed ahead of the assembler.
+class MultiFileSource : public BatchSource {
+  public:
+    static bool usable(const std::vector<std::string>& paths) {
+        if (paths.size() < 2) return false;
+        for (const auto& p : paths) {
+            struct stat st;
+            if (stat(p.c_str(), &st) != 0 || !S_ISREG(st.st_mode) || st.st_size > (1ll << 30)) return false;   // a parsed file lives on the heap
+        }
+        return true;
+    }
+    MultiFileSource(const std::vector<std::string>& paths, std::vector<Batch>& slots, int n_threads)
+        : paths_(paths), slots_(slots), files_(paths.size()), window_(static_cast<size_t>(std::max(2, 2 * n_threads))) {
+        for (size_t s = 0; s < slots.size(); s++) free_.push(static_cast<int>(s));
+        for (int t = 0; t < std::max(1, n_threads); t++) workers_.emplace_back([this] { work(); });
+        assembler_ = std::thread([this] { assemble(); });
+    }
+    ~MultiFileSource() override { join(); }
+    int next_filled() override { return filled_.pop(); }
+    void release(int slot) override { free_.push(slot); }
+    void abort() override {
+        { std::lock_guard<std::mutex> lk(mu_); aborted_ = true; }
+        cv_.notify_all();
+        for (size_t s = 0; s < slots_.size() + 2; s++) free_.push(-1);
+    }
+    void join() override {
+        for (auto& w : workers_) if (w.joinable()) w.join();
+        workers_.clear();
+        if (assembler_.joinable()) assembler_.join();
+    }
+    const std::string& error() const override { return err_; }
+
+  private:
+    struct Parsed {
+        std::vector<uint8_t> bases; std::vector<uint64_t> ends; std::vector<char> ids; std::vector<uint32_t> id_ends;
+        std::string err; bool done = false;
+    };
+    void work() {
+        for (;;) {
+            const size_t f = claim_.fetch_add(1);
+            if (f >= files_.size()) return;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return aborted_ || f < assembled_ + window_; });
+                if (aborted_) return;
+            }
+            Parsed P;
+            FastqReader reader(std::vector<std::string>{paths_[f]});
+            FastqReader::View v;
+            while (reader.next(v, P.err)) {
+                P.bases.insert(P.bases.end(), v.seq, v.seq + v.seq_len);
+                P.ends.push_back(P.bases.size());
+                P.ids.insert(P.ids.end(), v.id, v.id + v.id_len);
+                P.id_ends.push_back(static_cast<uint32_t>(P.ids.size()));
+            }
+            P.done = true;
+            { std::lock_guard<std::mutex> lk(mu_); files_[f] = std::move(P); }
+            cv_.notify_all();
+        }
+    }
+    void assemble() {
+        int cur = free_.pop();
+        if (cur < 0) return;
+        slots_[cur].clear();
+        for (size_t f = 0; f < files_.size(); f++) {
+            Parsed P;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return aborted_ || files_[f].done; });
+                if (aborted_) return;
+                P = std::move(files_[f]);
+            }
+            if (!P.err.empty()) { err_ = P.err; filled_.push(-2); return; }
+            uint64_t b0 = 0; uint32_t i0 = 0;
+            for (size_t r = 0; r < P.ends.size(); r++) {
+                const size_t len = P.ends[r] - b0;
+                Batch* B = &slots_[cur];
+                if (len > B->cap_bytes) { err_ = "read longer than the batch buffer (raise --batch-mb)"; filled_.push(-2); return; }
+                if (B->bytes + len > B->cap_bytes || B->n_reads + 1 > B->cap_reads) {
+                    filled_.push(cur);
+                    cur = free_.pop();
+                    if (cur < 0) return;
+                    B = &slots_[cur];
+                    B->clear();
+                }
+                B->append(P.ids.data() + i0, P.id_ends[r] - i0, reinterpret_cast<const char*>(P.bases.data()) + b0, len);
+                b0 = P.ends[r]; i0 = P.id_ends[r];
+            }
+            { std::lock_guard<std::mutex> lk(mu_); assembled_ = f + 1; }
+            cv_.notify_all();
+        }
+        if (slots_[cur].n_reads > 0) filled_.push(cur);
+        filled_.push(-1);
+    }
+    std::vector<std::string> paths_;
+    std::vector<Batch>& slots_;
+    std::vector<Parsed> files_;
+    size_t window_, assembled_ = 0;
+    std::atomic<size_t> claim_{0};
+    std::mutex mu_;
+    std::condition_variable cv_;
+    Channel<int> free_, filled_;
+    std::vector<std::thread> workers_;
+    std::thread assembler_;
+    std::string err_;
+    bool aborted_ = false;
+};
+
 // Slots + source for a run: plain files are cut into chunks of `chunk` FASTQ bytes (<= chunk/2 bases each) and parsed by up to
 // 8 of the -t threads; anything else (gzip, pipes, -t 1, --single-reader) goes through one reader thread.
 struct Ingest {
     std::vector<Batch> slots;
     std::unique_ptr<BatchSource> source;
-    bool parallel = false;
+    bool parallel = false, multifile = false;
     bool open(const Args& a, int in_flight, bool pinned, std::string& err) {
         const size_t cap_bytes = a.batch_mb << 20, cap_reads = 1u << 22;
         const int parse_threads = std::min(8, std::max(1, a.threads));
@@ -399,7 +509,9 @@ struct Ingest {
         const size_t slot_bytes = parallel ? std::min(cap_bytes, chunk / 2) + (16u << 20) : cap_bytes;
         slots.resize(n_slots);
         for (auto& b : slots) if (!b.alloc(slot_bytes, cap_reads, pinned)) { err = pinned ? "pinned host allocation failed" : "host allocation failed"; return false; }
+        multifile = !parallel && parse_threads > 1 && !a.single_reader && MultiFileSource::usable(a.input);
         if (parallel) source.reset(new ParallelSource(a.input, slots, chunk, parse_threads));
+        else if (multifile) source.reset(new MultiFileSource(a.input, slots, parse_threads));
         else source.reset(new SequentialSource(a.input, slots));
         return true;
     }
@@ -563,10 +675,10 @@ int run_fastq_stats(const Args& a) {
         n += B.n_reads; bases += B.bytes; batches++;
         ingest.source->release(cur);
     }
-    const bool par = ingest.parallel;
+    const char* kind = ingest.parallel ? "parallel" : ingest.multifile ? "multifile" : "sequential";
     ingest.close();
     if (rc == 0) std::printf("records=%llu bases=%llu fnv=%016llx batches=%llu reader=%s\n", static_cast<unsigned long long>(n), static_cast<unsigned long long>(bases),
-                             static_cast<unsigned long long>(h), static_cast<unsigned long long>(batches), par ? "parallel" : "sequential");
+                             static_cast<unsigned long long>(h), static_cast<unsigned long long>(batches), kind);
     return rc;
 }
 

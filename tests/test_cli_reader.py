@@ -79,12 +79,25 @@ def test_parallel_chunked_reader_equals_sequential(tmp_path):
     assert stats([pa, pb, pc], "--single-reader", want_reader="sequential") == want
     for chunk_kb, threads in [(1, 8), (3, 4), (64, 8), (300, 3), (100000, 8)]:
         assert stats([pa, pb, pc], "--chunk-kb", str(chunk_kb), "-t", str(threads), want_reader="parallel") == want, (chunk_kb, threads)
-    # -t 1 and gzip inputs fall back to the single reader thread
+    # -t 1 falls back to the single reader thread; several files with gzip among them are inflated and parsed one file per worker
     assert stats([pa, pb, pc], "-t", "1", want_reader="sequential") == want
-    pz = tmp_path / "z.fastq.gz"
-    with gzip.open(pz, "wt") as f:
-        f.write(text(recs[:5]))
-    stats([pa, pz], want_reader="sequential")
+    zs = []
+    for k in range(7):
+        pz = tmp_path / f"z{k}.fastq.gz"
+        with gzip.open(pz, "wt") as f:
+            f.write(text(recs[20 * k:20 * (k + 1)]))
+        zs.append(pz)
+    pe = tmp_path / "zz_empty.fastq"; pe.write_text("")
+    want_z = (140, sum(len(s) for _, s in recs[:140]), fnv(recs[:140]))
+    assert stats(zs[:3] + [pe] + zs[3:], "-t", "4", want_reader="multifile") == want_z
+    assert stats(zs[:3] + [pe] + zs[3:], "-t", "3", "--batch-mb", "1", want_reader="multifile") == want_z      # many small batches
+    assert stats(zs[:3] + [pe] + zs[3:], "--single-reader", want_reader="sequential") == want_z
+    stats([zs[0]], want_reader="sequential")                                                                     # one gzip file: one zlib stream
+    badz = tmp_path / "bad.fastq.gz"
+    with gzip.open(badz, "wt") as f:
+        f.write("@r1\nACGT\n+\nII\n")
+    r = subprocess.run([EXE, "fastq-stats", "-i", str(zs[0]), str(badz), str(zs[1]), "-t", "4"], capture_output=True, text=True, timeout=60)
+    assert r.returncode != 0 and "quality length" in r.stdout, r.stdout
     # errors surface from the parser threads too
     bad = tmp_path / "bad.fastq"; bad.write_text(text(recs[:20]) + "@r1\nACGT\n+\nII\n" + text(recs[20:40]))
     r = subprocess.run([EXE, "fastq-stats", "-i", str(bad), "--chunk-kb", "2", "-t", "4"], capture_output=True, text=True, timeout=60)
