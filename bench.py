@@ -158,6 +158,8 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # the ranks share the host cores: split them for the host-side packing of the end-to-end leg
+        os.environ.setdefault("BB_PACK_THREADS", str(max(1, (os.cpu_count() or 1) // int(os.environ.get("LOCAL_WORLD_SIZE", world)))))
 
     gs = bb.GroupSet.from_kit(KIT)
     G = gs.as_dicts()
