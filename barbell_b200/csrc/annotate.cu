@@ -380,9 +380,7 @@ struct Engine {
             BB_CUDA(cudaEventRecord(ev_copy[0], stream));
             if (total > split) BB_CUDA(cudaMemcpyAsync(d_bases.as<uint8_t>() + split, bases + split, total - split, cudaMemcpyHostToDevice, stream));
             BB_CUDA(cudaEventRecord(ev_copy[1], stream));
-            const auto t0 = std::chrono::steady_clock::now();
-            if (split) pack_nibbles(bases, split, h_pack, kAlpha.code, pack_threads);
-            const double pack_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            const double pack_s = split ? pack_nibbles(bases, split, h_pack, kAlpha.code, pack_threads) : 0.0;   // the pool's own time
             if (split) {
                 BB_CUDA(cudaMemcpyAsync(d_packed.p, h_pack, split / 2, cudaMemcpyHostToDevice, stream));
                 k_unpack_nibbles<<<static_cast<unsigned>((split / 16 + 255) / 256), 256, 0, stream>>>(d_packed.as<uint8_t>(), d_bases.as<uint8_t>(), split);
@@ -392,8 +390,10 @@ struct Engine {
             BB_CUDA(cudaMemcpyAsync(d_offsets.p, offsets, static_cast<size_t>(n_reads + 1) * 8, cudaMemcpyHostToDevice, stream));
             BB_CUDA(cudaEventSynchronize(ev_copy[1]));            // run() synchronises the stream a few kernels later anyway
             float copy_ms = 0.f;
+            // P = rate of the (shared) packing pool while it works; B = the link's rate = the fastest tail copy seen lately (a copy
+            // that queued behind another batch's copy looks slower than the link is)
             if (total - split >= (1u << 20) && cudaEventElapsedTime(&copy_ms, ev_copy[0], ev_copy[1]) == cudaSuccess && copy_ms > 0.f)
-                link_rate = 0.5 * link_rate + 0.5 * (static_cast<double>(total - split) / (copy_ms * 1e-3));
+                link_rate = std::max(0.98 * link_rate, static_cast<double>(total - split) / (copy_ms * 1e-3));
             if (split >= (1u << 20) && pack_s > 0.0) pack_rate = 0.5 * pack_rate + 0.5 * (static_cast<double>(split) / pack_s);
             h2d_bytes += (total - split) + split / 2 + static_cast<uint64_t>(n_reads + 1) * 8;
             const double x = pack_rate / (link_rate + 0.5 * pack_rate);

@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <functional>
 #include <mutex>
@@ -67,9 +68,10 @@ class Pool {
         cv_.notify_all();
         for (auto& w : workers_) w.join();
     }
-    // run fn(chunk) for chunk in [0, n_chunks) on the pool + the calling thread
-    void run(int n_chunks, const std::function<void(int)>& fn) {
+    // run fn(chunk) for chunk in [0, n_chunks) on the pool + the calling thread; returns the seconds the region itself took
+    double run(int n_chunks, const std::function<void(int)>& fn) {
         std::unique_lock<std::mutex> call(call_mu_);              // one parallel region at a time
+        const auto t0 = std::chrono::steady_clock::now();
         {
             std::lock_guard<std::mutex> lk(mu_);
             fn_ = &fn; next_.store(0); total_ = n_chunks; pending_ = n_chunks; gen_++;
@@ -79,6 +81,7 @@ class Pool {
         std::unique_lock<std::mutex> lk(mu_);
         done_cv_.wait(lk, [&] { return pending_ == 0; });
         fn_ = nullptr;
+        return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     }
     int size() const { return static_cast<int>(workers_.size()) + 1; }
 
@@ -126,15 +129,19 @@ int pack_default_threads() {
     return static_cast<int>(std::min(64u, std::max(1u, hc)));
 }
 
-void pack_nibbles(const uint8_t* src, size_t n, uint8_t* dst, const uint8_t* code, int threads) {
+double pack_nibbles(const uint8_t* src, size_t n, uint8_t* dst, const uint8_t* code, int threads) {
     static const bool avx2 = __builtin_cpu_supports("avx2");
     // (an AVX-512 VBMI form -- one vpermi2b as the 128-entry table -- packs no faster per core, the loop is bound by the core's
     //  streaming bandwidth, and end to end it was SLOWER on the B200 host: 4.5 vs 6.8 M reads/s, so it is not built)
     auto one = [&](const uint8_t* s, size_t len, uint8_t* d) { if (avx2) pack_avx2(s, len, d, code); else pack_scalar(s, len, d, code); };
     const size_t kChunk = 4u << 20;                              // bases per work item (even, so chunks start on a byte boundary)
     const int n_chunks = static_cast<int>((n + kChunk - 1) / kChunk);
-    if (threads <= 1 || n_chunks <= 1) { one(src, n, dst); return; }
-    pool(threads).run(n_chunks, [&](int c) {
+    if (threads <= 1 || n_chunks <= 1) {
+        const auto t0 = std::chrono::steady_clock::now();
+        one(src, n, dst);
+        return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    }
+    return pool(threads).run(n_chunks, [&](int c) {
         const size_t lo = static_cast<size_t>(c) * kChunk, len = std::min(kChunk, n - lo);
         one(src + lo, len, dst + (lo >> 1));
     });

@@ -6,6 +6,7 @@
 namespace bb {
 // code[256]: byte -> 4-bit IUPAC base set (the only property of a text byte the search depends on).
 // Packs n bases into (n+1)/2 bytes: out[i] = code[src[2i]] | code[src[2i+1]] << 4, using up to `threads` host threads.
-void pack_nibbles(const uint8_t* src, size_t n, uint8_t* dst, const uint8_t* code, int threads);
+// returns the seconds spent packing (the wait for the shared thread pool, when another caller is packing, is not counted)
+double pack_nibbles(const uint8_t* src, size_t n, uint8_t* dst, const uint8_t* code, int threads);
 int pack_default_threads();
 }  // namespace bb
