@@ -14,3 +14,28 @@ for kit, kw in (("SQK-NBD114-96", {}), ("SQK-RBK114-96", {}), ("SQK-RBK114-96", 
         rows = an.annotate(b, o)
         print(kit, kw, "filter" if uf else "exact", len(rows), "rows")
         an.close()
+
+# the barcode stage's other variants: 60-row patterns (16-byte column history), a barcode count that is not a multiple of 32,
+# regions with ambiguity codes / garbage bytes (general variant), long insertions (replayed Lodhi recurrence), packed H2D copy
+rnd = np.random.default_rng(33)
+acgt = np.frombuffer(b"ACGT", np.uint8)
+pre, suf = b"GGTCTAGACCATGCTAGGAT", b"TTGACCGATTCAGGCATCAA"
+seqs = []
+for i in range(37):
+    core = bytes(rnd.choice(acgt, 40))
+    seqs.append(pre + b"ACGT"[i % 4:i % 4 + 1] + core[1:-1] + b"ACGT"[(i // 4) % 4:(i // 4) % 4 + 1] + suf)
+gs = bb.GroupSet.from_seqs([(seqs, [f"X{i}" for i in range(37)], 0)])
+b, o, _ = synth.make_reads(gs.as_dicts(), 200, (150, 1500), seed=34)
+b = b.copy()
+idx = rnd.integers(0, len(b), len(b) // 50)
+b[idx] = rnd.choice(np.frombuffer(b"RYKMSWBDHVNacgtn-*x", np.uint8), len(idx))
+for kw in (dict(), dict(pack_h2d=True)):
+    an = bb.Annotator(gs, **kw)
+    rows = an.annotate(b, o)
+    print("custom 60-row panel", kw, len(rows), "rows")
+    an.close()
+gs = bb.GroupSet.from_kit("SQK-NBD114-96")
+big, obig, _ = synth.make_reads(gs.as_dicts(), 600, (2000, 5000), seed=35, n_frac=0.02)
+an = bb.Annotator(gs, pack_h2d=True)
+print("NBD packed copy, 2 % N:", len(an.annotate(big, obig)), "rows")
+an.close()
