@@ -682,8 +682,11 @@ __global__ void __launch_bounds__(128) k_flank_verify(const VerifyArgs V, const 
     const int span = G.m + G.k;
     for (uint64_t it = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; it < total; it += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
         if (it < n_end) {
-            const uint32_t r = static_cast<uint32_t>(it >> 2);
-            const int strand = static_cast<int>((it >> 1) & 1), which = static_cast<int>(it & 1);
+            // all head windows first, then all tail windows (about three times as long): the threads of a warp do the same kind
+            const int which = it >= n_end / 2 ? 1 : 0;
+            const uint64_t q = which ? it - n_end / 2 : it;
+            const uint32_t r = static_cast<uint32_t>(q >> 1);
+            const int strand = static_cast<int>(q & 1);
             const int n = static_cast<int>(__ldg(A.offsets + r + 1) - __ldg(A.offsets + r));
             if (n == 0) continue;
             // head: end positions [0, m+k]; tail: [n-m-k, n+m]; one window when they touch
