@@ -344,3 +344,32 @@ def test_cli_filter_inspect_trim(tmp_path):
                         "--only-side", "left"], capture_output=True, text=True)
     assert r.returncode == 0 and "Trimming complete!" in r.stdout, r.stdout + r.stderr
     assert any(f.name.endswith(".trimmed.fastq") for f in (tmp_path / "out").iterdir())
+
+
+def test_python_mirror_of_the_post_stages(tmp_path, capfd):
+    """barbell_b200.post: kit_info / kit_patterns / filter / inspect / trim_matches with the reference's argument names."""
+    from barbell_b200 import post
+    assert post.kit_info("SQK-RBK114-96") == ("RBK096_kit14", ["RBK01 - RBK96", "RBK01 - RBK96"], False)
+    assert post.kit_patterns("SQK-NBD114-96") == ["Ftag[fw, *, @left(0..250), >>]", "Ftag[<<, rc, *, @right(0..250)]",
+                                                  "Ftag[fw, ?1, @left(0..250), >>]__Ftag[<<, rc, ?1, @right(0..250)]"]
+    assert len(post.kit_patterns("SQK-RBK114-96", maximize=True)) == 5
+    with pytest.raises(bb.BarbellError):
+        post.kit_info("SQK-NOPE")
+    rng = random.Random(21)
+    rows = rand_rows(rng, 120)
+    (tmp_path / "a.tsv").write_text(P.to_tsv(rows))
+    counts = post.filter(tmp_path / "a.tsv", tmp_path / "f.tsv", tmp_path / "d.tsv", post.kit_patterns("SQK-NBD114-96", maximize=True))
+    import copy
+    kept, dropped = P.filter_rows(copy.deepcopy(rows), [P.parse_pattern(p) for p in post.kit_patterns("SQK-NBD114-96", maximize=True)])
+    n_reads = len({r.read_id for r in rows})
+    assert (tmp_path / "f.tsv").read_text() == P.to_tsv(kept) and counts["kept"] + counts["dropped"] == counts["total"] == n_reads
+    with pytest.raises(bb.BarbellError, match="Pattern parse error"):
+        post.filter(tmp_path / "a.tsv", tmp_path / "x.tsv", None, ["Ftag[fw]__What[x]"])
+    post.inspect(tmp_path / "f.tsv", top_n=2, read_pattern_out=tmp_path / "p.tsv")
+    assert len((tmp_path / "p.tsv").read_text().split("\n")) == len({r.read_id for r in kept}) + 1
+    reads = "".join(f"@{rid} d\n{'ACGT' * (L // 4)}{'A' * (L % 4)}\n+\n{'I' * L}\n" for rid, L in {r.read_id: r.read_len for r in rows}.items())
+    (tmp_path / "r.fastq").write_text(reads)
+    c = post.trim_matches(tmp_path / "f.tsv", [tmp_path / "r.fastq"], tmp_path / "out", add_orientation=False, add_flank=False, only_side="left")
+    assert c["total"] == n_reads and c["trimmed"] + c["failed"] == len({r.read_id for r in kept}) and c["trimmed"] > 10
+    with pytest.raises(bb.BarbellError, match="ambiguous"):
+        post.trim_matches(tmp_path / "f.tsv", [tmp_path / "r.fastq"], tmp_path / "out2", sort_labels=True, only_side="left")
