@@ -376,7 +376,7 @@ struct FilterArgs {
     uint64_t* windows;           // global queue of windows to verify
     uint32_t* n_windows;
     uint32_t win_cap;
-    uint32_t* overflow;          // set when a CTA queue or the global queue overflowed (host falls back to the exact scan)
+    uint32_t* overflow;          // set when the global window queue overflowed (host falls back to the exact scan)
     int halo_l, halo_r;          // text kept in shared memory before / after the CTA's chunks (pre-check of the second run)
 };
 
@@ -578,8 +578,20 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_flank_filter(const FilterAr
         if (r_e >= 0) push(BB_RC, r_s, r_e);
     }
     __syncthreads();
-    const uint32_t nq = *s_qn;
-    if (nq > kRunQueue) { if (tid == 0) atomicExch(F.overflow, 1u); return; }
+    uint32_t nq = *s_qn;
+    if (nq > kRunQueue) {
+        // More candidate runs than the CTA can queue (low-complexity text that keeps matching the run): every chunk of this tile
+        // becomes ONE candidate run per strand (all of its positions), the pre-check is skipped, and the windows that follow from
+        // those runs are verified exactly.
+        nq = 0;
+        if (active && b > a) {
+            const int Df = m - (G.f_q0 + q), Dr = m - G.f_q0, ps = a + 1, pe = b;
+            const int lo_f = max(ps + Df - k, 1), hi_f = min(pe + Df + k, n);
+            const int lo_r = max(n - pe + Dr - k, 1), hi_r = min(n - ps + Dr + k, n);
+            if (lo_f <= hi_f) s_stage[atomicAdd(s_wn, 1u)] = make_window(r, BB_FWD, lo_f, hi_f - lo_f);
+            if (lo_r <= hi_r) s_stage[atomicAdd(s_wn, 1u)] = make_window(r, BB_RC, lo_r, hi_r - lo_r);
+        }
+    }
     // ---- phase 3: pre-check of the CTA's runs on the shared text, survivors -> windows ----
     {
         const int qs = G.f_qs;

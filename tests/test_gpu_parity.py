@@ -310,15 +310,21 @@ def test_cli_fastq_to_annotation_tsv(tmp_path):
     assert r.returncode == 0 and "Error during processing" in r.stdout
 
 
-def test_prefilter_queue_overflow_falls_back_to_exact_scan():
-    """A read of N (matches everything) makes every position a filter candidate: the CTA queue overflows and the batch is
-    re-run with the exact scan; the result must still equal the oracle."""
+def test_prefilter_queue_overflow_falls_back_to_exact_verification():
+    """Low-complexity text that keeps matching the filter's run: a periodic repeat of the flank prefix gives a candidate run every
+    14 bases -- more than 2048 per CTA tile -- so those tiles are verified exactly (one window per chunk and strand); poly-N
+    makes every position a candidate (one long run per chunk).  The result must still equal the oracle."""
     gs = bb.GroupSet.from_kit("SQK-NBD114-96")
     b, o, _ = synth.make_reads(gs.as_dicts(), 40, (500, 3000), seed=31)
-    junk = np.frombuffer(b"N" * 6000 + b"ATTGCTAAGGTTAA" * 300, np.uint8)
-    bases = np.concatenate([b, junk])
-    offsets = np.concatenate([o, [o[-1] + 6000, o[-1] + len(junk)]]).astype(np.uint64)
-    _check(gs, bases, offsets)
+    tag = synth.full_tags(gs.as_dicts()[0])[11]
+    rep = np.frombuffer(b"ATTGCTAAGGTTAA" * 12000, np.uint8).copy()      # 168 kb: two whole CTA tiles of the repeat
+    rep[100_000:100_000 + len(tag)] = tag                                  # ... with a real tag inside
+    junk = [np.frombuffer(b"N" * 6000, np.uint8), np.frombuffer(b"ATTGCTAAGGTTAA" * 300, np.uint8), rep,
+            synth.revcomp(np.frombuffer(b"ATTGCTAAGGTTAA" * 7000, np.uint8))]
+    bases = np.concatenate([b] + junk)
+    offsets = np.concatenate([o, o[-1] + np.cumsum([len(x) for x in junk])]).astype(np.uint64)
+    rows = _check(gs, bases, offsets)
+    assert (rows["read_idx"] == 42).any()                                  # the tag inside the repeat was found
 
 
 def test_long_barcodes_unpacked_history_and_odd_counts():
