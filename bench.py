@@ -209,7 +209,7 @@ def main():
     ms_max = float(t.item())
     value = world * n_reads * args.steps / (ms_max / 1e3)
 
-    # ---- end to end: pinned host buffers through bb_submit / bb_collect (two streams), copies inside the timed region ----
+    # ---- end to end: pinned host buffers through bb_submit / bb_collect (4 sub-batches in flight), copies inside the timed region ----
     e2e = None
     if not args.no_e2e:
         n_sub, depth = args.e2e_sub, args.e2e_depth
