@@ -181,6 +181,22 @@ def test_custom_dual_end_384_panel():
     assert (rows["match_type"] < 2).sum() > 50
 
 
+def test_every_kit_preset():
+    """One kit name per preset of the reference's table (kits.rs:635-708: 21 presets, flanks of 44..90 rows, k = 3..20,
+    4..96 barcodes, one or two templates): rows and flank hits equal the oracle."""
+    import json
+    import os
+    names = json.load(open(os.path.join(os.path.dirname(bb.lib_path()), "data", "kits.json")))["kit_names"]
+    first = {}
+    for kit, preset in names:
+        first.setdefault(preset, kit)
+    assert len(first) >= 20
+    for preset, kit in sorted(first.items()):
+        gs = bb.GroupSet.from_kit(kit)
+        b, o, _ = synth.make_reads(gs.as_dicts(), 150, (200, 2500), seed=100 + len(preset))
+        _check(gs, b, o)
+
+
 def test_thresholds_and_alpha_variants():
     gs = bb.GroupSet.from_kit("SQK-NBD114-96", max_flank_errors=8)
     b, o, _ = synth.make_reads(gs.as_dicts(), 300, (100, 1500), seed=28, p_mut=0.12)
