@@ -619,13 +619,15 @@ int orc_demux(const orc_group *groups, int n_groups, const orc_params *prm, uint
     return r;
 }
 
-enum { PER = 64 };   /* per-read row / hit capacity inside the batch driver */
+/* per-read row / hit capacity inside the batch driver: 64, or ORC_PER_READ from the environment (fuzzing with repeat-heavy reads) */
+static int per_read(void) { const char *e = getenv("ORC_PER_READ"); int v = e ? atoi(e) : 64; return v < 8 ? 8 : (v > 65536 ? 65536 : v); }
 typedef struct {
     const demux_state *S; const orc_group *groups; const orc_params *prm; const uint8_t *bases; const uint64_t *offsets;
-    uint32_t base, nb; orc_row *tmp; int32_t *htmp; int *cnt; volatile uint32_t *next;
+    uint32_t base, nb; orc_row *tmp; int32_t *htmp; int *cnt; volatile uint32_t *next; int per;
 } job_t;
 static void *worker(void *arg) {
     job_t *J = (job_t *)arg;
+    const int PER = J->per;
     for (;;) {
         uint32_t q0 = __sync_fetch_and_add(J->next, 16u);
         if (q0 >= J->nb) break;
@@ -657,7 +659,8 @@ static int64_t batch_impl(const orc_group *groups, int n_groups, const orc_param
     if (n_threads > 1024) n_threads = 1024;
     /* reads are processed in parallel into per-read slots, then concatenated in input order */
     int64_t total = 0; int fail = 0;
-    uint32_t CH = 8192;
+    const int PER = per_read();
+    uint32_t CH = (uint32_t)(8192 * 64 / PER); if (CH < 16) CH = 16;
     orc_row *tmp = hits6 ? NULL : (orc_row *)malloc(sizeof(orc_row) * (size_t)CH * PER);
     int32_t *htmp = hits6 ? (int32_t *)malloc(sizeof(int32_t) * 6 * (size_t)CH * PER) : NULL;
     int *cnt = (int *)malloc(sizeof(int) * CH);
@@ -665,7 +668,7 @@ static int64_t batch_impl(const orc_group *groups, int n_groups, const orc_param
     for (uint32_t base = 0; base < n_reads && !fail; base += CH) {
         uint32_t nb = n_reads - base < CH ? n_reads - base : CH;
         volatile uint32_t next = 0;
-        job_t J = {S, groups, prm, bases, offsets, base, nb, tmp, htmp, cnt, &next};
+        job_t J = {S, groups, prm, bases, offsets, base, nb, tmp, htmp, cnt, &next, PER};
         for (int t = 1; t < n_threads; t++) pthread_create(&th[t], NULL, worker, &J);
         worker(&J);
         for (int t = 1; t < n_threads; t++) pthread_join(th[t], NULL);
