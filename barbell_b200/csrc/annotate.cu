@@ -92,7 +92,7 @@ struct Engine {
     std::string err;
     uint64_t launches = 0, h2d_bytes = 0;   // kernels launched / bytes copied host -> device by this engine
     // device buffers
-    DBuf d_bases, d_offsets, d_nch, d_chunk_base, d_tile_first, d_windows, d_entries, d_sorted, d_cub, d_flags, d_hitkeys, d_hits, d_hist, d_rows, d_valid, d_rows_out, d_hits6;
+    DBuf d_bases, d_offsets, d_nch, d_chunk_base, d_tile_first, d_tile_span, d_windows, d_entries, d_sorted, d_cub, d_flags, d_hitkeys, d_hits, d_hist, d_rows, d_valid, d_rows_out, d_hits6;
     DBuf d_counters;                     // [0] n_entries (u32) [2] n_selected (u32) [4..5] kept reads (u64)
     uint32_t entries_cap = 0;
     bool use_filter = true;              // bb_opts.flags bit 0 disables the pre-filter (exact scan everywhere)
@@ -127,7 +127,7 @@ struct Engine {
     }
     void destroy() {
         cudaSetDevice(device);
-        for (DBuf* b : {&d_bases, &d_offsets, &d_nch, &d_chunk_base, &d_tile_first, &d_windows, &d_entries, &d_sorted, &d_cub, &d_flags, &d_hitkeys, &d_hits, &d_hist, &d_rows,
+        for (DBuf* b : {&d_bases, &d_offsets, &d_nch, &d_chunk_base, &d_tile_first, &d_tile_span, &d_windows, &d_entries, &d_sorted, &d_cub, &d_flags, &d_hitkeys, &d_hits, &d_hist, &d_rows,
                         &d_valid, &d_rows_out, &d_hits6, &d_counters})
             b->release();
         if (h_counters) cudaFreeHost(h_counters);
@@ -168,6 +168,7 @@ struct Engine {
         BB_CUDA(d_nch.ensure(static_cast<size_t>(n_reads + 1) * 4));
         BB_CUDA(d_chunk_base.ensure(static_cast<size_t>(n_reads + 1) * 4));
         BB_CUDA(d_tile_first.ensure(static_cast<size_t>(n_tiles) * 4));
+        BB_CUDA(d_tile_span.ensure(static_cast<size_t>(n_tiles) * 16));
         k_chunk_count<<<(n_reads + 1 + 255) / 256, 256, 0, st>>>(offsets, n_reads, d_nch.as<uint32_t>());
         launches++;
         {
@@ -176,7 +177,7 @@ struct Engine {
             BB_CUDA(d_cub.ensure(tmp));
             BB_CUDA(cub::DeviceScan::ExclusiveSum(d_cub.p, tmp, d_nch.as<uint32_t>(), d_chunk_base.as<uint32_t>(), static_cast<int>(n_reads + 1), st));
         }
-        k_tile_index<<<(n_tiles + 255) / 256, 256, 0, st>>>(d_chunk_base.as<uint32_t>(), n_reads, n_tiles, d_tile_first.as<uint32_t>());
+        k_tile_index<<<(n_tiles + 255) / 256, 256, 0, st>>>(d_chunk_base.as<uint32_t>(), offsets, n_reads, n_tiles, d_tile_first.as<uint32_t>(), d_tile_span.as<uint64_t>());
         launches++;
         BB_CUDA(cudaGetLastError());
 
@@ -195,7 +196,7 @@ struct Engine {
                 const DevGroup& G = gt->host[g];
                 ScanArgs A{};
                 A.bases = bases; A.offsets = offsets; A.n_reads = n_reads; A.total16 = total16;
-                A.chunk_base = d_chunk_base.as<uint32_t>(); A.tile_first = d_tile_first.as<uint32_t>();
+                A.chunk_base = d_chunk_base.as<uint32_t>(); A.tile_first = d_tile_first.as<uint32_t>(); A.tile_span = d_tile_span.as<uint64_t>();
                 A.group = g;
                 A.entries = d_entries.as<uint64_t>(); A.n_entries = d_cnt; A.cap = entries_cap;
                 if (G.f_on && use_filter && !force_exact) {

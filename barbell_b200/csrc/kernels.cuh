@@ -142,6 +142,7 @@ struct ScanArgs {
     const uint64_t* offsets;     // n_reads + 1
     const uint32_t* chunk_base;  // n_reads + 1: exclusive prefix sum of ceil(len / kChunk)
     const uint32_t* tile_first;  // per CTA: read owning the CTA's first chunk
+    const uint64_t* tile_span;   // per CTA: [2t] first / [2t+1] one-past-last byte of its chunks in `bases` (no halo)
     uint32_t n_reads;
     uint64_t total16;            // readable bytes of `bases` (total rounded up to 16)
     int group;
@@ -171,17 +172,31 @@ __device__ __forceinline__ uint32_t find_chunk_read(const uint32_t* __restrict__
     return a - 1;
 }
 
-// per CTA: the read that owns chunk cta*256 (thread per CTA)
-__global__ void k_tile_index(const uint32_t* __restrict__ chunk_base, uint32_t n_reads, uint32_t n_tiles, uint32_t* __restrict__ tile_first) {
+// per CTA: the read that owns chunk cta*256 and the byte span of the CTA's chunks (thread per CTA), so that the scan kernels can
+// issue their TMA copy before any chunk lookup
+__global__ void k_tile_index(const uint32_t* __restrict__ chunk_base, const uint64_t* __restrict__ offsets, uint32_t n_reads, uint32_t n_tiles,
+                             uint32_t* __restrict__ tile_first, uint64_t* __restrict__ tile_span) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_tiles) return;
-    const uint32_t c = t * kScanThreads;
-    uint32_t a = 0, b = n_reads + 1;                   // first index with chunk_base[idx] > c
-    while (a < b) {
-        const uint32_t mid = (a + b) >> 1;
-        if (chunk_base[mid] <= c) a = mid + 1; else b = mid;
-    }
-    tile_first[t] = a - 1;
+    const uint32_t total_chunks = chunk_base[n_reads];
+    auto owner = [&](uint32_t c) {                      // read owning chunk c: last index with chunk_base[idx] <= c
+        uint32_t a = 0, b = n_reads + 1;
+        while (a < b) {
+            const uint32_t mid = (a + b) >> 1;
+            if (chunk_base[mid] <= c) a = mid + 1; else b = mid;
+        }
+        return a - 1;
+    };
+    const uint32_t c_first = t * kScanThreads;
+    const uint32_t r_first = owner(c_first);
+    tile_first[t] = r_first;
+    if (c_first >= total_chunks) { tile_span[2 * t] = 0; tile_span[2 * t + 1] = 0; return; }
+    const uint32_t c_last = min(c_first + kScanThreads, total_chunks) - 1;
+    const uint32_t r_last = owner(c_last);
+    const uint64_t g_lo = offsets[r_first] + static_cast<uint64_t>(c_first - chunk_base[r_first]) * kChunk;
+    uint64_t g_hi = offsets[r_last] + static_cast<uint64_t>(c_last - chunk_base[r_last] + 1) * kChunk;
+    if (g_hi > offsets[r_last + 1]) g_hi = offsets[r_last + 1];
+    tile_span[2 * t] = g_lo; tile_span[2 * t + 1] = g_hi;
 }
 
 // top-aligned column step: returns the bottom-row delta (+1 / 0 / -1)
@@ -236,12 +251,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_flank_scan(const ScanArgs A
     if (tid == 0) {
         mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        const uint32_t c_last = min(c_first + kScanThreads, total_chunks) - 1;
-        const uint32_t r_last = find_chunk_read(A.chunk_base, A.n_reads, r_first, c_last);
-        const uint64_t g_lo = __ldg(A.offsets + r_first) + static_cast<uint64_t>(c_first - __ldg(A.chunk_base + r_first)) * kChunk;
-        uint64_t g_hi = __ldg(A.offsets + r_last) + static_cast<uint64_t>(c_last - __ldg(A.chunk_base + r_last) + 1) * kChunk;
-        const uint64_t r_end = __ldg(A.offsets + r_last + 1);
-        if (g_hi > r_end) g_hi = r_end;
+        const uint64_t g_lo = __ldg(A.tile_span + 2 * blockIdx.x), g_hi = __ldg(A.tile_span + 2 * blockIdx.x + 1);
         uint64_t lo = g_lo >= static_cast<uint64_t>(W) ? g_lo - W : 0;
         lo &= ~15ull;
         uint64_t hi = (g_hi + W + 15) & ~15ull;
@@ -468,12 +478,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_flank_filter(const FilterAr
         *s_qn = 0; *s_wn = 0;
         mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        const uint32_t c_last = min(c_first + kScanThreads, total_chunks) - 1;
-        const uint32_t r_last = find_chunk_read(A.chunk_base, A.n_reads, r_first, c_last);
-        const uint64_t g_lo = __ldg(A.offsets + r_first) + static_cast<uint64_t>(c_first - __ldg(A.chunk_base + r_first)) * kChunk;
-        uint64_t g_hi = __ldg(A.offsets + r_last) + static_cast<uint64_t>(c_last - __ldg(A.chunk_base + r_last) + 1) * kChunk;
-        const uint64_t r_end = __ldg(A.offsets + r_last + 1);
-        if (g_hi > r_end) g_hi = r_end;
+        const uint64_t g_lo = __ldg(A.tile_span + 2 * blockIdx.x), g_hi = __ldg(A.tile_span + 2 * blockIdx.x + 1);
         uint64_t lo = g_lo >= static_cast<uint64_t>(F.halo_l) ? g_lo - F.halo_l : 0;
         lo &= ~15ull;
         uint64_t hi = (g_hi + F.halo_r + 15) & ~15ull;
