@@ -8,7 +8,7 @@ python tools/make_fastq.py $TMP/reads.fastq $N > /dev/null
 ls -la $TMP/reads.fastq | awk '{print "fastq bytes", $5}' | tee $OUT/throughput.txt
 for mode in "--single-reader" "-t 4" "-t 8" "-t 8"; do
   s=$(date +%s%N)
-  barbell_b200/barbell annotate --kit SQK-NBD114-96 -i $TMP/reads.fastq -o $TMP/out.tsv $mode | tail -2 | tr '\n' ' '
+  barbell_b200/barbell annotate --kit SQK-NBD114-96 -i $TMP/reads.fastq -o $TMP/out.tsv $mode | tail -1 | tee -a $OUT/throughput.txt
   e=$(date +%s%N)
   echo "| mode=[$mode] wall_ms=$(( (e - s) / 1000000 )) reads=$N" | tee -a $OUT/throughput.txt
   md5sum $TMP/out.tsv | tee -a $OUT/throughput.txt
