@@ -36,7 +36,7 @@ EXPORTS = ["bb_groups_from_kit", "bb_groups_from_fasta", "bb_groups_add", "bb_gr
            "bb_groups_count", "bb_groups_data", "bb_groups_label", "bb_groups_free", "bb_edit_cut_off", "bb_label_range",
            "bb_lookup_barcode_seq", "bb_create",
            "bb_destroy", "bb_last_error", "bb_set_groups", "bb_annotate", "bb_annotate_device", "bb_fetch_rows",
-           "bb_submit", "bb_collect", "bb_counters", "bb_host_alloc", "bb_host_free", "bb_pack_nibbles", "bb_last_stage_ms", "bb_kernel_launches", "bb_h2d_bytes", "bb_fetch_flank_hits",
+           "bb_submit", "bb_collect", "bb_counters", "bb_host_alloc", "bb_host_free", "bb_pack_nibbles", "bb_pack_crumbs", "bb_last_stage_ms", "bb_kernel_launches", "bb_h2d_bytes", "bb_fetch_flank_hits",
            "bb_kit_info", "bb_kit_filter_patterns", "bb_pattern_parse", "bb_filter", "bb_inspect", "bb_trim",
            "bb_abi_version"]
 
@@ -86,6 +86,7 @@ def lib():
     L.bb_host_alloc.argtypes = [C.c_size_t]; L.bb_host_alloc.restype = C.c_void_p
     L.bb_host_free.argtypes = [C.c_void_p]; L.bb_host_free.restype = None
     L.bb_pack_nibbles.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
+    L.bb_pack_crumbs.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
     L.bb_abi_version.restype = C.c_int
     _lib = L
     return L
@@ -204,7 +205,7 @@ class Annotator:
                  pack_h2d=False):
         self._ctx = C.c_void_p()
         self.groups = groups
-        o = _Opts(device, alpha, min_score, min_score_diff, 0, 0, (0 if use_filter else 1) | (2 if pack_h2d else 0))
+        o = _Opts(device, alpha, min_score, min_score_diff, 0, 0, (0 if use_filter else 1) | (4 if pack_h2d == "crumbs" else 2 if pack_h2d else 0))
         err = C.create_string_buffer(512)
         rc = lib().bb_create(C.byref(o), C.byref(self._ctx), err, 512)
         if rc != 0:

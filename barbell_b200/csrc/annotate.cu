@@ -96,7 +96,8 @@ struct Engine {
     DBuf d_counters;                     // [0] n_entries (u32) [2] n_selected (u32) [4..5] kept reads (u64)
     uint32_t entries_cap = 0;
     bool use_filter = true;              // bb_opts.flags bit 0 disables the pre-filter (exact scan everywhere)
-    bool pack_h2d = false;               // bb_opts.flags bit 1: nibble-pack the bases on the host before the PCIe copy
+    int pack_mode = 0;                   // bb_opts.flags bit 1: nibble-pack the bases on the host before the PCIe copy (1); bit 2: 2 bits per base
+                                         // + an exception list (2; falls back to 1 for good when a batch has too many non-ACGT bytes)
     int pack_threads = 1;
     uint8_t* h_pack = nullptr; size_t h_pack_cap = 0;   // pinned staging of the packed bases
     DBuf d_packed;
@@ -363,27 +364,52 @@ struct Engine {
         if (offsets[0] != 0) { set_error("offsets[0] must be 0"); return BB_ERR_INVALID; }
         BB_CUDA(d_bases.ensure(((total + 15) & ~15ull) + 16));
         BB_CUDA(d_offsets.ensure(static_cast<size_t>(n_reads + 1) * 8));
-        if (pack_h2d && total >= (1u << 20)) {
-            // Two bases per byte over PCIe for the HEAD of the batch (packed on the host cores, expanded on the device; lossless
-            // for this path) while the TAIL goes over the link as it is: the plain copy is queued first, so the DMA engine moves
-            // it while the cores pack.  The split balances the two resources: with P = pack rate and B = link rate (both measured
-            // on every batch), head fraction x solves (1 - x/2) / B = x / P.
+        if (pack_mode && total >= (1u << 20)) {
+            // Fewer bytes over PCIe for the HEAD of the batch (packed on the host cores, expanded on the device; lossless for this
+            // path) while the TAIL goes over the link as it is: the plain copy is queued first, so the DMA engine moves it while
+            // the cores pack.  The split balances the two resources: with P = pack rate, B = link rate (both measured on every
+            // batch) and r = packed bytes per base, head fraction x solves (1 - x + r x) / B = x / P.
             const uint64_t split = std::min<uint64_t>(total, static_cast<uint64_t>(pack_frac * static_cast<double>(total))) & ~63ull;
-            const size_t pbytes = static_cast<size_t>(split / 2 + 64);
-            if (pbytes > h_pack_cap) {
+            const size_t n_items = static_cast<size_t>(split >> 22) + 1;                       // work items of the packer (4 M bases each)
+            const size_t exc_cap = static_cast<size_t>(split / 64) + (n_items + 1) * 256;       // crumb mode: up to ~1.5 % non-ACGT bytes
+            if (h_pack_cap < static_cast<size_t>(total / 2 + 64)) {
                 if (h_pack) cudaFreeHost(h_pack);
                 h_pack = nullptr; h_pack_cap = 0;
-                const size_t want = static_cast<size_t>(total / 2 + 64) + static_cast<size_t>(total / 8);
+                const size_t want = static_cast<size_t>(total / 2 + 64) + static_cast<size_t>(total / 8) + (1u << 16);
                 BB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&h_pack), want));
                 h_pack_cap = want;
             }
-            BB_CUDA(d_packed.ensure(pbytes));
             BB_CUDA(cudaEventRecord(ev_copy[0], stream));
             if (total > split) BB_CUDA(cudaMemcpyAsync(d_bases.as<uint8_t>() + split, bases + split, total - split, cudaMemcpyHostToDevice, stream));
             BB_CUDA(cudaEventRecord(ev_copy[1], stream));
-            const double pack_s = split ? pack_nibbles(bases, split, h_pack, kAlpha.code, pack_threads) : 0.0;   // the pool's own time
-            if (split) {
-                BB_CUDA(cudaMemcpyAsync(d_packed.p, h_pack, split / 2, cudaMemcpyHostToDevice, stream));
+            double pack_s = 0.0;
+            size_t wire = 0;                                                                   // bytes of the packed copy
+            bool crumbs = pack_mode == 2 && split > 0;
+            if (crumbs) {
+                const size_t pk = (static_cast<size_t>(split / 4) + 63) & ~size_t(63);
+                size_t n_exc = 0; bool over = false;
+                if (pk + exc_cap * 8 > h_pack_cap) over = true;
+                else pack_s = pack_crumbs(bases, split, h_pack, reinterpret_cast<uint64_t*>(h_pack + pk), exc_cap, &n_exc, &over, kAlpha.code, pack_threads);
+                if (over) { crumbs = false; pack_mode = 1; pack_rate *= 0.5; }                  // N-rich input: nibbles from here on
+                else {
+                    wire = pk + n_exc * 8;
+                    BB_CUDA(d_packed.ensure(wire + 64));
+                    BB_CUDA(cudaMemcpyAsync(d_packed.p, h_pack, wire, cudaMemcpyHostToDevice, stream));
+                    k_unpack_crumbs<<<static_cast<unsigned>((split / 16 + 255) / 256), 256, 0, stream>>>(d_packed.as<uint8_t>(), d_bases.as<uint8_t>(), split);
+                    launches++;
+                    if (n_exc) {
+                        k_patch_exceptions<<<static_cast<unsigned>((n_exc + 255) / 256), 256, 0, stream>>>(
+                            reinterpret_cast<const uint64_t*>(d_packed.as<uint8_t>() + pk), n_exc, d_bases.as<uint8_t>(), split);
+                        launches++;
+                    }
+                    BB_CUDA(cudaGetLastError());
+                }
+            }
+            if (!crumbs && split) {
+                pack_s += pack_nibbles(bases, split, h_pack, kAlpha.code, pack_threads);      // the pool's own time
+                wire = static_cast<size_t>(split / 2);
+                BB_CUDA(d_packed.ensure(wire + 64));
+                BB_CUDA(cudaMemcpyAsync(d_packed.p, h_pack, wire, cudaMemcpyHostToDevice, stream));
                 k_unpack_nibbles<<<static_cast<unsigned>((split / 16 + 255) / 256), 256, 0, stream>>>(d_packed.as<uint8_t>(), d_bases.as<uint8_t>(), split);
                 launches++;
                 BB_CUDA(cudaGetLastError());
@@ -396,8 +422,9 @@ struct Engine {
             if (total - split >= (1u << 20) && cudaEventElapsedTime(&copy_ms, ev_copy[0], ev_copy[1]) == cudaSuccess && copy_ms > 0.f)
                 link_rate = std::max(0.98 * link_rate, static_cast<double>(total - split) / (copy_ms * 1e-3));
             if (split >= (1u << 20) && pack_s > 0.0) pack_rate = 0.5 * pack_rate + 0.5 * (static_cast<double>(split) / pack_s);
-            h2d_bytes += (total - split) + split / 2 + static_cast<uint64_t>(n_reads + 1) * 8;
-            const double x = pack_rate / (link_rate + 0.5 * pack_rate);
+            h2d_bytes += (total - split) + wire + static_cast<uint64_t>(n_reads + 1) * 8;
+            const double saved = pack_mode == 2 ? 0.75 : 0.5;     // 1 - r
+            const double x = pack_rate / (link_rate + saved * pack_rate);
             pack_frac = std::min(1.0, std::max(0.05, 0.5 * pack_frac + 0.5 * x));
         } else {
             BB_CUDA(cudaMemcpyAsync(d_bases.p, bases, total, cudaMemcpyHostToDevice, stream));
@@ -487,7 +514,7 @@ int bb_create(const bb_opts* opts, bb_ctx** out, char* err, size_t errlen) {
         c->eng[i].gt = &c->gt;
         c->eng[i].prm.min_score = opts->min_score; c->eng[i].prm.min_score_diff = opts->min_score_diff;
         c->eng[i].use_filter = (opts->flags & 1u) == 0;
-        c->eng[i].pack_h2d = (opts->flags & 2u) != 0;
+        c->eng[i].pack_mode = (opts->flags & 4u) ? 2 : (opts->flags & 2u) ? 1 : 0;
         c->eng[i].pack_threads = bb::pack_default_threads();
     }
     *out = c;
@@ -793,6 +820,14 @@ int bb_pack_nibbles(const uint8_t* src, uint64_t n, uint8_t* dst) {
     if ((!src || !dst) && n) return BB_ERR_INVALID;
     bb::pack_nibbles(src, n, dst, bb::kAlpha.code, bb::pack_default_threads());
     return BB_OK;
+}
+
+int bb_pack_crumbs(const uint8_t* src, uint64_t n, uint8_t* dst, uint64_t* exc, uint64_t exc_cap, uint64_t* n_exc) {
+    if (((!src || !dst) && n) || !n_exc || (!exc && exc_cap)) return BB_ERR_INVALID;
+    size_t used = 0; bool over = false;
+    bb::pack_crumbs(src, n, dst, exc, exc_cap, &used, &over, bb::kAlpha.code, bb::pack_default_threads());
+    *n_exc = used;
+    return over ? BB_ERR_OVERFLOW : BB_OK;
 }
 
 void* bb_host_alloc(size_t bytes) {

@@ -58,6 +58,77 @@ __attribute__((target("avx2"))) void pack_avx2(const uint8_t* src, size_t n, uin
     pack_scalar(src + i, n - i, dst + (i >> 1), code);
 }
 
+// ---- two bits per base + an exception list ------------------------------------------------------------------------------
+// Reads are almost all A/C/G/T, so the densest lossless wire format for this path is 2 bits per base (A C G T = 0 1 2 3, any
+// case, U as T) with every other byte sent as an exception: (position << 4 | 4-bit base set).  The device expands the crumbs
+// to letters and then patches the exceptions (k_unpack_crumbs, k_patch_exceptions).
+constexpr uint64_t kExcEmpty = ~0ull;                             // filler of a partly used exception block (the device skips it)
+constexpr size_t kExcBlock = 256;                                 // entries a work item takes from the shared list at a time
+
+struct ExcWriter {
+    uint64_t* buf; size_t cap; std::atomic<uint64_t>* next; std::atomic<bool>* overflow;
+    size_t cur = 0, end = 0;
+    void push(uint64_t v) {
+        if (cur == end) {
+            const uint64_t b = next->fetch_add(kExcBlock);
+            if (b + kExcBlock > cap) { overflow->store(true); next->fetch_sub(kExcBlock); return; }
+            cur = static_cast<size_t>(b); end = cur + kExcBlock;
+        }
+        buf[cur++] = v;
+    }
+    void finish() { while (cur < end) buf[cur++] = kExcEmpty; }
+};
+
+// base set -> crumb; 0x80 marks "not a single base": goes to the exception list
+alignas(32) const uint8_t kCrumbOfSet[32] = {0x80, 0, 1, 0x80, 2, 0x80, 0x80, 0x80, 3, 0x80, 0x80, 0x80, 0x80, 0x80, 0x80, 0x80,
+                                             0x80, 0, 1, 0x80, 2, 0x80, 0x80, 0x80, 3, 0x80, 0x80, 0x80, 0x80, 0x80, 0x80, 0x80};
+
+void crumbs_scalar(const uint8_t* src, size_t pos0, size_t n, uint8_t* dst, const uint8_t* code, ExcWriter& w) {
+    for (size_t i = 0; i < n; i += 4) {
+        uint8_t b = 0;
+        for (size_t t = 0; t < 4 && i + t < n; t++) {
+            const uint8_t v = code[src[i + t]], cr = kCrumbOfSet[v];
+            if (cr & 0x80) w.push(static_cast<uint64_t>(pos0 + i + t) << 4 | v);
+            else b = static_cast<uint8_t>(b | cr << (2 * t));
+        }
+        dst[i >> 2] = b;
+    }
+}
+
+// 128 input bytes -> 32 output bytes per iteration
+__attribute__((target("avx2"))) void crumbs_avx2(const uint8_t* src, size_t pos0, size_t n, uint8_t* dst, const uint8_t* code, ExcWriter& w) {
+    alignas(32) uint8_t tl[32], th[32];
+    for (int i = 0; i < 16; i++) { tl[i] = tl[i + 16] = code[0x40 + i]; th[i] = th[i + 16] = code[0x50 + i]; }
+    const __m256i TL = _mm256_load_si256(reinterpret_cast<const __m256i*>(tl));
+    const __m256i TH = _mm256_load_si256(reinterpret_cast<const __m256i*>(th));
+    const __m256i S = _mm256_load_si256(reinterpret_cast<const __m256i*>(kCrumbOfSet));
+    const __m256i three = _mm256_set1_epi8(3);
+    const __m256i mul4 = _mm256_set1_epi16(0x0401), mul16 = _mm256_set1_epi16(0x1001);
+    const bool aligned = (reinterpret_cast<uintptr_t>(dst) & 31) == 0;
+    size_t i = 0;
+    for (; i + 128 <= n; i += 128) {
+        __m256i c[4];
+        for (int q = 0; q < 4; q++) {
+            const __m256i v = codes32(_mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + i + 32 * q)), TL, TH);
+            const __m256i s = _mm256_shuffle_epi8(S, v);
+            uint32_t m = static_cast<uint32_t>(_mm256_movemask_epi8(s));
+            while (m) {                                                     // rare: bytes that are not a single base
+                const int t = __builtin_ctz(m); m &= m - 1;
+                const size_t at = i + 32 * q + t;
+                w.push(static_cast<uint64_t>(pos0 + at) << 4 | code[src[at]]);
+            }
+            c[q] = _mm256_and_si256(s, three);
+        }
+        const __m256i n01 = _mm256_permute4x64_epi64(_mm256_packus_epi16(_mm256_maddubs_epi16(c[0], mul4), _mm256_maddubs_epi16(c[1], mul4)), 0xD8);
+        const __m256i n23 = _mm256_permute4x64_epi64(_mm256_packus_epi16(_mm256_maddubs_epi16(c[2], mul4), _mm256_maddubs_epi16(c[3], mul4)), 0xD8);
+        const __m256i pk = _mm256_permute4x64_epi64(_mm256_packus_epi16(_mm256_maddubs_epi16(n01, mul16), _mm256_maddubs_epi16(n23, mul16)), 0xD8);
+        if (aligned) _mm256_stream_si256(reinterpret_cast<__m256i*>(dst + (i >> 2)), pk);
+        else _mm256_storeu_si256(reinterpret_cast<__m256i*>(dst + (i >> 2)), pk);
+    }
+    if (aligned) _mm_sfence();
+    crumbs_scalar(src + i, pos0 + i, n - i, dst + (i >> 2), code, w);
+}
+
 class Pool {
   public:
     explicit Pool(int n) {
@@ -145,5 +216,33 @@ double pack_nibbles(const uint8_t* src, size_t n, uint8_t* dst, const uint8_t* c
         const size_t lo = static_cast<size_t>(c) * kChunk, len = std::min(kChunk, n - lo);
         one(src + lo, len, dst + (lo >> 1));
     });
+}
+
+double pack_crumbs(const uint8_t* src, size_t n, uint8_t* dst, uint64_t* exc, size_t exc_cap, size_t* n_exc, bool* overflow,
+                   const uint8_t* code, int threads) {
+    static const bool avx2 = __builtin_cpu_supports("avx2");
+    std::atomic<uint64_t> next{0};
+    std::atomic<bool> over{false};
+    auto one = [&](const uint8_t* s, size_t pos0, size_t len, uint8_t* d) {
+        ExcWriter w{exc, exc_cap, &next, &over};
+        if (avx2) crumbs_avx2(s, pos0, len, d, code, w); else crumbs_scalar(s, pos0, len, d, code, w);
+        w.finish();
+    };
+    const size_t kChunk = 4u << 20;                              // bases per work item (a multiple of 4: chunks start on a byte boundary)
+    const int n_chunks = static_cast<int>((n + kChunk - 1) / kChunk);
+    double secs;
+    if (threads <= 1 || n_chunks <= 1) {
+        const auto t0 = std::chrono::steady_clock::now();
+        one(src, 0, n, dst);
+        secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    } else {
+        secs = pool(threads).run(n_chunks, [&](int c) {
+            const size_t lo = static_cast<size_t>(c) * kChunk, len = std::min(kChunk, n - lo);
+            one(src + lo, lo, len, dst + (lo >> 2));
+        });
+    }
+    *n_exc = static_cast<size_t>(next.load());
+    *overflow = over.load();
+    return secs;
 }
 }  // namespace bb

@@ -8,5 +8,10 @@ namespace bb {
 // Packs n bases into (n+1)/2 bytes: out[i] = code[src[2i]] | code[src[2i+1]] << 4, using up to `threads` host threads.
 // returns the seconds spent packing (the wait for the shared thread pool, when another caller is packing, is not counted)
 double pack_nibbles(const uint8_t* src, size_t n, uint8_t* dst, const uint8_t* code, int threads);
+// Two bits per base for A/C/G/T (any case, U as T) into (n+3)/4 bytes, every other byte as an exception entry
+// (position << 4 | base set) appended to exc[0, exc_cap) in blocks; unused entries of a block hold ~0.  *n_exc = entries to copy,
+// *overflow = the list was too small (the output is then unusable).  Returns the packing seconds like pack_nibbles.
+double pack_crumbs(const uint8_t* src, size_t n, uint8_t* dst, uint64_t* exc, size_t exc_cap, size_t* n_exc, bool* overflow,
+                   const uint8_t* code, int threads);
 int pack_default_threads();
 }  // namespace bb

@@ -1111,6 +1111,34 @@ __global__ void k_unpack_nibbles(const uint8_t* __restrict__ packed, uint8_t* __
     *reinterpret_cast<uint4*>(bases + g) = make_uint4(out[0], out[1], out[2], out[3]);
 }
 
+// The denser wire format (host/pack.cpp pack_crumbs): 2 bits per base for A C G T, 16 bases per thread (4 bytes in, 16 bytes out) ...
+__global__ void k_unpack_crumbs(const uint8_t* __restrict__ packed, uint8_t* __restrict__ bases, uint64_t n_bases) {
+    const uint64_t g = (blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x) * 16;
+    if (g >= n_bases) return;
+    const uint32_t lut = 0x54474341u;                 // crumbs 0..3 : A C G T (little endian bytes)
+    const uint32_t in = *reinterpret_cast<const uint32_t*>(packed + (g >> 2));
+    uint32_t out[4];
+#pragma unroll
+    for (int w = 0; w < 4; w++) {
+        uint32_t v = 0;
+#pragma unroll
+        for (int t = 0; t < 4; t++) v |= ((lut >> (((in >> (8 * w + 2 * t)) & 3u) * 8)) & 0xffu) << (8 * t);
+        out[w] = v;
+    }
+    *reinterpret_cast<uint4*>(bases + g) = make_uint4(out[0], out[1], out[2], out[3]);
+}
+// ... and every byte that is not a single base arrives as (position << 4 | base set) and is written over the placeholder
+// (same set -> letter table as k_unpack_nibbles; ~0 = unused entry of a partly filled block)
+__global__ void k_patch_exceptions(const uint64_t* __restrict__ exc, uint64_t n_exc, uint8_t* __restrict__ bases, uint64_t n_bases) {
+    const uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
+    if (i >= n_exc) return;
+    const uint64_t v = exc[i];
+    if (v == ~0ull || (v >> 4) >= n_bases) return;
+    const uint64_t lut_lo = 0x565352474d434158ull, lut_hi = 0x4e42444b48595754ull;
+    const uint32_t c = static_cast<uint32_t>(v) & 15u;
+    bases[v >> 4] = static_cast<uint8_t>(((c & 8u) ? lut_hi : lut_lo) >> ((c & 7u) * 8));
+}
+
 // flank hit list for parity checks of the flank stage alone
 __global__ void k_export_hits(const Hit* __restrict__ hits, uint32_t n_hits, int32_t* __restrict__ out6) {
     const uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;

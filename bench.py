@@ -260,15 +260,20 @@ def main():
         an_pack = bb.Annotator(gs, device=local, pack_h2d=True)
         dt_pack, rows_pack, moved_pack = timed_e2e(an_pack)
         an_pack.close()
-        assert rows_pack == rows_e2e and moved_plain == h2d
-        modes = {"plain": (dt_plain, moved_plain), "packed": (dt_pack, moved_pack)}
+        # flags bit 2: the denser wire format, 2 bits per base for A/C/G/T + an exception list for every other byte
+        an_crumb = bb.Annotator(gs, device=local, pack_h2d="crumbs")
+        dt_crumb, rows_crumb, moved_crumb = timed_e2e(an_crumb)
+        an_crumb.close()
+        assert rows_pack == rows_e2e and rows_crumb == rows_e2e and moved_plain == h2d
+        modes = {"plain": (dt_plain, moved_plain), "packed": (dt_pack, moved_pack), "crumbs": (dt_crumb, moved_crumb)}
         best = min(modes, key=lambda k: modes[k][0])
         dt = modes[best][0]
         e2e = dict(value=world * n_reads * args.steps / dt, unit="reads/s", h2d_bytes_per_step=modes[best][1],
                    d2h_bytes_per_step=int(rows_e2e // args.steps * 88),
                    api=f"bb_submit/bb_collect, pinned host buffers, {n_sub} sub-batches per step, {depth} in flight; mode=" + best +
-                       (" (head of every batch nibble-packed by the library on the host cores and expanded on the device, tail copied as it is; "
-                        "bytes counted by the library: bb_h2d_bytes)" if best == "packed" else ""),
+                       (" (head of every batch packed by the library on the host cores -- " +
+                        ("4 bits per base" if best == "packed" else "2 bits per base + exception list") +
+                        " -- and expanded on the device, tail copied as it is; bytes counted by the library: bb_h2d_bytes)" if best != "plain" else ""),
                    gbases_per_s=world * total * args.steps / dt / 1e9,
                    by_mode={k: world * n_reads * args.steps / v[0] for k, v in modes.items()},
                    h2d_bytes_by_mode={k: v[1] for k, v in modes.items()})

@@ -74,7 +74,9 @@ typedef struct {
     uint32_t max_batch_reads;   /* (0 = 4 Mi reads) */
     uint32_t flags;             /* bit 0: disable the lossless pre-filter (exact full-length scan everywhere);
                                    bit 1: nibble-pack the head of every batch on the host cores before the PCIe copy while the tail is copied
-                                   as it is; the split adapts to the measured pack and link rates (bb_annotate / bb_submit) */
+                                   as it is; the split adapts to the measured pack and link rates (bb_annotate / bb_submit);
+                                   bit 2: like bit 1 with the denser wire format: 2 bits per base for A/C/G/T plus an exception list for every
+                                   other byte (a batch with more than ~1.5 % such bytes switches the context to the nibble format) */
 } bb_opts;
 
 typedef struct bb_ctx bb_ctx;
@@ -152,6 +154,10 @@ void bb_host_free(void *p);
 /* the wire format of flags bit 1, exposed for hosts that want to pack while parsing: dst[i] = set(src[2i]) | set(src[2i+1]) << 4,
    set() = 4-bit IUPAC base set (A=1, C=2, G=4, T=8; non-IUPAC bytes 0); dst holds (n+1)/2 bytes */
 int  bb_pack_nibbles(const uint8_t *src, uint64_t n, uint8_t *dst);
+/* the wire format of flags bit 2: dst[i] = crumb(src[4i]) | crumb(src[4i+1]) << 2 | crumb(src[4i+2]) << 4 | crumb(src[4i+3]) << 6 with
+   A C G T (any case, U as T) = 0 1 2 3, dst holds (n+3)/4 bytes; every other byte has crumb 0 and an entry (position << 4 | set())
+   in exc[0, *n_exc), appended in blocks whose unused entries are ~0.  BB_ERR_OVERFLOW when exc_cap entries do not suffice */
+int  bb_pack_crumbs(const uint8_t *src, uint64_t n, uint8_t *dst, uint64_t *exc, uint64_t exc_cap, uint64_t *n_exc);
 
 /* ---- the stages that consume annotation.tsv (host side, no GPU): filter, inspect, trim -- so that `barbell kit` runs the
  *      reference's whole pipeline, src/kits/use_kit.rs:11-109 ---- */

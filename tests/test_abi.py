@@ -76,3 +76,39 @@ def test_pack_nibbles_matches_numpy():
         dst = np.zeros((n + 1) // 2 + 1, np.uint8)
         assert bb.lib().bb_pack_nibbles(src.ctypes.data, n, dst.ctypes.data) == 0
         assert (dst[:(n + 1) // 2] == want).all()
+
+
+def test_pack_crumbs_matches_numpy():
+    """bb_pack_crumbs (AVX2 + thread pool, exception blocks) against a numpy restatement: mostly-ACGT input with every other byte
+    value sprinkled in, lengths around the 4- and 128-base steps and past the 4 M-base work item; and the overflow return."""
+    import ctypes as C
+    import numpy as np
+    code = np.zeros(256, np.uint8)
+    for ch, v in zip(b"ACGTURYSWKMBDHVN", [1, 2, 4, 8, 8, 5, 10, 6, 9, 12, 3, 14, 13, 11, 7, 15]):
+        code[ch] = v; code[ch | 0x20] = v
+    crumb_of = np.full(16, 255, np.uint8); crumb_of[[1, 2, 4, 8]] = [0, 1, 2, 3]
+    rnd = np.random.default_rng(10)
+    for n, frac in ((0, 0), (1, 0.5), (3, 0.5), (127, 0.1), (128, 0.1), (131, 0.1), (1000, 1.0), (9_000_003, 0.004), (9_000_003, 0.0)):
+        src = rnd.choice(np.frombuffer(b"ACGTacgtUu", np.uint8), n)
+        odd = rnd.random(n) < frac
+        src[odd] = rnd.integers(0, 256, int(odd.sum()), dtype=np.uint8)
+        sets = code[src]
+        cr = crumb_of[sets]
+        exc_want = np.sort((np.flatnonzero(cr == 255).astype(np.uint64) << np.uint64(4)) | sets[cr == 255].astype(np.uint64))
+        cr = np.where(cr == 255, 0, cr).astype(np.uint8)
+        cr = np.concatenate([cr, np.zeros((-n) % 4, np.uint8)])
+        want = cr[0::4] | (cr[1::4] << 2) | (cr[2::4] << 4) | (cr[3::4] << 6)
+        cap = len(exc_want) + 256 * (n // (4 << 20) + 2)
+        dst = np.zeros((n + 3) // 4 + 1, np.uint8)
+        exc = np.zeros(cap, np.uint64)
+        n_exc = C.c_uint64(0)
+        assert bb.lib().bb_pack_crumbs(src.ctypes.data, n, dst.ctypes.data, exc.ctypes.data, cap, C.byref(n_exc)) == 0
+        assert (dst[:(n + 3) // 4] == want).all()
+        got = exc[:n_exc.value]
+        assert n_exc.value % 256 == 0 and n_exc.value <= cap
+        got = np.sort(got[got != np.uint64(0xFFFFFFFFFFFFFFFF)])
+        assert len(got) == len(exc_want) and (got == exc_want).all()
+    # too small an exception list is reported, not silently truncated
+    src = np.frombuffer(b"N" * 4096, np.uint8).copy()
+    dst = np.zeros(1025, np.uint8); exc = np.zeros(512, np.uint64); n_exc = C.c_uint64(0)
+    assert bb.lib().bb_pack_crumbs(src.ctypes.data, 4096, dst.ctypes.data, exc.ctypes.data, 512, C.byref(n_exc)) == -3   # BB_ERR_OVERFLOW

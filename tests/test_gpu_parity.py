@@ -386,3 +386,33 @@ def test_nibble_packed_host_to_device_copy_is_lossless():
     an.close()
     assert got.tobytes() == want.tobytes() and got2.tobytes() == want.tobytes() and tag == 7
     assert 6 * (len(b) // 2) < moved < 6 * (len(b) + 8 * len(o))      # fewer bytes than six plain copies
+
+
+@pytest.mark.gpu
+def test_crumb_packed_host_to_device_copy_is_lossless():
+    """bb_opts.flags bit 2: 2 bits per base for A/C/G/T plus an exception list for every other byte (N, IUPAC codes, lower case
+    is folded, junk bytes); rows must not change.  An N-rich batch overflows the exception list and the context falls back to
+    the nibble format -- same rows again."""
+    gs = bb.GroupSet.from_kit("SQK-NBD114-96")
+    b, o, _ = synth.make_reads(gs.as_dicts(), 3000, (200, 3000), seed=43, n_frac=0.002)
+    b = b.copy()
+    rnd = np.random.default_rng(6)
+    idx = rnd.integers(0, len(b), 3000)
+    b[idx] = rnd.choice(np.frombuffer(b"acgtnRYKMSWBDHVryU-*.@x", np.uint8), len(idx))
+    want = O.demux_batch(gs.as_dicts(), b, o)
+    an = _annotator(gs, pack_h2d="crumbs")
+    got = an.annotate(b, o)
+    an.submit(b.ctypes.data, o.ctypes.data, len(o) - 1, tag=9)
+    tag, got2 = an.collect()
+    for _ in range(4):                                   # the head/tail split moves from batch to batch
+        assert an.annotate(b, o).tobytes() == want.tobytes()
+    moved = an.h2d_bytes()
+    assert got.tobytes() == want.tobytes() and got2.tobytes() == want.tobytes() and tag == 9
+    assert 6 * (len(b) // 4) < moved < 6 * (len(b) + 8 * len(o))
+    # 6 % N: too many exceptions -> nibble format from here on, still lossless
+    b2, o2, _ = synth.make_reads(gs.as_dicts(), 3000, (200, 3000), seed=44, n_frac=0.06)
+    want2 = O.demux_batch(gs.as_dicts(), b2, o2)
+    for _ in range(3):
+        assert an.annotate(b2, o2).tobytes() == want2.tobytes()
+    assert an.annotate(b, o).tobytes() == want.tobytes()
+    an.close()

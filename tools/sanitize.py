@@ -29,13 +29,18 @@ b, o, _ = synth.make_reads(gs.as_dicts(), 200, (150, 1500), seed=34)
 b = b.copy()
 idx = rnd.integers(0, len(b), len(b) // 50)
 b[idx] = rnd.choice(np.frombuffer(b"RYKMSWBDHVNacgtn-*x", np.uint8), len(idx))
-for kw in (dict(), dict(pack_h2d=True)):
+for kw in (dict(), dict(pack_h2d=True), dict(pack_h2d="crumbs")):
     an = bb.Annotator(gs, **kw)
     rows = an.annotate(b, o)
     print("custom 60-row panel", kw, len(rows), "rows")
     an.close()
 gs = bb.GroupSet.from_kit("SQK-NBD114-96")
 big, obig, _ = synth.make_reads(gs.as_dicts(), 600, (2000, 5000), seed=35, n_frac=0.02)
-an = bb.Annotator(gs, pack_h2d=True)
-print("NBD packed copy, 2 % N:", len(an.annotate(big, obig)), "rows")
+for mode in (True, "crumbs"):                            # 2 % N: the crumb format overflows its exception list and falls back
+    an = bb.Annotator(gs, pack_h2d=mode)
+    print("NBD packed copy", mode, "2 % N:", len(an.annotate(big, obig)), "rows")
+    an.close()
+clean, oclean, _ = synth.make_reads(gs.as_dicts(), 600, (2000, 5000), seed=36, n_frac=0.001)
+an = bb.Annotator(gs, pack_h2d="crumbs")
+print("NBD crumb copy, 0.1 % N:", len(an.annotate(clean, oclean)), "rows")
 an.close()
