@@ -355,11 +355,17 @@ struct Engine {
         return BB_OK;
     }
 
+    static double now_ms() {
+        static const auto t0 = std::chrono::steady_clock::now();
+        return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    }
     // host-buffer form: copy in, run, copy rows to pinned memory
     int run_host(const uint8_t* bases, const uint64_t* offsets, uint32_t n_reads, uint64_t* n_rows) {
         BB_CUDA(cudaSetDevice(device));
         *n_rows = 0;
         if (n_reads == 0) { last_reads = 0; last_rows = 0; last_kept = 0; return BB_OK; }
+        static const bool trace = std::getenv("BB_TRACE") != nullptr;        // one line of host timestamps per batch on stderr
+        double tr[6] = {now_ms(), 0, 0, 0, 0, 0}, tr_pack_ms = 0;
         const uint64_t total = offsets[n_reads] - offsets[0];
         if (offsets[0] != 0) { set_error("offsets[0] must be 0"); return BB_ERR_INVALID; }
         BB_CUDA(d_bases.ensure(((total + 15) & ~15ull) + 16));
@@ -379,11 +385,15 @@ struct Engine {
                 BB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&h_pack), want));
                 h_pack_cap = want;
             }
+            // sized for the whole batch in either format once, not for this batch's split: the split moves from batch to batch and a
+            // re-allocation (cudaFree) would stall every stream of the device
+            BB_CUDA(d_packed.ensure(static_cast<size_t>(total / 2) + (1u << 16)));
             BB_CUDA(cudaEventRecord(ev_copy[0], stream));
             if (total > split) BB_CUDA(cudaMemcpyAsync(d_bases.as<uint8_t>() + split, bases + split, total - split, cudaMemcpyHostToDevice, stream));
             BB_CUDA(cudaEventRecord(ev_copy[1], stream));
             double pack_s = 0.0;
             size_t wire = 0;                                                                   // bytes of the packed copy
+            tr[1] = now_ms();
             bool crumbs = pack_mode == 2 && split > 0;
             if (crumbs) {
                 const size_t pk = (static_cast<size_t>(split / 4) + 63) & ~size_t(63);
@@ -393,7 +403,6 @@ struct Engine {
                 if (over) { crumbs = false; pack_mode = 1; pack_rate *= 0.5; }                  // N-rich input: nibbles from here on
                 else {
                     wire = pk + n_exc * 8;
-                    BB_CUDA(d_packed.ensure(wire + 64));
                     BB_CUDA(cudaMemcpyAsync(d_packed.p, h_pack, wire, cudaMemcpyHostToDevice, stream));
                     k_unpack_crumbs<<<static_cast<unsigned>((split / 16 + 255) / 256), 256, 0, stream>>>(d_packed.as<uint8_t>(), d_bases.as<uint8_t>(), split);
                     launches++;
@@ -408,14 +417,15 @@ struct Engine {
             if (!crumbs && split) {
                 pack_s += pack_nibbles(bases, split, h_pack, kAlpha.code, pack_threads);      // the pool's own time
                 wire = static_cast<size_t>(split / 2);
-                BB_CUDA(d_packed.ensure(wire + 64));
                 BB_CUDA(cudaMemcpyAsync(d_packed.p, h_pack, wire, cudaMemcpyHostToDevice, stream));
                 k_unpack_nibbles<<<static_cast<unsigned>((split / 16 + 255) / 256), 256, 0, stream>>>(d_packed.as<uint8_t>(), d_bases.as<uint8_t>(), split);
                 launches++;
                 BB_CUDA(cudaGetLastError());
             }
+            tr[2] = now_ms(); tr_pack_ms = pack_s * 1e3;
             BB_CUDA(cudaMemcpyAsync(d_offsets.p, offsets, static_cast<size_t>(n_reads + 1) * 8, cudaMemcpyHostToDevice, stream));
             BB_CUDA(cudaEventSynchronize(ev_copy[1]));            // run() synchronises the stream a few kernels later anyway
+            tr[3] = now_ms();
             float copy_ms = 0.f;
             // P = rate of the (shared) packing pool while it works; B = the link's rate = the fastest tail copy seen lately (a copy
             // that queued behind another batch's copy looks slower than the link is)
@@ -426,6 +436,8 @@ struct Engine {
             const double saved = pack_mode == 2 ? 0.75 : 0.5;     // 1 - r
             const double x = pack_rate / (link_rate + saved * pack_rate);
             pack_frac = std::min(1.0, std::max(0.05, 0.5 * pack_frac + 0.5 * x));
+            static const char* fixed = std::getenv("BB_PACK_FRAC");                           // experiment knob: pin the split
+            if (fixed) pack_frac = std::atof(fixed);
         } else {
             BB_CUDA(cudaMemcpyAsync(d_bases.p, bases, total, cudaMemcpyHostToDevice, stream));
             BB_CUDA(cudaMemcpyAsync(d_offsets.p, offsets, static_cast<size_t>(n_reads + 1) * 8, cudaMemcpyHostToDevice, stream));
@@ -433,12 +445,17 @@ struct Engine {
         }
         int rc = run(d_bases.as<uint8_t>(), d_offsets.as<uint64_t>(), n_reads, total, stream, n_rows);
         if (rc != BB_OK) return rc;
+        tr[4] = now_ms();
         if (*n_rows) {
             rc = ensure_host_rows(*n_rows);
             if (rc != BB_OK) return rc;
             BB_CUDA(cudaMemcpyAsync(h_rows, d_rows_out.p, *n_rows * sizeof(bb_row), cudaMemcpyDeviceToHost, stream));
             BB_CUDA(cudaStreamSynchronize(stream));
         }
+        tr[5] = now_ms();
+        if (trace)
+            std::fprintf(stderr, "[bb trace] eng %p start %.2f tail-queued +%.2f packed(+wait) +%.2f tail-arrived +%.2f kernels-done +%.2f rows-home +%.2f  frac %.2f pack %.2f ms\n",
+                         static_cast<void*>(this), tr[0], tr[1] - tr[0], tr[2] - tr[0], tr[3] - tr[0], tr[4] - tr[0], tr[5] - tr[0], pack_mode ? pack_frac : 0.0, tr_pack_ms);
         return BB_OK;
     }
 };
