@@ -68,10 +68,12 @@ constexpr size_t kExcBlock = 256;                                 // entries a w
 struct ExcWriter {
     uint64_t* buf; size_t cap; std::atomic<uint64_t>* next; std::atomic<bool>* overflow;
     size_t cur = 0, end = 0;
+    bool dead = false;                                            // the list is full: the batch will be re-packed as nibbles
     void push(uint64_t v) {
+        if (dead) return;
         if (cur == end) {
             const uint64_t b = next->fetch_add(kExcBlock);
-            if (b + kExcBlock > cap) { overflow->store(true); next->fetch_sub(kExcBlock); return; }
+            if (b + kExcBlock > cap) { overflow->store(true); next->fetch_sub(kExcBlock); dead = true; return; }
             cur = static_cast<size_t>(b); end = cur + kExcBlock;
         }
         buf[cur++] = v;

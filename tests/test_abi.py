@@ -112,3 +112,11 @@ def test_pack_crumbs_matches_numpy():
     src = np.frombuffer(b"N" * 4096, np.uint8).copy()
     dst = np.zeros(1025, np.uint8); exc = np.zeros(512, np.uint64); n_exc = C.c_uint64(0)
     assert bb.lib().bb_pack_crumbs(src.ctypes.data, 4096, dst.ctypes.data, exc.ctypes.data, 512, C.byref(n_exc)) == -3   # BB_ERR_OVERFLOW
+    # ... also with every packing thread hitting the end of the list at once: nothing is written past exc_cap
+    n = 9_000_000
+    src = np.full(n, ord("N"), np.uint8)
+    dst = np.zeros(n // 4 + 8, np.uint8)
+    cap = 4096
+    exc = np.full(cap + 4096, 0x5A5A5A5A5A5A5A5A, np.uint64)
+    assert bb.lib().bb_pack_crumbs(src.ctypes.data, n, dst.ctypes.data, exc.ctypes.data, cap, C.byref(n_exc)) == -3
+    assert (exc[cap:] == np.uint64(0x5A5A5A5A5A5A5A5A)).all() and n_exc.value <= cap
