@@ -29,7 +29,7 @@ class _Group(C.Structure):
 
 class _Opts(C.Structure):
     _fields_ = [("device", C.c_int32), ("alpha", C.c_float), ("min_score", C.c_double), ("min_score_diff", C.c_double),
-                ("max_batch_bytes", C.c_uint64), ("max_batch_reads", C.c_uint32), ("flags", C.c_uint32)]
+                ("max_batch_bytes", C.c_uint64), ("max_batch_reads", C.c_uint32), ("flags", C.c_uint32), ("policy", C.c_uint32)]
 
 
 EXPORTS = ["bb_groups_from_kit", "bb_groups_from_fasta", "bb_groups_add", "bb_groups_set_flank_threshold",
@@ -202,10 +202,10 @@ class Annotator:
     """One GPU context = the reference's Demuxer (src/annotate/searcher.rs:12-29, 202-227, 430-490) in batch form."""
 
     def __init__(self, groups: GroupSet, device=0, alpha=0.4, min_score=0.2, min_score_diff=0.1, use_filter=True,
-                 pack_h2d=False):
+                 pack_h2d=False, policy=0):
         self._ctx = C.c_void_p()
         self.groups = groups
-        o = _Opts(device, alpha, min_score, min_score_diff, 0, 0, (0 if use_filter else 1) | (4 if pack_h2d == "crumbs" else 2 if pack_h2d else 0))
+        o = _Opts(device, alpha, min_score, min_score_diff, 0, 0, (0 if use_filter else 1) | (4 if pack_h2d == "crumbs" else 2 if pack_h2d else 0), policy)
         err = C.create_string_buffer(512)
         rc = lib().bb_create(C.byref(o), C.byref(self._ctx), err, 512)
         if rc != 0:

@@ -71,7 +71,7 @@ struct Alphabet {
 };
 static const Alphabet kAlpha;
 
-static double lodhi_all_match(int l) {   // reference searcher.rs:229-239 with the recurrence of orc_lodhi / k_barcode
+static double lodhi_all_match(int l) {   // reference searcher.rs:229-239 with the recurrence of the reference's forward pass
     volatile double a1 = 0.0, a2 = 0.0, s = 0.0;
     for (int p = 0; p < l; p++) { s = s + 0.5 * a2; a2 = 0.5 * (a2 + a1); a1 = 0.5 * (a1 + 1.0); }
     return s;
@@ -80,7 +80,7 @@ static double lodhi_all_match(int l) {   // reference searcher.rs:229-239 with t
 struct GroupTables {          // device copies for all groups of a ctx (shared by its engines)
     std::vector<DevGroup> host;
     DBuf d_groups, d_blob, d_code;
-    int n = 0, max_trace_cols = 0, max_nw = 1, max_region = 0, max_bar_len = 0;
+    int n = 0, max_trace_cols = 0, max_nw = 1, max_region = 0, max_bar_len = 0, max_own_rows = 0;
     void release() { d_groups.release(); d_blob.release(); d_code.release(); host.clear(); n = 0; }
 };
 
@@ -99,6 +99,7 @@ struct Engine {
     int pack_mode = 0;                   // bb_opts.flags bit 1: nibble-pack the bases on the host before the PCIe copy (1); bit 2: 2 bits per base
                                          // + an exception list (2; falls back to 1 for good when a batch has too many non-ACGT bytes)
     int pack_threads = 1;
+    int pol = 0;                         // bb_opts.policy (barcode_rows.cuh kPol*)
     uint8_t* h_pack = nullptr; size_t h_pack_cap = 0;   // pinned staging of the packed bases
     DBuf d_packed;
     uint64_t last_windows = 0;
@@ -146,6 +147,24 @@ struct Engine {
         size_t want = n + n / 2 + 1024;
         BB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&h_rows), want * sizeof(bb_row)));
         h_rows_cap = want;
+        return BB_OK;
+    }
+
+    // K3: one warp (= CTA) per flank match; the grid is as many CTAs as fit the chip at once (shared memory bounds them)
+    template <int NWT, bool PACKED, bool S2PAT>
+    int launch_barcode(const BarArgs& B, uint32_t n_hits, cudaStream_t st) {
+        const size_t smem = barcode_rows_smem<NWT, PACKED>(gt->max_bar_len, gt->max_own_rows);
+        static thread_local size_t cfg_smem = 0; static thread_local int per_sm = 0;
+        if (cfg_smem != smem) {
+            BB_CUDA(cudaFuncSetAttribute(k_barcode_rows<NWT, PACKED, S2PAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+            BB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_barcode_rows<NWT, PACKED, S2PAT>, 32, smem));
+            if (per_sm < 1) { set_error("barcode kernel does not fit: %zu bytes of shared memory per warp", smem); return BB_ERR_INVALID; }
+            cfg_smem = smem;
+        }
+        const unsigned blocks = std::min<unsigned>(n_hits, 148u * static_cast<unsigned>(per_sm));
+        k_barcode_rows<NWT, PACKED, S2PAT><<<blocks, 32, smem, st>>>(B);
+        launches++;
+        BB_CUDA(cudaGetLastError());
         return BB_OK;
     }
 
@@ -198,11 +217,12 @@ struct Engine {
                 ScanArgs A{};
                 A.bases = bases; A.offsets = offsets; A.n_reads = n_reads; A.total16 = total16;
                 A.chunk_base = d_chunk_base.as<uint32_t>(); A.tile_first = d_tile_first.as<uint32_t>(); A.tile_span = d_tile_span.as<uint64_t>();
-                A.group = g;
+                A.group = g; A.strand_xor = (pol & kPolS6RcFirst) ? 1 : 0;
                 A.entries = d_entries.as<uint64_t>(); A.n_entries = d_cnt; A.cap = entries_cap;
                 if (G.f_on && use_filter && !force_exact) {
                     // pre-filter (both strands in one 32-bit word) + exact verification of the candidate and read-end windows
-                    const uint32_t win_cap = static_cast<uint32_t>(std::min<uint64_t>(total / 48 + (1u << 20), 1u << 30));
+                    uint32_t win_cap = static_cast<uint32_t>(std::min<uint64_t>(total / 48 + (1u << 20), 1u << 30));
+                    if (const char* wc = std::getenv("BB_WIN_CAP")) win_cap = static_cast<uint32_t>(std::max(1, std::atoi(wc)));   // test knob: force the overflow fall-back
                     BB_CUDA(d_windows.ensure(static_cast<size_t>(win_cap) * 8));
                     BB_CUDA(cudaMemsetAsync(d_cnt + 6, 0, 4, st));          // [6] window count ([7] overflow flag is sticky per attempt)
                     int halo_l = 0, halo_r = 0;
@@ -213,7 +233,7 @@ struct Engine {
                     // scan + candidate runs + pre-check with the second N-free run (all on the shared text tile) -> windows
                     k_flank_filter<<<n_tiles, kScanThreads, smem, st>>>(F, G);
                     launches++;
-                    VerifyArgs V{A, d_windows.as<uint64_t>(), d_cnt + 6};
+                    VerifyArgs V{A, d_windows.as<uint64_t>(), d_cnt + 6, d_cnt + 7, win_cap};
                     if (G.nw == 1) k_flank_verify<1><<<148 * 16, 128, 0, st>>>(V, G);
                     else k_flank_verify<2><<<148 * 16, 128, 0, st>>>(V, G);
                     launches++;
@@ -268,7 +288,8 @@ struct Engine {
             BB_CUDA(cudaMemcpyAsync(d_sorted.p, uniq, static_cast<size_t>(n_entries) * 8, cudaMemcpyDeviceToDevice, st));
         }
         BB_CUDA(d_flags.ensure(n_entries));
-        k_resolve<<<(n_entries + 255) / 256, 256, 0, st>>>(d_sorted.as<uint64_t>(), n_entries, offsets, d_groups(), d_flags.as<uint8_t>());
+        BB_CUDA(cudaMemcpyAsync(d_cnt + 1, h_counters + 1, 4, cudaMemcpyHostToDevice, st));   // [1] = entries after the sort / unique
+        k_resolve<<<(n_entries + 255) / 256, 256, 0, st>>>(d_sorted.as<uint64_t>(), d_cnt + 1, offsets, d_groups(), d_flags.as<uint8_t>(), pol);
         launches++;
         BB_CUDA(cudaGetLastError());
         BB_CUDA(d_hitkeys.ensure(static_cast<size_t>(n_entries) * 8));
@@ -293,7 +314,7 @@ struct Engine {
             T.n_slots = blocks * 64;
             BB_CUDA(d_hist.ensure(static_cast<size_t>(gt->max_trace_cols + 2) * 2 * gt->max_nw * 8 * T.n_slots));
             T.bases = bases; T.offsets = offsets; T.hit_keys = d_hitkeys.as<uint64_t>(); T.n_hits = n_hits;
-            T.groups = d_groups(); T.hist = d_hist.as<uint64_t>(); T.hits = d_hits.as<Hit>();
+            T.groups = d_groups(); T.hist = d_hist.as<uint64_t>(); T.hits = d_hits.as<Hit>(); T.pol = pol;
             k_trace<<<blocks, 64, 0, st>>>(T);
             launches++;
             BB_CUDA(cudaGetLastError());
@@ -305,21 +326,17 @@ struct Engine {
         BB_CUDA(d_valid.ensure(n_hits));
         {
             BarArgs B{};
-            B.bases = bases; B.offsets = offsets; B.hits = d_hits.as<Hit>(); B.n_hits = n_hits; B.groups = d_groups();
+            B.bases = bases; B.offsets = offsets; B.hits = d_hits.as<Hit>(); B.n_hits = d_cnt + 2; B.groups = d_groups();
             B.code = gt->d_code.as<uint8_t>(); B.prm = prm; B.rows = d_rows.as<bb_row>(); B.row_valid = d_valid.as<uint8_t>();
-            B.hist_cols = gt->max_region;
-            const bool packed = gt->max_bar_len <= 48;
-            const size_t smem = barcode_smem_bytes(B.hist_cols, packed);
-            const unsigned blocks = std::min<unsigned>((n_hits + kBarWarps - 1) / kBarWarps, 148 * 32 / kBarWarps);
-            if (packed) {
-                BB_CUDA(cudaFuncSetAttribute(k_barcode<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-                k_barcode<true><<<blocks, kBarWarps * 32, smem, st>>>(B);
-            } else {
-                BB_CUDA(cudaFuncSetAttribute(k_barcode<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-                k_barcode<false><<<blocks, kBarWarps * 32, smem, st>>>(B);
+            B.sh_rows = gt->max_bar_len; B.pol = pol;
+            const bool packed = gt->max_region <= 48, s2 = (pol & kPolS2PatFirst) != 0;
+            int rc = packed ? (s2 ? launch_barcode<1, true, true>(B, n_hits, st) : launch_barcode<1, true, false>(B, n_hits, st))
+                            : (s2 ? launch_barcode<1, false, true>(B, n_hits, st) : launch_barcode<1, false, false>(B, n_hits, st));
+            if (rc != BB_OK) return rc;
+            if (gt->max_region > 64) {   // regions of more than 64 bases (large automatic k): the three-word instantiation takes those flank matches
+                rc = s2 ? launch_barcode<3, false, true>(B, n_hits, st) : launch_barcode<3, false, false>(B, n_hits, st);
+                if (rc != BB_OK) return rc;
             }
-            launches++;
-            BB_CUDA(cudaGetLastError());
         }
         BB_CUDA(cudaEventRecord(ev[4], st));
 
@@ -533,6 +550,7 @@ int bb_create(const bb_opts* opts, bb_ctx** out, char* err, size_t errlen) {
         c->eng[i].use_filter = (opts->flags & 1u) == 0;
         c->eng[i].pack_mode = (opts->flags & 4u) ? 2 : (opts->flags & 2u) ? 1 : 0;
         c->eng[i].pack_threads = bb::pack_default_threads();
+        c->eng[i].pol = static_cast<int>(opts->policy) & bb::kPolMask;
     }
     *out = c;
     return BB_OK;
@@ -561,11 +579,16 @@ int bb_set_groups(bb_ctx* c, const bb_group* groups, int32_t n_groups) {
     if (n_groups > kMaxGroups) return bad("at most 8 query groups are supported");
     if (cudaSetDevice(c->opts.device) != cudaSuccess) return bad("cudaSetDevice failed");
     const float alpha = c->opts.alpha;
-    // blob layout per group: eq[2][256][nw] u64 | bar_eq[2][nb][16] u64 | ov[m+1] i32 (padded to 8)
+    // blob layout per group: eq[2][256][nw] u64 | eq_top | filter masks | bar_off[2][nb][64] u8 | sh_off[2][64] u8 | ov[m+1] i32 (padded to 8)
+    const int pol = static_cast<int>(c->opts.policy) & kPolMask;
     std::vector<uint64_t> blob;
     std::vector<size_t> off_eq(n_groups), off_eqt(n_groups), off_feq(n_groups), off_bar(n_groups), off_ov(n_groups);
     std::vector<DevGroup> hg(n_groups);
-    int max_trace = 0, max_nw = 1, max_region = 0, max_bar_len = 0;
+    int max_trace = 0, max_nw = 1, max_region = 0, max_bar_len = 0, max_own_rows = 0;
+    auto over_cost = [&](int t) {             // policy S3: floor (default) / round-to-nearest / ceil of the f32 product
+        const float v = static_cast<float>(t) * alpha;
+        return (pol & kPolS3Round) ? static_cast<int>(std::floor(v + 0.5f)) : (pol & kPolS3Ceil) ? static_cast<int>(std::ceil(v)) : static_cast<int>(std::floor(v));
+    };
     for (int g = 0; g < n_groups; g++) {
         const bb_group& S = groups[g];
         DevGroup& D = hg[g];
@@ -575,7 +598,7 @@ int bb_set_groups(bb_ctx* c, const bb_group* groups, int32_t n_groups) {
         if (S.bar_len < 1 || S.bar_len > kMaxBarLen) return bad("padded barcode length must be 1..64");
         if (S.n_barcodes < 1 || S.n_barcodes > 32 * kMaxBarRounds) return bad("1..512 barcodes per group");
         if (S.k_flank < 0 || S.k_flank > 120) return bad("flank threshold must be 0..120");
-        const int ov_m = static_cast<int>(std::floor(static_cast<float>(m) * alpha));
+        const int ov_m = over_cost(m);
         if (S.k_flank >= ov_m - 1) return bad("flank threshold too large for the overhang cost: need k < floor(alpha*len)-1");
         if (S.bar1 - S.bar0 + 1 + S.k_flank + 2 * kPadding > kRegionMax) return bad("barcode region (mask + k + 20) exceeds 160 characters");
         if (S.bar0 < 0 || S.bar1 < S.bar0 || S.bar1 >= m || S.pad0 < 0 || S.pad0 > S.bar0) return bad("inconsistent bar/pad regions");
@@ -595,7 +618,7 @@ int bb_set_groups(bb_ctx* c, const bb_group* groups, int32_t n_groups) {
         std::vector<uint8_t> pc(m);
         for (int i = 0; i < m; i++) pc[i] = kAlpha.code[static_cast<uint8_t>(S.flank[i])];
         std::vector<int> ov(m + 1);
-        for (int t = 0; t <= m; t++) ov[t] = static_cast<int>(std::floor(static_cast<float>(t) * alpha));
+        for (int t = 0; t <= m; t++) ov[t] = over_cost(t);
         for (int i = 0; i < m; i++) {
             D.pv_plain[i >> 6] |= 1ull << (i & 63);
             if (ov[i + 1] - ov[i]) D.pv_over[i >> 6] |= 1ull << (i & 63);
@@ -672,18 +695,33 @@ int bb_set_groups(bb_ctx* c, const bb_group* groups, int32_t n_groups) {
                 feq[ch] = v;
             }
         }
+        // barcode patterns as one byte per row = 8 * (4-bit IUPAC set): forward, and explicitly reverse-complemented (barcodes.rs:85-90);
+        // + per strand the leading rows all barcodes share (computed once per flank match by k_barcode_rows)
         off_bar[g] = blob.size();
-        blob.resize(blob.size() + static_cast<size_t>(2) * S.n_barcodes * 16, 0);
-        for (int b = 0; b < S.n_barcodes; b++)
-            for (int i = 0; i < S.bar_len; i++) {
-                const uint8_t ch = static_cast<uint8_t>(S.barcodes[static_cast<size_t>(b) * S.bar_len + i]);
-                const uint8_t cf = kAlpha.code[ch], cr = kAlpha.code[kAlpha.rcchar[ch]];
-                const int ir = S.bar_len - 1 - i;
-                for (int code = 0; code < 16; code++) {
-                    if (cf & code) blob[off_bar[g] + (static_cast<size_t>(0) * S.n_barcodes + b) * 16 + code] |= 1ull << i;
-                    if (cr & code) blob[off_bar[g] + (static_cast<size_t>(1) * S.n_barcodes + b) * 16 + code] |= 1ull << ir;
+        blob.resize(blob.size() + (static_cast<size_t>(2) * S.n_barcodes * 64 + 2 * 64) / 8, 0);
+        {
+            uint8_t* off = reinterpret_cast<uint8_t*>(blob.data() + off_bar[g]);
+            uint8_t* shoff = off + static_cast<size_t>(2) * S.n_barcodes * 64;
+            for (int b = 0; b < S.n_barcodes; b++)
+                for (int i = 0; i < S.bar_len; i++) {
+                    const uint8_t ch = static_cast<uint8_t>(S.barcodes[static_cast<size_t>(b) * S.bar_len + i]);
+                    off[(static_cast<size_t>(0) * S.n_barcodes + b) * 64 + i] = static_cast<uint8_t>(kAlpha.code[ch] << 3);
+                    off[(static_cast<size_t>(1) * S.n_barcodes + b) * 64 + (S.bar_len - 1 - i)] = static_cast<uint8_t>(kAlpha.code[kAlpha.rcchar[ch]] << 3);
                 }
+            for (int st = 0; st < 2; st++) {
+                const uint8_t* first = off + static_cast<size_t>(st) * S.n_barcodes * 64;
+                int P = S.bar_len;
+                for (int b = 1; b < S.n_barcodes; b++) {
+                    const uint8_t* cur = first + static_cast<size_t>(b) * 64;
+                    int q = 0;
+                    while (q < P && cur[q] == first[q]) q++;
+                    P = q;
+                }
+                D.sh_p[st] = P;
+                std::memcpy(shoff + 64 * st, first, 64);
+                max_own_rows = std::max(max_own_rows, S.bar_len - P);
             }
+        }
         off_ov[g] = blob.size();
         blob.resize(blob.size() + (m + 2) / 2 + 1, 0);
         std::memcpy(reinterpret_cast<int*>(blob.data() + off_ov[g]), ov.data(), sizeof(int) * (m + 1));
@@ -699,14 +737,16 @@ int bb_set_groups(bb_ctx* c, const bb_group* groups, int32_t n_groups) {
         hg[g].eq_top = base + off_eqt[g];
         hg[g].f_eq = reinterpret_cast<const uint32_t*>(base + off_feq[g]);
         hg[g].f_seq = hg[g].f_eq + 256;
-        hg[g].bar_eq = base + off_bar[g];
+        hg[g].bar_off = reinterpret_cast<const uint8_t*>(base + off_bar[g]);
+        hg[g].sh_off = hg[g].bar_off + static_cast<size_t>(2) * groups[g].n_barcodes * 64;
+        hg[g].pol = pol;
         hg[g].ov = reinterpret_cast<const int*>(base + off_ov[g]);
     }
     cudaError_t e1 = cudaMemcpy(T.d_blob.p, blob.data(), blob.size() * 8, cudaMemcpyHostToDevice);
     cudaError_t e2 = cudaMemcpy(T.d_groups.p, hg.data(), sizeof(DevGroup) * n_groups, cudaMemcpyHostToDevice);
     cudaError_t e3 = cudaMemcpy(T.d_code.p, kAlpha.code, 256, cudaMemcpyHostToDevice);
     if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) return (ctx_error(c, "cudaMemcpy of the pattern tables failed"), BB_ERR_CUDA);
-    T.host = hg; T.n = n_groups; T.max_trace_cols = max_trace; T.max_nw = max_nw; T.max_region = max_region; T.max_bar_len = max_bar_len;
+    T.host = hg; T.n = n_groups; T.max_trace_cols = max_trace; T.max_nw = max_nw; T.max_region = max_region; T.max_bar_len = max_bar_len; T.max_own_rows = max_own_rows;
     return BB_OK;
 }
 

@@ -12,8 +12,9 @@
 //  K2a resolve      sassy's local-minimum reporting rule applied to the sorted entries.
 //  K2b trace        traceback of every reported flank match -> text_start and the barcode text region
 //                   (reference cigar_parse.rs:71-82, searcher.rs:442-456).
-//  K3  barcode      reference searcher.rs:267-426: all barcodes of the group against the region (one warp per flank
-//                   match, barcodes across lanes), fallback pass, traceback, Lodhi score, thresholds, row assembly.
+//  K3  barcode_rows reference searcher.rs:267-426: all barcodes of the group against the region (one warp per flank
+//                   match, barcodes across lanes, the DP rows laid along the text: barcode_rows.cuh), fallback pass,
+//                   traceback, Lodhi score, thresholds, row assembly.
 //  K4  collapse     reference interval.rs:4-79, one thread per read.
 //
 // The arithmetic mirrors the CPU oracle's policies S1-S7 bit for bit (the oracle is test infrastructure: nothing here
@@ -26,7 +27,7 @@
 
 #include "../../include/barbell_b200.h"
 #include "device_types.cuh"
-#include "barcode_lane.cuh"
+#include "barcode_rows.cuh"
 
 namespace bb {
 
@@ -146,6 +147,7 @@ struct ScanArgs {
     uint32_t n_reads;
     uint64_t total16;            // readable bytes of `bases` (total rounded up to 16)
     int group;
+    int strand_xor;              // policy S6: 1 = the key's strand bit is inverted so that Rc matches sort before forward ones
     uint64_t* entries;
     uint32_t* n_entries;
     uint32_t cap;
@@ -230,7 +232,7 @@ __device__ __forceinline__ int col_step_top(Col<NW>& c, const uint64_t* __restri
 
 __device__ __forceinline__ void scan_emit(const ScanArgs& A, uint32_t r, int strand, uint32_t pos, int cost) {
     const uint32_t idx = atomicAdd(A.n_entries, 1u);
-    if (idx < A.cap) A.entries[idx] = make_key(r, A.group, strand, pos, cost);
+    if (idx < A.cap) A.entries[idx] = make_key(r, A.group, strand ^ A.strand_xor, pos, cost);
 }
 
 template <int NW>
@@ -647,6 +649,8 @@ struct VerifyArgs {
     ScanArgs S;
     const uint64_t* windows;
     const uint32_t* n_windows;
+    const uint32_t* overflow;    // set by the filter when a window queue overflowed: the queue has holes, the batch is re-run exactly
+    uint32_t win_cap;
 };
 
 template <int NW>
@@ -694,8 +698,11 @@ __global__ void __launch_bounds__(128) k_flank_verify(const VerifyArgs V, const 
     for (int i = threadIdx.x; i < 2 * 256 * NW; i += blockDim.x) s_eq[i] = __ldg(G.eq_top + i);
     __syncthreads();
     const ScanArgs& A = V.S;
+    // an overflowed queue holds unwritten slots (a CTA that could not reserve returns without writing): nothing of it may be
+    // decoded, the host re-runs the batch with the exact scan
+    if (__ldg(V.overflow)) return;
     const uint64_t n_end = 4ull * A.n_reads;
-    const uint64_t total = n_end + __ldg(V.n_windows);
+    const uint64_t total = n_end + min(__ldg(V.n_windows), V.win_cap);
     const int span = G.m + G.k;
     for (uint64_t it = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; it < total; it += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
         if (it < n_end) {
@@ -723,34 +730,46 @@ __global__ void __launch_bounds__(128) k_flank_verify(const VerifyArgs V, const 
 // ---------------------------------------------------------------------------------------------------------------
 // K2a: local-minimum rule on the sorted entries (oracle policy S1)
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void k_resolve(const uint64_t* __restrict__ keys, uint32_t n, const uint64_t* __restrict__ offsets,
-                          const DevGroup* __restrict__ groups, uint8_t* __restrict__ flags) {
-    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= n) return;
-    const uint64_t key = keys[e];
-    const uint64_t id = key >> kKeyPosShift;
-    const int cost = static_cast<int>(key & 0xff);
-    const uint32_t r = static_cast<uint32_t>(key >> kKeyReadShift);
-    const int g = static_cast<int>((key >> kKeyGroupShift) & 7);
-    const uint32_t pos = static_cast<uint32_t>((key >> kKeyPosShift) & ((1u << 28) - 1));
-    const uint32_t len = static_cast<uint32_t>(offsets[r + 1] - offsets[r]);
-    const uint32_t last = len + groups[g].m;   // the flank searcher always has the overhang extension
-    // does the cost go up after this position?
-    bool up = true;
-    if (pos == last) up = true;
-    else if (e + 1 < n && (keys[e + 1] >> kKeyPosShift) == id + 1) up = static_cast<int>(keys[e + 1] & 0xff) > cost;
-    // was the last strict change before this position a decrease?  (missing neighbours are > k >= cost)
-    bool dec = true;
-    uint64_t cur = id;
-    for (uint32_t q = e; q > 0; q--) {
-        const uint64_t pk = keys[q - 1];
-        if ((pk >> kKeyPosShift) != cur - 1) break;
-        const int pc = static_cast<int>(pk & 0xff);
-        if (pc > cost) break;
-        if (pc < cost) { dec = false; break; }
-        cur--;
+__global__ void k_resolve(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ n_ptr, const uint64_t* __restrict__ offsets,
+                          const DevGroup* __restrict__ groups, uint8_t* __restrict__ flags, int pol) {
+    const uint32_t n = __ldg(n_ptr);
+    for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+        const uint64_t key = keys[e];
+        const uint64_t id = key >> kKeyPosShift;
+        const int cost = static_cast<int>(key & 0xff);
+        const uint32_t r = static_cast<uint32_t>(key >> kKeyReadShift);
+        const int g = static_cast<int>((key >> kKeyGroupShift) & 7);
+        const uint32_t pos = static_cast<uint32_t>((key >> kKeyPosShift) & ((1u << 28) - 1));
+        const uint32_t len = static_cast<uint32_t>(offsets[r + 1] - offsets[r]);
+        const uint32_t last = len + groups[g].m;   // the flank searcher always has the overhang extension
+        // A plateau of equal costs is a reported minimum when the last strict change before it was a decrease (or there is none)
+        // and the first strict change after it is an increase (or the row ends); missing neighbours are > k >= cost.
+        // walk left over the plateau: `dec` = it is entered by a decrease; `first` = this entry is its left end
+        bool dec = true, first = true;
+        uint64_t cur = id;
+        for (uint32_t q = e; q > 0; q--) {
+            const uint64_t pk = keys[q - 1];
+            if ((pk >> kKeyPosShift) != cur - 1) break;
+            const int pc = static_cast<int>(pk & 0xff);
+            if (pc > cost) break;
+            if (pc < cost) { dec = false; break; }
+            cur--; first = false;
+        }
+        // walk right: `up` = it is left by an increase; `lastp` = this entry is its right end
+        bool up = true, lastp = true;
+        cur = id;
+        uint32_t p = pos;
+        for (uint32_t q = e; p != last && q + 1 < n; q++) {
+            const uint64_t nk = keys[q + 1];
+            if ((nk >> kKeyPosShift) != cur + 1) break;
+            const int nc = static_cast<int>(nk & 0xff);
+            if (nc > cost) break;
+            if (nc < cost) { up = false; break; }
+            cur++; p++; lastp = false;
+            if (!(pol & kPolS1Left)) break;                    // right-end reporting only needs the next entry
+        }
+        flags[e] = (up && dec && ((pol & kPolS1Left) ? first : lastp)) ? 1 : 0;
     }
-    flags[e] = (up && dec) ? 1 : 0;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -765,6 +784,7 @@ struct TraceArgs {
     uint64_t* hist;          // [col][2*NW][slot]
     uint32_t n_slots;
     Hit* hits;
+    int pol;                 // kPolS2PatFirst, kPolS6RcFirst
 };
 
 template <int NW>
@@ -772,7 +792,7 @@ __device__ void trace_one(const TraceArgs& A, const DevGroup& G, uint32_t h, uin
     const uint64_t key = A.hit_keys[h];
     const uint32_t r = static_cast<uint32_t>(key >> kKeyReadShift);
     const int g = static_cast<int>((key >> kKeyGroupShift) & 7);
-    const int strand = static_cast<int>((key >> kKeyStrandShift) & 1);
+    const int strand = static_cast<int>((key >> kKeyStrandShift) & 1) ^ ((A.pol & kPolS6RcFirst) ? 1 : 0);
     const int pos = static_cast<int>((key >> kKeyPosShift) & ((1u << 28) - 1));
     const int cost = static_cast<int>(key & 0xff);
     const uint64_t rs0 = A.offsets[r];
@@ -818,8 +838,11 @@ __device__ void trace_one(const TraceArgs& A, const DevGroup& G, uint32_t h, uin
             const bool match = (__ldg(eq + ch * NW + ((i - 1) >> 6)) >> ((i - 1) & 63)) & 1ull;
             if (match && d == gcur) { di = 1; dj = 1; }
             else if (d + 1 == gcur) { di = 1; dj = 1; }
-            else if (cell(i, j - 1) + 1 == gcur) { di = 0; dj = 1; }
-            else { di = 1; dj = 0; }
+            else if (!(A.pol & kPolS2PatFirst)) {
+                if (cell(i, j - 1) + 1 == gcur) { di = 0; dj = 1; } else { di = 1; dj = 0; }
+            } else {
+                if (cell(i - 1, j) + 1 == gcur) { di = 1; dj = 0; } else { di = 0; dj = 1; }
+            }
         }
         i -= di; j -= dj;
         if (i >= G.bar0 && i <= G.bar1) {                     // pre-op position (i, j) of this op
@@ -863,18 +886,17 @@ struct BarArgs {
     const uint8_t* bases;
     const uint64_t* offsets;
     const Hit* hits;
-    uint32_t n_hits;
+    const uint32_t* n_hits;   // device-side count of flank matches
     const DevGroup* groups;
     const uint8_t* code;      // [256] byte -> 4-bit IUPAC set
     Params prm;
     bb_row* rows;             // one slot per hit
     uint8_t* row_valid;
-    int hist_cols;            // history columns per lane in shared memory (longest region)
+    int sh_rows;              // shared-memory rows reserved for the records of the shared leading rows / the per-row traceback records
+    int pol;                  // kPolS1Left | kPolS5Last (S2 is a template parameter)
 };
 
-constexpr int kBarWarps = 1;     // (2 warps per block would save the 1 KB block reserve, but measured slower: 3.38 vs 3.20 ms)
 constexpr int kMaxBarRounds = 16;   // up to 512 barcodes per group
-constexpr int kCodesPad = (kRegionMax + 15) & ~15;
 
 __device__ __forceinline__ int64_t rel_dist_to_end(int64_t pos, int64_t read_len) {   // searcher.rs:183-199
     if (pos < 0) return 1;
@@ -902,51 +924,73 @@ struct TopTwo {
     int ok = 0, pi = 0, ei = 0, pj = 0, ej = 0, cost = 0, ts = 0, te = 0;   // map_pat_to_text_with_cost of the top
 };
 
-// Shared-memory size of k_barcode for regions of up to `cols` bases: the lane's 5 match masks, the (diag, stop) bit-vectors of
-// HALF of the columns (barcode_lane() keeps the upper half, then the lower half resident; 12 bytes per column and lane when
-// the pattern has <= 48 rows: rows live in bits [16, 64), so the two low halves share one 32-bit word; 16 bytes otherwise),
-// one traceback record per column, and the region's bases.
-__host__ __device__ inline size_t barcode_hist_bytes(int cols, bool packed) { return static_cast<size_t>((cols + 1) / 2) * 32 * (packed ? 12 : 16); }
-__host__ __device__ inline size_t barcode_warp_bytes(int cols, bool packed) {
-    return kEqSlots * 32 * sizeof(uint64_t) + barcode_hist_bytes(cols, packed) + ((static_cast<size_t>(cols) * 32 + 15) & ~static_cast<size_t>(15)) + kCodesPad;
+// Shared memory of one k_barcode_rows CTA (= one warp): the 16 text masks, the records of the shared leading rows, the lanes'
+// pattern codes, one traceback record byte per row and lane, and the lanes' own-row records.
+template <int NWT, bool PACKED>
+__host__ __device__ inline size_t barcode_rows_smem(int sh_rows, int own_rows) {
+    return 1024 + 16 * NWT * 8 + static_cast<size_t>(sh_rows) * 3 * NWT * 8 + 64 + 32 * kOffStride + static_cast<size_t>(sh_rows) * 32 +
+           row_hist_bytes<NWT, PACKED>(own_rows) + 16;
 }
-__host__ __device__ inline size_t barcode_smem_bytes(int cols, bool packed) { return kBarWarps * barcode_warp_bytes(cols, packed); }
 
-// One warp per flank match; lane = barcode pattern (rounds of 32); the per-pattern work is barcode_lane()
-// (barcode_lane.cuh: forward pass with column history, column-per-iteration traceback, Lodhi score).
+// One warp (= one CTA) per flank match; lane = barcode pattern (rounds of 32).  The region's text masks and the pattern rows
+// all barcodes share are computed once per flank match, the per-pattern work is rows_lane() (barcode_rows.cuh: forward pass
+// over the pattern's own rows with one record per row, row-per-iteration traceback, Lodhi score).
 // The per-pattern best minimum is the same with k = floor(0.4*len) and with the fallback k = len (the first
 // lowest-cost minimum); the threshold only decides WHICH patterns are candidates, so both candidate sets are reduced
 // side by side and the fallback rule (searcher.rs:303-306) picks one at the end.
-template <bool PACKED>
-__global__ void __launch_bounds__(kBarWarps * 32, 20 / kBarWarps) k_barcode(const BarArgs A) {
+// NWT = 1 takes the flank matches whose region has <= 64 bases (all of them for the shipped kits), NWT = 3 the others.
+template <int NWT, bool PACKED, bool S2PAT>
+__global__ void __launch_bounds__(32) k_barcode_rows(const BarArgs A) {
     extern __shared__ __align__(16) unsigned char bar_smem[];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const size_t ncol = static_cast<size_t>(A.hist_cols);
-    unsigned char* wbase = bar_smem + static_cast<size_t>(wib) * barcode_warp_bytes(A.hist_cols, PACKED);
-    uint64_t* eqs_s = reinterpret_cast<uint64_t*>(wbase);                    // [5 base sets][32 lanes]
-    const ColHist<PACKED> hist{reinterpret_cast<uint32_t*>(eqs_s + kEqSlots * 32), lane};
-    uint8_t* rec = wbase + kEqSlots * 32 * sizeof(uint64_t) + barcode_hist_bytes(A.hist_cols, PACKED);   // [column][lane]
-    uint8_t* txt = rec + ((ncol * 32 + 15) & ~static_cast<size_t>(15));                                    // region bases (region_byte)
-    const uint32_t n_warps = gridDim.x * kBarWarps;
-    for (uint32_t h = blockIdx.x * kBarWarps + wib; h < A.n_hits; h += n_warps) {
+    const int lane = threadIdx.x;
+    uint32_t* lut = reinterpret_cast<uint32_t*>(bar_smem);                                 // [256] bottom-row scan table
+    uint64_t* tm = reinterpret_cast<uint64_t*>(bar_smem + 1024);                           // [16][NWT]
+    uint64_t* sh = tm + 16 * NWT;                                                          // [sh_rows][3][NWT]
+    uint8_t* s_shoff = reinterpret_cast<uint8_t*>(sh + static_cast<size_t>(A.sh_rows) * 3 * NWT);   // [64] codes of the shared rows
+    uint8_t* s_off = s_shoff + 64;                                                         // [32 lanes][kOffStride]
+    uint8_t* rec = s_off + 32 * kOffStride;                                                // [sh_rows][32]
+    const RowHist<NWT, PACKED> hist{reinterpret_cast<uint32_t*>(rec + ((static_cast<size_t>(A.sh_rows) * 32 + 15) & ~static_cast<size_t>(15))), lane};
+    for (int q = lane; q < 256; q += 32) lut[q] = scan_lut_entry(q);
+    const uint32_t n_hits = __ldg(A.n_hits);
+    for (uint32_t h = blockIdx.x; h < n_hits; h += gridDim.x) {
         const Hit H = A.hits[h];
-        if (!H.has_region) { if (lane == 0) A.row_valid[h] = 0; continue; }   // searcher.rs:445-449
+        if (!H.has_region) { if (NWT == 1 && lane == 0) A.row_valid[h] = 0; continue; }    // searcher.rs:445-449
+        const int rn = H.re - H.rs;
+        if (NWT == 1 ? rn > 64 : rn <= 64) continue;            // the other instantiation's flank matches
         const DevGroup& G = A.groups[H.group];
         const uint64_t rs0 = A.offsets[H.read];
         const int n = static_cast<int>(A.offsets[H.read + 1] - rs0);
-        const int rn = H.re - H.rs;
         const int L = G.bar_len, nb = G.n_barcodes, k1 = G.k_bar;
-        const int sh = 64 - L;                                  // patterns are top-aligned like the flank scan
+        const int P = H.strand == BB_FWD ? G.sh_p[0] : G.sh_p[1];
+        // ---- text masks: B[a] = region bases whose set holds base a; tm[c] = bases that match a pattern character with set c ----
         __syncwarp();
-        bool plain_l = true;                                     // every base of the region is A, C, G, T or N (the usual case)
-        for (int q = lane; q < rn; q += 32) {
-            const uint8_t v = region_byte(__ldg(A.code + A.bases[rs0 + H.rs + q]));
-            txt[q] = v;
-            plain_l = plain_l && (v >> 4) < kEqOther;
+        {
+            const uint8_t* tp = A.bases + rs0 + H.rs;
+            uint64_t B[4][NWT];
+#pragma unroll
+            for (int w = 0; w < NWT; w++) {
+                const int q0 = 64 * w + lane, q1 = q0 + 32;
+                const uint32_t c0 = q0 < rn ? __ldg(A.code + tp[q0]) : 0u, c1 = q1 < rn ? __ldg(A.code + tp[q1]) : 0u;
+#pragma unroll
+                for (int a = 0; a < 4; a++)
+                    B[a][w] = __ballot_sync(0xffffffffu, (c0 >> a) & 1u) | (static_cast<uint64_t>(__ballot_sync(0xffffffffu, (c1 >> a) & 1u)) << 32);
+            }
+            if (lane < 16) {
+#pragma unroll
+                for (int w = 0; w < NWT; w++) {
+                    uint64_t v = 0;
+#pragma unroll
+                    for (int a = 0; a < 4; a++) v |= ((lane >> a) & 1) ? B[a][w] : 0ull;
+                    tm[lane * NWT + w] = v;
+                }
+                reinterpret_cast<uint32_t*>(s_shoff)[lane] = __ldg(reinterpret_cast<const uint32_t*>(G.sh_off + 64 * H.strand) + lane);
+            }
         }
-        const bool plain = __all_sync(0xffffffffu, plain_l);
-        const uint64_t* eqs = G.bar_eq + static_cast<size_t>(H.strand) * nb * 16;
-        const uint64_t wild = sh ? ((1ull << sh) - 1ull) : 0ull;
+        __syncwarp();
+        // ---- the leading rows all barcodes of this strand share: once per flank match ----
+        uint64_t ph0[NWT], mh0[NWT];
+        rows_prefix<NWT, S2PAT>(tm, s_shoff, P, lane == 0, sh, ph0, mh0);
+        const uint8_t* offs_g = G.bar_off + static_cast<size_t>(H.strand) * nb * 64;
 
         TopTwo all, strict;          // candidates under the fallback k = len / under k1
         int matched = 0;
@@ -956,15 +1000,17 @@ __global__ void __launch_bounds__(kBarWarps * 32, 20 / kBarWarps) k_barcode(cons
             bool has1 = false;
             __syncwarp();
             if (b < nb) {
+                const uint4* src = reinterpret_cast<const uint4*>(offs_g + static_cast<size_t>(b) * 64);
+                uint32_t* dst = reinterpret_cast<uint32_t*>(s_off + lane * kOffStride);
 #pragma unroll
-                for (int sl = 0; sl < kEqSlots; sl++)       // base sets {A}, {C}, {G}, {T}, {ACGT} = codes 1, 2, 4, 8, 15
-                    eqs_s[sl * 32 + lane] = (__ldg(eqs + static_cast<size_t>(b) * 16 + (sl < 4 ? (1 << sl) : 15)) << sh) | wild;
+                for (int q = 0; q < 4; q++) {
+                    if (16 * q < L) { const uint4 v = __ldg(src + q); dst[4 * q] = v.x; dst[4 * q + 1] = v.y; dst[4 * q + 2] = v.z; dst[4 * q + 3] = v.w; }
+                }
             }
             __syncwarp();
             if (b < nb) {
                 LaneAlign R;
-                if (plain) barcode_lane<PACKED, true>(eqs_s + lane, txt, rn, L, G.pbar0, G.pbar1, hist, rec + lane, R);
-                else barcode_lane<PACKED, false>(eqs_s + lane, txt, rn, L, G.pbar0, G.pbar1, hist, rec + lane, R);
+                rows_lane<NWT, PACKED, S2PAT>(tm, s_off + lane * kOffStride, rn, L, P, ph0, mh0, sh, hist, rec + lane, lut, G.pbar0, G.pbar1, A.pol, R);
                 has1 = R.cbest <= k1;
                 const double sn = G.perfect > 0.0 ? R.s / G.perfect : 0.0;
 #pragma unroll

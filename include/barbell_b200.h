@@ -17,7 +17,7 @@
 extern "C" {
 #endif
 
-#define BB_ABI_VERSION 1
+#define BB_ABI_VERSION 2
 
 typedef enum {
     BB_OK = 0,
@@ -77,7 +77,19 @@ typedef struct {
                                    as it is; the split adapts to the measured pack and link rates (bb_annotate / bb_submit);
                                    bit 2: like bit 1 with the denser wire format: 2 bits per base for A/C/G/T plus an exception list for every
                                    other byte (a batch with more than ~1.5 % such bytes switches the context to the nibble format) */
+    uint32_t policy;            /* BB_POL_* bits: choices of sassy 0.2.1 (Cargo.lock:1060-1063; called at src/annotate/searcher.rs:282-288, 438)
+                                   that the reference's own tests (src/annotate/cigar_parse.rs:104-176) do not pin.  0 = the documented defaults;
+                                   a maintainer who can run upstream flips them here -- no kernel changes */
 } bb_opts;
+
+enum {
+    BB_POL_S1_LEFT = 1,        /* `search` reports the LEFT end of a bottom-row cost plateau (default: the right end) */
+    BB_POL_S2_PAT_FIRST = 2,   /* traceback prefers a pattern-only step [Del] over a text-only step [Ins] (default: text-only first) */
+    BB_POL_S5_LAST = 4,        /* best match per barcode pattern = the LAST of equal lowest-cost minima (default: the first, searcher.rs:294-300) */
+    BB_POL_S6_RC_FIRST = 8,    /* `search` lists reverse-complement matches before forward ones (default: forward first) */
+    BB_POL_S3_ROUND = 16,      /* overhang cost of t rows = round-to-nearest(t*alpha) (default: floor) */
+    BB_POL_S3_CEIL = 32        /* ... = ceil(t*alpha) */
+};
 
 typedef struct bb_ctx bb_ctx;
 typedef struct bb_groupset bb_groupset;

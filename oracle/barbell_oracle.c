@@ -23,6 +23,9 @@
  *                   reversed frame).
  *  S7 alphabet    : IUPAC letters, case-insensitive, U=T, X and every non-letter byte match nothing.
  *  Lodhi          : S_3(C, 1/2) by the forward recurrence in orc_lodhi() in IEEE f64, positions advance on every op.
+ * Every one of S1, S2, S3, S5, S6 can be FLIPPED at run time (orc_policy.flags, ORC_POL_* in barbell_oracle.h); the product
+ * has the same switches (bb_opts.policy), and the GPU == oracle suite runs under every setting, so a maintainer with the
+ * upstream crates can move both to whatever sassy 0.2.1 really does without touching a kernel (tools/ref_parity.sh --policy).
  */
 #include "barbell_oracle.h"
 #include <math.h>
@@ -34,7 +37,7 @@
 #define NW_MAX 4          /* patterns up to 256 characters */
 #define PADDING 10        /* src/lib.rs:10 */
 
-static orc_policy g_policy = {1};
+static orc_policy g_policy = {1, 0};
 void orc_set_policy(const orc_policy *p) { g_policy = *p; }
 int orc_max_threads(void) { long n = sysconf(_SC_NPROCESSORS_ONLN); return n > 0 ? (int)n : 1; }
 
@@ -76,7 +79,10 @@ static void pat_build(pat_t *P, const uint8_t *pc, int m, float alpha) {
             if (pc[i] & c) P->eq[c][i >> 6] |= 1ull << (i & 63);
     for (int i = 0; i < m; i++) P->pv_plain[i >> 6] |= 1ull << (i & 63);
     P->has_over = alpha >= 0.0f;
-    for (int t = 0; t <= m; t++) P->ov[t] = P->has_over ? (int)floorf((float)t * alpha) : t;
+    for (int t = 0; t <= m; t++) {            /* S3: floor (default) / round-to-nearest / ceil of the f32 product */
+        float v = (float)t * alpha;
+        P->ov[t] = !P->has_over ? t : (g_policy.flags & ORC_POL_S3_ROUND) ? (int)floorf(v + 0.5f) : (g_policy.flags & ORC_POL_S3_CEIL) ? (int)ceilf(v) : (int)floorf(v);
+    }
     for (int i = 0; i < m; i++)
         if (P->ov[i + 1] - P->ov[i]) P->pv_over[i >> 6] |= 1ull << (i & 63);
 }
@@ -118,14 +124,16 @@ static void fvec_push(fvec *f, fmatch m) {
 
 /* S1: walk the extended cost row and collect reported end positions */
 static int local_minima(const int32_t *c, int P, int k, int *pos) {
-    int n = 0, dec = 1, prev = c[0];
+    int n = 0, dec = 1, prev = c[0], pstart = 0;
+    const int left = g_policy.flags & ORC_POL_S1_LEFT;      /* report the left instead of the right end of the plateau */
     for (int p = 1; p < P; p++) {
         int cur = c[p];
-        if (cur > prev && dec && prev <= k) pos[n++] = p - 1;
+        if (cur > prev && dec && prev <= k) pos[n++] = left ? pstart : p - 1;
         if (cur < prev) dec = 1; else if (cur > prev) dec = 0;
+        if (cur != prev) pstart = p;
         prev = cur;
     }
-    if (dec && prev <= k) pos[n++] = P - 1;
+    if (dec && prev <= k) pos[n++] = left ? pstart : P - 1;
     return n;
 }
 
@@ -157,8 +165,13 @@ static void traceback(const cells_t *C, const uint8_t *pc, const uint8_t *tc, in
         int d = cell(C, i - 1, j - 1);
         if ((pc[i - 1] & tc[j - 1]) && d == g) { rev[n++] = ORC_OP_MATCH; i--; j--; }
         else if (d + 1 == g) { rev[n++] = ORC_OP_SUB; i--; j--; }
-        else if (cell(C, i, j - 1) + 1 == g) { rev[n++] = ORC_OP_TEXT; j--; }
-        else { rev[n++] = ORC_OP_PAT; i--; }
+        else if (!(g_policy.flags & ORC_POL_S2_PAT_FIRST)) {
+            if (cell(C, i, j - 1) + 1 == g) { rev[n++] = ORC_OP_TEXT; j--; }
+            else { rev[n++] = ORC_OP_PAT; i--; }
+        } else {
+            if (cell(C, i - 1, j) + 1 == g) { rev[n++] = ORC_OP_PAT; i--; }
+            else { rev[n++] = ORC_OP_TEXT; j--; }
+        }
     }
     fm->ps = i; fm->ts = j; fm->n_ops = n;
     fm->ops = (uint8_t *)malloc((size_t)n + 1);
@@ -277,11 +290,12 @@ static void push_frame_matches(fvec *fv, int n, int strand, orc_match **out, int
 static int search_codes(const pattern_t *pt, const uint8_t *tc, const uint8_t *trc, int n, int k, orc_match **out) {
     int cnt = 0, cap = 0; *out = NULL;
     fvec fv = {0};
-    search_frame(pt, tc, n, k, &fv);
-    push_frame_matches(&fv, n, ORC_FWD, out, &cnt, &cap);
-    if (trc) {
-        search_frame(pt, trc, n, k, &fv);
-        push_frame_matches(&fv, n, ORC_RC, out, &cnt, &cap);
+    const int rc_first = (g_policy.flags & ORC_POL_S6_RC_FIRST) && trc;    /* S6 */
+    for (int pass = 0; pass < 2; pass++) {
+        const int strand = pass == (rc_first ? 1 : 0) ? ORC_FWD : ORC_RC;
+        if (strand == ORC_RC && !trc) continue;
+        search_frame(pt, strand == ORC_FWD ? tc : trc, n, k, &fv);
+        push_frame_matches(&fv, n, strand, out, &cnt, &cap);
     }
     return cnt;
 }
@@ -525,7 +539,8 @@ static void barcode_stage(const demux_state *S, const orc_group *G, int g, const
             /* search_encoded_patterns at this k, keep the lowest-cost match, first seen wins (searcher.rs:294-300) */
             const int32_t *cb = c + (size_t)b * (rn + L + 2);
             int np = local_minima(cb, rn + 1, k, pos), bi = -1;
-            for (int q = 0; q < np; q++) if (bi < 0 || cb[pos[q]] < cb[pos[bi]]) bi = q;
+            for (int q = 0; q < np; q++)      /* S5: the first (default) or the last of equal lowest-cost minima */
+                if (bi < 0 || cb[pos[q]] < cb[pos[bi]] || ((g_policy.flags & ORC_POL_S5_LAST) && cb[pos[q]] == cb[pos[bi]])) bi = q;
             have[b] = bi >= 0; if (bi >= 0) { bestpos[b] = pos[bi]; matched++; }
         }
     }

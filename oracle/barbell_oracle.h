@@ -115,8 +115,17 @@ int64_t orc_flank_hits_batch(const orc_group *groups, int n_groups, const orc_pa
 int  orc_max_threads(void);
 
 /* policies (S1..S7 of SURVEY.md A.3). Defaults documented in barbell_oracle.c */
+enum {
+    ORC_POL_S1_LEFT = 1,       /* S1: report the LEFT end of a bottom-row cost plateau (default: the right end) */
+    ORC_POL_S2_PAT_FIRST = 2,  /* S2: traceback prefers pattern-only [Del] over text-only [Ins] (default: text-only first) */
+    ORC_POL_S5_LAST = 4,       /* S5: best-per-pattern keeps the LAST of equal lowest-cost minima (default: the first) */
+    ORC_POL_S6_RC_FIRST = 8,   /* S6: `search` lists the Rc matches before the forward ones (default: forward first) */
+    ORC_POL_S3_ROUND = 16,     /* S3: overhang cost of t rows = round-to-nearest(t*alpha) (default: floor) */
+    ORC_POL_S3_CEIL = 32       /* S3: ... = ceil(t*alpha) */
+};
 typedef struct {
     int use_myers;         /* 1 = bit-vector scan + windowed traceback (fast); 0 = naive full DP matrix (cross-check) */
+    int flags;             /* ORC_POL_* bits; 0 = the documented defaults.  Same bits as bb_opts.policy of the product. */
 } orc_policy;
 void orc_set_policy(const orc_policy *p);
 

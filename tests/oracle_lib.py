@@ -40,7 +40,12 @@ assert ROW_DTYPE.itemsize == 88
 
 
 class OrcPolicy(C.Structure):
-    _fields_ = [("use_myers", C.c_int)]
+    _fields_ = [("use_myers", C.c_int), ("flags", C.c_int)]
+
+
+# orc_policy.flags == bb_opts.policy bits
+POL_S1_LEFT, POL_S2_PAT_FIRST, POL_S5_LAST, POL_S6_RC_FIRST, POL_S3_ROUND, POL_S3_CEIL = 1, 2, 4, 8, 16, 32
+_cur_policy = [1, 0]
 
 
 _lib = None
@@ -86,9 +91,27 @@ def lib():
     return _lib
 
 
-def set_policy(use_myers=1):
-    p = OrcPolicy(use_myers)
+def set_policy(use_myers=None, flags=None):
+    if use_myers is not None:
+        _cur_policy[0] = int(use_myers)
+    if flags is not None:
+        _cur_policy[1] = int(flags)
+    p = OrcPolicy(_cur_policy[0], _cur_policy[1])
     lib().orc_set_policy(C.byref(p))
+
+
+class policy:
+    """with O.policy(flags): ... -- runs the oracle under the given ORC_POL_* bits and restores the previous setting"""
+
+    def __init__(self, flags):
+        self.flags = flags
+
+    def __enter__(self):
+        self.saved = _cur_policy[1]
+        set_policy(flags=self.flags)
+
+    def __exit__(self, *a):
+        set_policy(flags=self.saved)
 
 
 class Match:

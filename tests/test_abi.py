@@ -24,7 +24,7 @@ def test_header_symbols_exported():
     for s in syms:
         assert hasattr(L, s), f"{s} declared in include/barbell_b200.h but not exported"
     assert set(api.EXPORTS) == set(syms)
-    assert L.bb_abi_version() == 1
+    assert L.bb_abi_version() == 2
 
 
 def test_row_layout_matches_oracle_and_header():

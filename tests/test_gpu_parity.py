@@ -20,6 +20,7 @@ def _annotator(gs, **kw):
 def _check(gs, bases, offsets, **kw):
     """Both scan paths (lossless pre-filter + window verification, and the exact full-length scan) against the oracle."""
     out = []
+    kw = dict(kw)
     for use_filter in (True, False):
         an = _annotator(gs, use_filter=use_filter, **kw)
         try:
@@ -416,3 +417,44 @@ def test_crumb_packed_host_to_device_copy_is_lossless():
         assert an.annotate(b2, o2).tobytes() == want2.tobytes()
     assert an.annotate(b, o).tobytes() == want.tobytes()
     an.close()
+
+
+POLICY_SETS = [1, 2, 4, 8, 16, 32, 1 | 2 | 4 | 8, 2 | 4 | 16, 1 | 8 | 32, 63 - 32]
+
+
+@pytest.mark.parametrize("pol", POLICY_SETS)
+def test_search_policies_gpu_equals_oracle(pol):
+    """The choices of sassy that the reference's tests do not pin (S1 plateau side, S2 traceback order, S3 overhang rounding,
+    S5 tie between equal minima, S6 strand order) are run-time switches of BOTH the oracle (orc_policy.flags) and the product
+    (bb_opts.policy): under every setting the GPU rows and flank hits must equal the oracle's."""
+    for kit, kw, n in (("SQK-NBD114-96", {}, 400), ("SQK-RBK114-96", dict(max_flank_errors=5), 200), ("SQK-RBK114-96", {}, 120)):
+        gs = bb.GroupSet.from_kit(kit, **kw)
+        b, o, _ = synth.make_reads(gs.as_dicts(), n, (150, 2500), seed=900 + pol)
+        with O.policy(pol):
+            rows = _check(gs, b, o, policy=pol)
+        base = _annotator(gs)
+        try:
+            default_rows = base.annotate(b, o)
+        finally:
+            base.close()
+        if pol in (1, 2, 1 | 2 | 4 | 8) and kit == "SQK-NBD114-96":
+            assert rows.tobytes() != default_rows.tobytes(), "the policy did not change a single row: the knob is not wired"
+
+
+def test_global_window_queue_overflow_reruns_the_batch_exactly(monkeypatch):
+    """A window queue too small for the batch (forced with BB_WIN_CAP): CTAs that cannot reserve slots leave holes, so the
+    verify kernel must not decode the queue at all and the engine re-runs the batch with the exact scan -- same rows."""
+    gs = bb.GroupSet.from_kit("SQK-NBD114-96")
+    b, o, _ = synth.make_reads(gs.as_dicts(), 3000, (400, 3000), seed=4711)
+    an = _annotator(gs)
+    want = an.annotate(b, o)
+    an.close()
+    monkeypatch.setenv("BB_WIN_CAP", "7")
+    an = _annotator(gs)
+    try:
+        for _ in range(3):                              # stale queue contents of an earlier batch must not matter either
+            got = an.annotate(b, o)
+            assert got.tobytes() == want.tobytes()
+    finally:
+        an.close()
+    assert len(want) > 2000
