@@ -288,6 +288,7 @@ struct Engine {
             BB_CUDA(cudaMemcpyAsync(d_sorted.p, uniq, static_cast<size_t>(n_entries) * 8, cudaMemcpyDeviceToDevice, st));
         }
         BB_CUDA(d_flags.ensure(n_entries));
+        h_counters[1] = n_entries;
         BB_CUDA(cudaMemcpyAsync(d_cnt + 1, h_counters + 1, 4, cudaMemcpyHostToDevice, st));   // [1] = entries after the sort / unique
         k_resolve<<<(n_entries + 255) / 256, 256, 0, st>>>(d_sorted.as<uint64_t>(), d_cnt + 1, offsets, d_groups(), d_flags.as<uint8_t>(), pol);
         launches++;
@@ -697,6 +698,7 @@ int bb_set_groups(bb_ctx* c, const bb_group* groups, int32_t n_groups) {
         }
         // barcode patterns as one byte per row = 8 * (4-bit IUPAC set): forward, and explicitly reverse-complemented (barcodes.rs:85-90);
         // + per strand the leading rows all barcodes share (computed once per flank match by k_barcode_rows)
+        if (blob.size() & 1) blob.push_back(0);          // the kernel reads the codes with 16-byte loads
         off_bar[g] = blob.size();
         blob.resize(blob.size() + (static_cast<size_t>(2) * S.n_barcodes * 64 + 2 * 64) / 8, 0);
         {
