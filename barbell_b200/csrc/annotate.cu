@@ -100,6 +100,7 @@ struct Engine {
                                          // + an exception list (2; falls back to 1 for good when a batch has too many non-ACGT bytes)
     int pack_threads = 1;
     int pol = 0;                         // bb_opts.policy (barcode_rows.cuh kPol*)
+    bool k3_mitm = true;                 // barcode stage keeps half of the traceback records resident (BB_K3_MITM=0: all of them)
     uint8_t* h_pack = nullptr; size_t h_pack_cap = 0;   // pinned staging of the packed bases
     DBuf d_packed;
     uint64_t last_windows = 0;
@@ -151,21 +152,27 @@ struct Engine {
     }
 
     // K3: one warp (= CTA) per flank match; the grid is as many CTAs as fit the chip at once (shared memory bounds them)
-    template <int NWT, bool PACKED, bool S2PAT>
-    int launch_barcode(const BarArgs& B, uint32_t n_hits, cudaStream_t st) {
-        const size_t smem = barcode_rows_smem<NWT, PACKED>(gt->max_bar_len, gt->max_own_rows);
+    template <int NWT, bool PACKED, bool S2PAT, bool MITM>
+    int launch_barcode_v(const BarArgs& B, uint32_t n_hits, cudaStream_t st) {
+        const size_t smem = barcode_rows_smem<NWT, PACKED, MITM>(gt->max_bar_len, gt->max_own_rows);
         static thread_local size_t cfg_smem = 0; static thread_local int per_sm = 0;
         if (cfg_smem != smem) {
-            BB_CUDA(cudaFuncSetAttribute(k_barcode_rows<NWT, PACKED, S2PAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-            BB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_barcode_rows<NWT, PACKED, S2PAT>, 32, smem));
+            BB_CUDA(cudaFuncSetAttribute(k_barcode_rows<NWT, PACKED, S2PAT, MITM>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+            BB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_barcode_rows<NWT, PACKED, S2PAT, MITM>, 32, smem));
             if (per_sm < 1) { set_error("barcode kernel does not fit: %zu bytes of shared memory per warp", smem); return BB_ERR_INVALID; }
             cfg_smem = smem;
         }
         const unsigned blocks = std::min<unsigned>(n_hits, 148u * static_cast<unsigned>(per_sm));
-        k_barcode_rows<NWT, PACKED, S2PAT><<<blocks, 32, smem, st>>>(B);
+        k_barcode_rows<NWT, PACKED, S2PAT, MITM><<<blocks, 32, smem, st>>>(B);
         launches++;
         BB_CUDA(cudaGetLastError());
         return BB_OK;
+    }
+    template <int NWT, bool PACKED>
+    int launch_barcode(const BarArgs& B, uint32_t n_hits, cudaStream_t st) {
+        const bool s2 = (pol & kPolS2PatFirst) != 0;
+        if (k3_mitm) return s2 ? launch_barcode_v<NWT, PACKED, true, true>(B, n_hits, st) : launch_barcode_v<NWT, PACKED, false, true>(B, n_hits, st);
+        return s2 ? launch_barcode_v<NWT, PACKED, true, false>(B, n_hits, st) : launch_barcode_v<NWT, PACKED, false, false>(B, n_hits, st);
     }
 
     // The whole device pipeline on stream `st`; inputs resident on the device.
@@ -330,12 +337,18 @@ struct Engine {
             B.bases = bases; B.offsets = offsets; B.hits = d_hits.as<Hit>(); B.n_hits = d_cnt + 2; B.groups = d_groups();
             B.code = gt->d_code.as<uint8_t>(); B.prm = prm; B.rows = d_rows.as<bb_row>(); B.row_valid = d_valid.as<uint8_t>();
             B.sh_rows = gt->max_bar_len; B.pol = pol;
-            const bool packed = gt->max_region <= 48, s2 = (pol & kPolS2PatFirst) != 0;
-            int rc = packed ? (s2 ? launch_barcode<1, true, true>(B, n_hits, st) : launch_barcode<1, true, false>(B, n_hits, st))
-                            : (s2 ? launch_barcode<1, false, true>(B, n_hits, st) : launch_barcode<1, false, false>(B, n_hits, st));
+            // one launch per record format that the geometry can need; each takes the flank matches of its region lengths
+            B.rn_lo = -1; B.rn_hi = 48;
+            int rc = launch_barcode<1, true>(B, n_hits, st);
             if (rc != BB_OK) return rc;
-            if (gt->max_region > 64) {   // regions of more than 64 bases (large automatic k): the three-word instantiation takes those flank matches
-                rc = s2 ? launch_barcode<3, false, true>(B, n_hits, st) : launch_barcode<3, false, false>(B, n_hits, st);
+            if (gt->max_region > 48) {
+                B.rn_lo = 48; B.rn_hi = 64;
+                rc = launch_barcode<1, false>(B, n_hits, st);
+                if (rc != BB_OK) return rc;
+            }
+            if (gt->max_region > 64) {   // large automatic k (custom 115-bp tags)
+                B.rn_lo = 64; B.rn_hi = 1 << 20;
+                rc = launch_barcode<3, false>(B, n_hits, st);
                 if (rc != BB_OK) return rc;
             }
         }
@@ -552,6 +565,7 @@ int bb_create(const bb_opts* opts, bb_ctx** out, char* err, size_t errlen) {
         c->eng[i].pack_mode = (opts->flags & 4u) ? 2 : (opts->flags & 2u) ? 1 : 0;
         c->eng[i].pack_threads = bb::pack_default_threads();
         c->eng[i].pol = static_cast<int>(opts->policy) & bb::kPolMask;
+        if (const char* e = std::getenv("BB_K3_MITM")) c->eng[i].k3_mitm = std::atoi(e) != 0;
     }
     *out = c;
     return BB_OK;
@@ -698,29 +712,30 @@ int bb_set_groups(bb_ctx* c, const bb_group* groups, int32_t n_groups) {
         }
         // barcode patterns as one byte per row = 8 * (4-bit IUPAC set): forward, and explicitly reverse-complemented (barcodes.rs:85-90);
         // + per strand the leading rows all barcodes share (computed once per flank match by k_barcode_rows)
-        if (blob.size() & 1) blob.push_back(0);          // the kernel reads the codes with 16-byte loads
+        if (blob.size() & 1) blob.push_back(0);          // the kernel copies the codes with 16-byte loads
         off_bar[g] = blob.size();
-        blob.resize(blob.size() + (static_cast<size_t>(2) * S.n_barcodes * 64 + 2 * 64) / 8, 0);
+        const int n_rounds = (S.n_barcodes + 31) / 32;
+        blob.resize(blob.size() + (static_cast<size_t>(2) * n_rounds * 64 * 32 + 2 * 64) / 8, 0);
         {
+            // table layout [strand][round][row][lane]: a warp's load of one pattern row is 32 consecutive bytes
             uint8_t* off = reinterpret_cast<uint8_t*>(blob.data() + off_bar[g]);
-            uint8_t* shoff = off + static_cast<size_t>(2) * S.n_barcodes * 64;
+            uint8_t* shoff = off + static_cast<size_t>(2) * n_rounds * 64 * 32;
+            auto at = [&](int st, int b, int row) -> uint8_t& { return off[((static_cast<size_t>(st) * n_rounds + (b >> 5)) * 64 + row) * 32 + (b & 31)]; };
             for (int b = 0; b < S.n_barcodes; b++)
                 for (int i = 0; i < S.bar_len; i++) {
                     const uint8_t ch = static_cast<uint8_t>(S.barcodes[static_cast<size_t>(b) * S.bar_len + i]);
-                    off[(static_cast<size_t>(0) * S.n_barcodes + b) * 64 + i] = static_cast<uint8_t>(kAlpha.code[ch] << 3);
-                    off[(static_cast<size_t>(1) * S.n_barcodes + b) * 64 + (S.bar_len - 1 - i)] = static_cast<uint8_t>(kAlpha.code[kAlpha.rcchar[ch]] << 3);
+                    at(0, b, i) = static_cast<uint8_t>(kAlpha.code[ch] << 3);
+                    at(1, b, S.bar_len - 1 - i) = static_cast<uint8_t>(kAlpha.code[kAlpha.rcchar[ch]] << 3);
                 }
             for (int st = 0; st < 2; st++) {
-                const uint8_t* first = off + static_cast<size_t>(st) * S.n_barcodes * 64;
                 int P = S.bar_len;
                 for (int b = 1; b < S.n_barcodes; b++) {
-                    const uint8_t* cur = first + static_cast<size_t>(b) * 64;
                     int q = 0;
-                    while (q < P && cur[q] == first[q]) q++;
+                    while (q < P && at(st, b, q) == at(st, 0, q)) q++;
                     P = q;
                 }
                 D.sh_p[st] = P;
-                std::memcpy(shoff + 64 * st, first, 64);
+                for (int q = 0; q < 64; q++) shoff[64 * st + q] = at(st, 0, q);
                 max_own_rows = std::max(max_own_rows, S.bar_len - P);
             }
         }
@@ -740,7 +755,7 @@ int bb_set_groups(bb_ctx* c, const bb_group* groups, int32_t n_groups) {
         hg[g].f_eq = reinterpret_cast<const uint32_t*>(base + off_feq[g]);
         hg[g].f_seq = hg[g].f_eq + 256;
         hg[g].bar_off = reinterpret_cast<const uint8_t*>(base + off_bar[g]);
-        hg[g].sh_off = hg[g].bar_off + static_cast<size_t>(2) * groups[g].n_barcodes * 64;
+        hg[g].sh_off = hg[g].bar_off + static_cast<size_t>(2) * ((groups[g].n_barcodes + 31) / 32) * 64 * 32;
         hg[g].pol = pol;
         hg[g].ov = reinterpret_cast<const int*>(base + off_ov[g]);
     }

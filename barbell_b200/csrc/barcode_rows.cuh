@@ -35,7 +35,11 @@ constexpr int kPolS3Round = 16;     // S3: overhang cost of t hanging rows = rou
 constexpr int kPolS3Ceil = 32;      // S3: ... = ceil(t*alpha)
 constexpr int kPolMask = 63;
 
-constexpr int kOffStride = 68;      // bytes between two lanes' pattern-code arrays in shared memory (17 words: equal rows of the 32 lanes hit 32 banks)
+// Pattern codes live as [row][lane] bytes (element r of a lane's pattern at offs[r * kOffStride]): the global table is
+// [strand][round of 32 barcodes][row][lane], so a round's codes are one contiguous block that the warp copies into shared
+// memory with a few 16-byte loads, and a warp's read of one row is 32 consecutive bytes (conflict-free).
+constexpr int kOffStride = 32;
+BB_HD uint32_t ld_code(const uint8_t* p) { return *p; }
 
 BB_HD int bb_clz64(uint64_t x) {
 #if defined(__CUDA_ARCH__)
@@ -64,6 +68,14 @@ BB_HD double bb_bits_to_double(uint64_t x) {
     return __longlong_as_double(static_cast<long long>(x));
 #else
     double d; std::memcpy(&d, &x, 8); return d;
+#endif
+}
+// double whose high word is h and whose low word is 0 (powers of two and 0.0 are built with integer multiplies: FMA pipe, not ALU)
+BB_HD double bb_hi_to_double(uint32_t h) {
+#if defined(__CUDA_ARCH__)
+    return __hiloint2double(static_cast<int>(h), 0);
+#else
+    return bb_bits_to_double(static_cast<uint64_t>(h) << 32);
 #endif
 }
 BB_HD double bb_fma(double a, double b, double c) {
@@ -142,7 +154,7 @@ struct RowHist {
     uint32_t* w;
     int lane;
     BB_HD void store(int row, const uint64_t* a, const uint64_t* b) const {
-        uint32_t* q = w + static_cast<size_t>(row) * (32 * kWords) + lane;
+        uint32_t* q = w + row * (32 * kWords) + lane;
         if constexpr (PACKED) {
             q[0] = static_cast<uint32_t>(a[0]); q[32] = static_cast<uint32_t>(b[0]);
             q[64] = bb_pack16(static_cast<uint32_t>(a[0] >> 32), static_cast<uint32_t>(b[0] >> 32));
@@ -155,7 +167,7 @@ struct RowHist {
         }
     }
     BB_HD void load(int row, uint64_t* a, uint64_t* b) const {
-        const uint32_t* q = w + static_cast<size_t>(row) * (32 * kWords) + lane;
+        const uint32_t* q = w + row * (32 * kWords) + lane;
         if constexpr (PACKED) {
             const uint32_t hi = q[64];
             a[0] = q[0] | (static_cast<uint64_t>(hi & 0xffffu) << 32);
@@ -171,6 +183,8 @@ struct RowHist {
 };
 template <int NWT, bool PACKED>
 BB_HD constexpr size_t row_hist_bytes(int rows) { return static_cast<size_t>(rows) * 32 * 4 * RowHist<NWT, PACKED>::kWords; }
+// own-row records resident at a time: all of them, or the larger half with the meet-in-the-middle traceback
+BB_HD constexpr int resident_rows(int own_rows, bool mitm) { return mitm ? (own_rows + 1) / 2 : own_rows; }
 
 // match mask of a pattern row: offs = 8 * code, tm = [16][NWT]
 template <int NWT>
@@ -229,33 +243,39 @@ BB_HD uint32_t scan_lut_entry(int idx) {
 }
 
 // tm    : [16][NWT] text-column masks indexed by the 4-bit IUPAC set of a PATTERN character (bit j-1 = region base j matches)
-// offs  : this lane's pattern, one byte per row = 8 * code
+// offs  : this lane's pattern, one byte per row = 8 * code, row r at offs[r * kOffStride]
 // rn, L : region bases (<= 64 * NWT), pattern rows; P = rows already done by rows_prefix(), (ph, mh) = its row state
 // sh    : the records of the shared rows; hist: this lane's records of rows P+1..L; rec: per-row traceback records, rec[row * 32]
 // lut   : [256] scan_lut_entry()
 // pol   : kPolS1Left | kPolS5Last (S2 is the template parameter: it changes what the forward pass stores)
-template <int NWT, bool PACKED, bool S2PAT>
+// MITM : meet in the middle -- shared memory per alignment is what bounds the warps in flight, so only HALF of the own rows'
+//         records are resident at a time: the forward pass stores rows > H, the traceback walks those, then the forward
+//         recurrence is replayed from the shared row state over rows P+1..H -- this time storing -- and the traceback goes on.
+template <int NWT, bool PACKED, bool S2PAT, bool MITM>
 BB_HD void rows_lane(const uint64_t* tm, const uint8_t* offs, int rn, int L, int P, const uint64_t* ph0, const uint64_t* mh0, const uint64_t* sh,
                      const RowHist<NWT, PACKED>& hist, uint8_t* rec, const uint32_t* lut, int pb0, int pb1, int pol, LaneAlign& O) {
     constexpr int kRowWords = 32 * RowHist<NWT, PACKED>::kWords;
     uint64_t ph[NWT], mh[NWT];
 #pragma unroll
     for (int w = 0; w < NWT; w++) { ph[w] = ph0[w]; mh[w] = mh0[w]; }
-    // ---- forward pass over the lane's own rows, storing every row's record ----
-    {
+    // ---- forward pass over the lane's own rows, storing the records of rows > H (all own rows without MITM) ----
+    const int H = MITM ? P + ((L - P) >> 1) : P;
+    auto forward = [&](int r0, int r1, bool store, int slot0) {    // rows r0+1 .. r1 of the forward recurrence
         RowHist<NWT, PACKED> hp = hist;
-        const uint8_t* op = offs + P;
+        hp.w += slot0 * kRowWords;
+        const uint8_t* cp = offs + r0 * kOffStride;
 #pragma unroll 2
-        for (int r = P; r < L; r++) {
-            const uint64_t* e = row_mask<NWT>(tm, *op++);
+        for (int r = r0; r < r1; r++, cp += kOffStride) {
+            const uint64_t* e = row_mask<NWT>(tm, ld_code(cp));
             uint64_t ev[NWT], diag[NWT], stop[NWT];
 #pragma unroll
             for (int w = 0; w < NWT; w++) ev[w] = e[w];
             row_step<NWT, S2PAT>(ev, ph, mh, diag, stop);
-            hp.store(0, diag, stop);
-            hp.w += kRowWords;
+            if (store) { hp.store(0, diag, stop); hp.w += kRowWords; }
         }
-    }
+    };
+    if (H > P) forward(P, H, false, 0);
+    forward(H, L, true, 0);
     // ---- bottom row: D[L][j] = L + sum of the horizontal deltas.  S1 reports the plateaus that follow a decrease and are followed
     //      by an increase (or the end); "lowest cost, first seen" (searcher.rs:294-300) = the FIRST plateau at the global minimum ----
     int cbest, jend;
@@ -338,47 +358,52 @@ BB_HD void rows_lane(const uint64_t* tm, const uint8_t* offs, int rn, int L, int
         if (ev_b1) { T_b = T; M_b = M; j_first = j; }
         rec[(i - 1) * 32] = static_cast<uint8_t>((t << 1) | is_match);   // t <= path cost <= L <= 64
         // reversed op order: t non-match ops, then the leaving op; g = 2^-(t+1)
-        const double g = bb_bits_to_double(static_cast<uint64_t>(1022 - t) << 52);
-        const double mm = is_match ? 1.0 : 0.0;
-        s = bb_fma(is_match ? g : 0.0, a2, s);
-        a2 = g * bb_fma(mm, a1, a2);
-        a1 = bb_fma(g, a1, 0.5 * mm);
-    };
-    auto own_row_at = [&](int i, const RowHist<NWT, PACKED>& hp, bool ev_a, bool ev_b1, bool ev_b2) {
-        uint64_t diag[NWT], stop[NWT];
-        hp.load(0, diag, stop);
-        row(i, diag, stop, row_mask<NWT>(tm, offs[i - 1]), ev_a, ev_b1, ev_b2);
-    };
-    auto own_row = [&](int i, bool ev_a, bool ev_b1, bool ev_b2) {
-        RowHist<NWT, PACKED> hp = hist;
-        hp.w += (i - P - 1) * kRowWords;
-        own_row_at(i, hp, ev_a, ev_b1, ev_b2);
+        const uint32_t gh = static_cast<uint32_t>(1022 - t) << 20, um = static_cast<uint32_t>(is_match);
+        const double g = bb_hi_to_double(gh);
+        s = bb_fma(bb_hi_to_double(gh * um), a2, s);                      // is_match ? g : 0
+        a2 = g * bb_fma(bb_hi_to_double(0x3ff00000u * um), a1, a2);       // is_match ? 1 : 0
+        a1 = bb_fma(g, a1, bb_hi_to_double(0x3fe00000u * um));            // is_match ? 1/2 : 0
     };
     auto shared_row = [&](int i, bool ev_a, bool ev_b1, bool ev_b2) {
         const uint64_t* q = sh + static_cast<size_t>(3 * (i - 1)) * NWT;
         row(i, q, q + NWT, q + 2 * NWT, ev_a, ev_b1, ev_b2);
     };
-    auto rows_range = [&](int hi, int lo) {                  // rows hi, hi-1, .., lo without events
-        int i = hi;
-        RowHist<NWT, PACKED> hp = hist;
-        hp.w += (hi - P - 1) * kRowWords;
-#pragma unroll 2
-        for (; i >= lo && i > P; i--) { own_row_at(i, hp, false, false, false); hp.w -= kRowWords; }
-#pragma unroll 2
-        for (; i >= lo; i--) shared_row(i, false, false, false);
-    };
     const bool in_range = pb1 > pb0 && pb0 >= 0 && pb1 <= L;
-    if (!in_range) rows_range(L, 1);
-    else {
-        rows_range(L, pb1 + 1);
-        const bool same = pb1 == pb0 + 1;
-        if (pb1 > P) own_row(pb1, true, same, false); else shared_row(pb1, true, same, false);
-        if (!same) {
-            rows_range(pb1 - 1, pb0 + 2);
-            if (pb0 + 1 > P) own_row(pb0 + 1, false, true, false); else shared_row(pb0 + 1, false, true, false);
+    int base = H;                                            // own row i sits in slot i - 1 - base
+    for (int i = L; i >= 1;) {
+        if (MITM && i == H && base == H && H > P) {          // the traceback arrives at the lower half: replay it, storing
+#pragma unroll
+            for (int w = 0; w < NWT; w++) { ph[w] = ph0[w]; mh[w] = mh0[w]; }
+            forward(P, H, true, 0);
+            base = P;
         }
-        if (pb0 >= 1) { if (pb0 > P) own_row(pb0, false, false, true); else shared_row(pb0, false, false, true); }
-        rows_range(pb0 - 1, 1);
+        RowHist<NWT, PACKED> hp = hist;
+        hp.w += (i - 1 - base) * kRowWords;
+        const uint8_t* cp = offs + (i - 1) * kOffStride;
+        if (in_range && (i == pb1 || i == pb0 + 1 || i == pb0)) {        // the three rows with an event (warp-uniform)
+            if (i > P) {
+                uint64_t diag[NWT], stop[NWT];
+                hp.load(0, diag, stop);
+                row(i, diag, stop, row_mask<NWT>(tm, ld_code(cp)), i == pb1, i == pb0 + 1, i == pb0);
+            } else shared_row(i, i == pb1, i == pb0 + 1, i == pb0);
+            i--;
+            continue;
+        }
+        int lo = 1;                                          // plain rows down to the next event row / the next change of storage
+        if (in_range) lo = i > pb1 ? pb1 + 1 : i > pb0 + 1 ? pb0 + 2 : 1;
+        if (MITM && i > H && lo <= H) lo = H + 1;
+        if (i > P) {
+            if (lo <= P) lo = P + 1;
+#pragma unroll 2
+            for (; i >= lo; i--, cp -= kOffStride, hp.w -= kRowWords) {
+                uint64_t diag[NWT], stop[NWT];
+                hp.load(0, diag, stop);
+                row(i, diag, stop, row_mask<NWT>(tm, ld_code(cp)), false, false, false);
+            }
+        } else {
+#pragma unroll 2
+            for (; i >= lo; i--) shared_row(i, false, false, false);
+        }
     }
     const int n_ops = L + T;
     if (!lodhi_exact(s, n_ops)) {

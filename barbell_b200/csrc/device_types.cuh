@@ -32,7 +32,7 @@ struct DevGroup {
     const uint64_t* eq;                  // [2 strands][256 bytes][nw]  flank match masks indexed by the raw text byte
     const uint64_t* eq_top;              // same, top-aligned, wildcard rows below (used by the scan kernel)
     const int* ov;                       // [m+1] floor(t*alpha)
-    const uint8_t* bar_off;              // [2 strands][n_barcodes][64]: 8 * (4-bit IUPAC set) of every pattern row (Rc: of the reverse complement)
+    const uint8_t* bar_off;              // [2 strands][rounds of 32 barcodes][64 rows][32 lanes]: 8 * (4-bit IUPAC set) of every pattern row (Rc: of the reverse complement)
     const uint8_t* sh_off;               // [2 strands][64]: the same for the leading rows all barcodes of the strand share
     int sh_p[2], pol, pad3_;             // number of those rows per strand; search policy bits (barcode_rows.cuh kPol*)
     // lossless pre-filter (0 = off): rows [f_q0, f_q0 + f_q) of the flank are an N-free run with f_q <= 15 and 3k <= f_q

@@ -892,6 +892,7 @@ struct BarArgs {
     Params prm;
     bb_row* rows;             // one slot per hit
     uint8_t* row_valid;
+    int rn_lo, rn_hi;         // this launch takes the flank matches whose region has rn_lo < bases <= rn_hi
     int sh_rows;              // shared-memory rows reserved for the records of the shared leading rows / the per-row traceback records
     int pol;                  // kPolS1Left | kPolS5Last (S2 is a template parameter)
 };
@@ -924,12 +925,12 @@ struct TopTwo {
     int ok = 0, pi = 0, ei = 0, pj = 0, ej = 0, cost = 0, ts = 0, te = 0;   // map_pat_to_text_with_cost of the top
 };
 
-// Shared memory of one k_barcode_rows CTA (= one warp): the 16 text masks, the records of the shared leading rows, the lanes'
-// pattern codes, one traceback record byte per row and lane, and the lanes' own-row records.
-template <int NWT, bool PACKED>
+// Shared memory of one k_barcode_rows CTA (= one warp): the scan table, the 16 text masks, the records of the shared leading rows,
+// one traceback record byte per row and lane, and the lanes' own-row records.
+template <int NWT, bool PACKED, bool MITM>
 __host__ __device__ inline size_t barcode_rows_smem(int sh_rows, int own_rows) {
-    return 1024 + 16 * NWT * 8 + static_cast<size_t>(sh_rows) * 3 * NWT * 8 + 64 + 32 * kOffStride + static_cast<size_t>(sh_rows) * 32 +
-           row_hist_bytes<NWT, PACKED>(own_rows) + 16;
+    return 1024 + 16 * NWT * 8 + ((static_cast<size_t>(sh_rows) * 3 * NWT * 8 + 15) & ~static_cast<size_t>(15)) + 64 + static_cast<size_t>(sh_rows) * 32 + 64 * kOffStride +
+           row_hist_bytes<NWT, PACKED>(resident_rows(own_rows, MITM)) + 16;
 }
 
 // One warp (= one CTA) per flank match; lane = barcode pattern (rounds of 32).  The region's text masks and the pattern rows
@@ -938,25 +939,26 @@ __host__ __device__ inline size_t barcode_rows_smem(int sh_rows, int own_rows) {
 // The per-pattern best minimum is the same with k = floor(0.4*len) and with the fallback k = len (the first
 // lowest-cost minimum); the threshold only decides WHICH patterns are candidates, so both candidate sets are reduced
 // side by side and the fallback rule (searcher.rs:303-306) picks one at the end.
-// NWT = 1 takes the flank matches whose region has <= 64 bases (all of them for the shipped kits), NWT = 3 the others.
-template <int NWT, bool PACKED, bool S2PAT>
+// Launches: regions of <= 48 bases with 12-byte records (PACKED), 49..64 with 16-byte records, longer ones with three text words.
+// MITM = only half of the own rows' records are resident (more warps in flight for some replayed forward rows).
+template <int NWT, bool PACKED, bool S2PAT, bool MITM>
 __global__ void __launch_bounds__(32) k_barcode_rows(const BarArgs A) {
     extern __shared__ __align__(16) unsigned char bar_smem[];
     const int lane = threadIdx.x;
     uint32_t* lut = reinterpret_cast<uint32_t*>(bar_smem);                                 // [256] bottom-row scan table
     uint64_t* tm = reinterpret_cast<uint64_t*>(bar_smem + 1024);                           // [16][NWT]
     uint64_t* sh = tm + 16 * NWT;                                                          // [sh_rows][3][NWT]
-    uint8_t* s_shoff = reinterpret_cast<uint8_t*>(sh + static_cast<size_t>(A.sh_rows) * 3 * NWT);   // [64] codes of the shared rows
-    uint8_t* s_off = s_shoff + 64;                                                         // [32 lanes][kOffStride]
-    uint8_t* rec = s_off + 32 * kOffStride;                                                // [sh_rows][32]
-    const RowHist<NWT, PACKED> hist{reinterpret_cast<uint32_t*>(rec + ((static_cast<size_t>(A.sh_rows) * 32 + 15) & ~static_cast<size_t>(15))), lane};
+    uint8_t* s_shoff = reinterpret_cast<uint8_t*>(sh) + ((static_cast<size_t>(A.sh_rows) * 3 * NWT * 8 + 15) & ~static_cast<size_t>(15));   // [64] codes of the shared rows
+    uint8_t* rec = s_shoff + 64;                                                           // [sh_rows][32]
+    uint8_t* s_off = rec + static_cast<size_t>(A.sh_rows) * 32;                            // [64 rows][32 lanes] pattern codes of the round
+    const RowHist<NWT, PACKED> hist{reinterpret_cast<uint32_t*>(s_off + 64 * kOffStride), lane};
     for (int q = lane; q < 256; q += 32) lut[q] = scan_lut_entry(q);
     const uint32_t n_hits = __ldg(A.n_hits);
     for (uint32_t h = blockIdx.x; h < n_hits; h += gridDim.x) {
         const Hit H = A.hits[h];
-        if (!H.has_region) { if (NWT == 1 && lane == 0) A.row_valid[h] = 0; continue; }    // searcher.rs:445-449
+        if (!H.has_region) { if (A.rn_lo < 0 && lane == 0) A.row_valid[h] = 0; continue; }    // searcher.rs:445-449
         const int rn = H.re - H.rs;
-        if (NWT == 1 ? rn > 64 : rn <= 64) continue;            // the other instantiation's flank matches
+        if (rn <= A.rn_lo || rn > A.rn_hi) continue;            // another launch's flank matches
         const DevGroup& G = A.groups[H.group];
         const uint64_t rs0 = A.offsets[H.read];
         const int n = static_cast<int>(A.offsets[H.read + 1] - rs0);
@@ -990,7 +992,7 @@ __global__ void __launch_bounds__(32) k_barcode_rows(const BarArgs A) {
         // ---- the leading rows all barcodes of this strand share: once per flank match ----
         uint64_t ph0[NWT], mh0[NWT];
         rows_prefix<NWT, S2PAT>(tm, s_shoff, P, lane == 0, sh, ph0, mh0);
-        const uint8_t* offs_g = G.bar_off + static_cast<size_t>(H.strand) * nb * 64;
+        const uint8_t* offs_g = G.bar_off + static_cast<size_t>(H.strand) * ((nb + 31) / 32) * (64 * 32);   // [round][row][lane]
 
         TopTwo all, strict;          // candidates under the fallback k = len / under k1
         int matched = 0;
@@ -999,18 +1001,15 @@ __global__ void __launch_bounds__(32) k_barcode_rows(const BarArgs A) {
             const int b = rd * 32 + lane;
             bool has1 = false;
             __syncwarp();
-            if (b < nb) {
-                const uint4* src = reinterpret_cast<const uint4*>(offs_g + static_cast<size_t>(b) * 64);
-                uint32_t* dst = reinterpret_cast<uint32_t*>(s_off + lane * kOffStride);
-#pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    if (16 * q < L) { const uint4 v = __ldg(src + q); dst[4 * q] = v.x; dst[4 * q + 1] = v.y; dst[4 * q + 2] = v.z; dst[4 * q + 3] = v.w; }
-                }
+            {   // the round's codes: one contiguous [row][lane] block of the table -> shared memory, 16 bytes per lane and step
+                const uint4* src = reinterpret_cast<const uint4*>(offs_g + static_cast<size_t>(rd) * (64 * 32));
+                uint4* dst = reinterpret_cast<uint4*>(s_off);
+                for (int q = lane; q < 2 * L; q += 32) dst[q] = __ldg(src + q);
             }
             __syncwarp();
             if (b < nb) {
                 LaneAlign R;
-                rows_lane<NWT, PACKED, S2PAT>(tm, s_off + lane * kOffStride, rn, L, P, ph0, mh0, sh, hist, rec + lane, lut, G.pbar0, G.pbar1, A.pol, R);
+                rows_lane<NWT, PACKED, S2PAT, MITM>(tm, s_off + lane, rn, L, P, ph0, mh0, sh, hist, rec + lane, lut, G.pbar0, G.pbar1, A.pol, R);
                 has1 = R.cbest <= k1;
                 const double sn = G.perfect > 0.0 ? R.s / G.perfect : 0.0;
 #pragma unroll

@@ -73,6 +73,9 @@ def expect(pattern, region, pol=0):
 def check(lib, pattern, region, pb0, pb1, lane=0, P=0, pol=0, words=0):
     best = expect(pattern, region, pol)
     got = run_rows(lib, pattern, region, pb0, pb1, lane, P, pol, words)
+    mitm = run_rows(lib, pattern, region, pb0, pb1, lane, P, pol, words | 16)       # half of the records resident at a time
+    for k in ("cbest", "jend", "ts", "cnt", "i_first", "i_last", "j_first", "j_last", "sub_cost", "n_ops", "s", "replayed"):
+        assert mitm[k] == got[k], (k, pattern, region, pb0, pb1, P, pol, got, mitm)
     assert best is not None
     ctx = (pattern, region, pb0, pb1, P, pol, best, got)
     assert got["cbest"] == best.cost, ctx

@@ -22,11 +22,13 @@ def ald_panel(n_bar=384):
     return bb.GroupSet.from_seqs([(panel(gl), [f"L{i}" for i in range(n_bar)], 0), (panel(gr), [f"R{i}" for i in range(n_bar)], 1)])
 cases = [("SQK-NBD114-96", {}), ("SQK-RBK114-96", dict(max_flank_errors=5)), ("SQK-RBK114-96", {}), ("SQK-RBK114-96", dict(use_extended=True)),
          ("custom dual-end 384-barcode panel", None)]
-for kit, kw in cases:
+sel = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else range(len(cases))
+modes = (True,) if len(sys.argv) > 3 else (True, False)
+for kit, kw in [cases[i] for i in sel]:
     gs = ald_panel() if kw is None else bb.GroupSet.from_kit(kit, **kw)
     b, o, _ = synth.make_reads(gs.as_dicts(), n, 10000, seed=synth.SEED0 + 2)
     tb = torch.from_numpy(b).cuda(); to = torch.from_numpy(o.astype(np.int64)).cuda()
-    for uf in (True, False):
+    for uf in modes:
         an = bb.Annotator(gs, use_filter=uf)
         for it in range(3):
             l0 = an.kernel_launches()
