@@ -117,3 +117,52 @@ def make_reads(groups, n_reads, read_len=10000, seed=SEED0, p_mut=0.06, rc_frac=
         k = rng.binomial(total, n_frac)
         bases[rng.integers(0, total, size=k)] = ord("N")
     return bases, offsets, truth
+
+
+def _fasta_seqs(path):
+    seqs = []
+    for line in open(path):
+        line = line.strip()
+        if line.startswith(">"):
+            seqs.append(bytearray())
+        elif line and seqs:
+            seqs[-1] += line.upper().encode()
+    return [bytes(x) for x in seqs]
+
+
+def _common_prefix_len(seqs):
+    n = min(len(x) for x in seqs)
+    k = 0
+    while k < n and all(x[k] == seqs[0][k] for x in seqs):
+        k += 1
+    return k
+
+
+def dual_end_panel_specs(left_fasta, right_fasta, n_bar=384, seed=26):
+    """BASELINE configs[3]: a custom dual-end panel -- n_bar random 24-mers wrapped in the flanks of the reference's example
+    tags (examples/ald_left.fasta / ald_right.fasta, copied to tests/golden/), one Ftag and one Rtag group.  First / last barcode
+    base are varied so that the common prefix / suffix stay on the flanks.  Returns [(seqs, labels, match_type), ...] for
+    GroupSet.from_seqs (product) or the oracle's group builder."""
+    rnd = np.random.default_rng(seed)
+    specs = []
+    for path, tag, ty in ((left_fasta, "L", 0), (right_fasta, "R", 1)):
+        src = _fasta_seqs(path)
+        pre = _common_prefix_len(src)
+        suf = _common_prefix_len([x[::-1] for x in src])
+        front, rear = src[0][:pre], src[0][len(src[0]) - suf:]
+        seqs = []
+        for i in range(n_bar):
+            core = bytes(rnd.choice(_ACGT, 24))
+            seqs.append(front + b"ACGT"[i % 4:i % 4 + 1] + core[1:-1] + b"ACGT"[(i // 4) % 4:(i // 4) % 4 + 1] + rear)
+        specs.append((seqs, [f"{tag}{i}" for i in range(n_bar)], ty))
+    return specs
+
+
+def write_fastq(path, bases, offsets, prefix="read_"):
+    """FASTQ text of a batch (quality 'I' throughout)."""
+    n = len(offsets) - 1
+    qual = b"I" * int(np.diff(offsets.astype(np.int64)).max(initial=0))
+    with open(path, "wb", buffering=1 << 24) as f:
+        for i in range(n):
+            sq = bases[int(offsets[i]):int(offsets[i + 1])].tobytes()
+            f.write(b"@%s%d ch=1\n" % (prefix.encode(), i)); f.write(sq); f.write(b"\n+\n"); f.write(qual[:len(sq)]); f.write(b"\n")

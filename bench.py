@@ -2,20 +2,25 @@
 """bench.py -- throughput of the annotate hot path (BASELINE.json metric: reads/s and Gbases/s annotated).
 
 A "step" is one pass of the whole hot path (flank scan -> local minima -> traceback -> barcode stage -> collapse) over
-one batch of synthetic reads of configs[1] (SQK-NBD114-96, 10 kb reads).  `value` is measured with the batch resident
-in HBM (CUDA events on the launching stream); `e2e` goes through the pipelined C-ABI calls with pinned HOST buffers
-(host->device copy of the reads and device->host copy of the rows inside the timed region).
+one batch of synthetic 10 kb reads.  `value` is measured with the batch resident in HBM (CUDA events on the launching
+stream); `e2e` goes through the pipelined C-ABI calls with pinned HOST buffers (host->device copy of the reads and
+device->host copy of the rows inside the timed region); `e2e_fastq` is FASTQ text (page cache) -> annotation.tsv through
+the `barbell annotate` CLI.
 
-  python bench.py --gpus 1 --steps 5 --warmup 3
+  python bench.py                                   configs[1] (SQK-NBD114-96), the configuration the metric is quoted on
+  python bench.py --config rbk_k5|ald384|rbk_ext|nbd_ext      the other BASELINE configs (same JSON line, same keys)
   python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...      (one rank per GPU, weak scaling)
   python bench.py --impl reference ...     times the CPU restatement (oracle) on the host cores -- the reference is
-                                           Rust + crates.io dependencies and cannot be built in this image.
+                                           Rust + crates.io dependencies and cannot be built in this image.  This arm
+                                           never loads libbarbell_b200.so: its query groups come from oracle/groups_oracle.py.
 """
 import argparse
 import json
 import os
+import re
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -25,9 +30,26 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import numpy as np
 
-KIT = "SQK-NBD114-96"
 READ_LEN = 10000
-WORKLOAD = "SQK-NBD114-96 (96 native barcodes + flanks), synthetic 10 kb reads, 1xB200 per rank (BASELINE configs[1])"
+GOLD = os.path.join(ROOT, "tests", "golden")
+# reads: per device-resident batch of the GPU arm (10 kb each); ref_reads: per step of the CPU arm (a bounded sample of the same
+# workload; equal to `reads` for the configuration the driver compares); cpu_reads: sample timed for cpu_baseline inside the GPU arm
+CONFIGS = {
+    "nbd": dict(kit="SQK-NBD114-96", kw={}, reads=100000, ref_reads=100000, cpu_reads=40000,
+                workload="SQK-NBD114-96 (96 native barcodes + flanks), synthetic 10 kb reads, 1xB200 per rank (BASELINE configs[1])"),
+    "rbk_k5": dict(kit="SQK-RBK114-96", kw=dict(max_flank_errors=5), reads=100000, ref_reads=50000, cpu_reads=20000,
+                   workload="SQK-RBK114-96 rapid kit, --flank-max-errors 5, synthetic 10 kb reads, 1xB200 per rank (BASELINE configs[2])"),
+    "ald384": dict(panel=384, kw={}, reads=100000, ref_reads=2000, cpu_reads=2000,
+                   workload="custom dual-end 384-barcode panel (examples/ald_left + ald_right flanks, Ftag + Rtag, automatic k = 31 / 30), "
+                            "synthetic 10 kb reads, 1xB200 per rank (BASELINE configs[3])"),
+    "rbk_ext": dict(kit="SQK-RBK114-96", kw=dict(use_extended=True), reads=100000, ref_reads=8000, cpu_reads=4000,
+                    workload="SQK-RBK114-96 --use-extended (2 query groups, automatic k = 20 / 17: the kit whose Extended template really adds "
+                             "a pattern set), synthetic 10 kb reads, 1xB200 per rank (BASELINE configs[4] shape)"),
+    "nbd_ext": dict(kit="SQK-NBD114-96", kw=dict(use_extended=True), reads=100000, ref_reads=100000, cpu_reads=40000,
+                    workload="SQK-NBD114-96 --use-extended (BASELINE configs[4] as written; this kit has no Extended template at the reference "
+                             "commit, src/kits/kits.rs:311-316, so the groups equal configs[1]), synthetic 10 kb reads, 1xB200 per rank"),
+}
+E2E_MODE = "crumbs"     # fixed wire format of the end-to-end leg (bb_opts.flags bit 2)
 
 
 def peaks():
@@ -36,6 +58,35 @@ def peaks():
         d = json.load(open(p))
         return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def panel_specs(cfg):
+    from barbell_b200 import synth
+    return synth.dual_end_panel_specs(os.path.join(GOLD, "ald_left.fasta"), os.path.join(GOLD, "ald_right.fasta"), cfg["panel"])
+
+
+def oracle_groups(cfg):
+    """Query groups as the oracle's dicts, built by oracle/groups_oracle.py (no product code involved)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import groups_oracle as GO
+    if "panel" in cfg:
+        return GO.groups_from_seqs(panel_specs(cfg))
+    return GO.groups_from_kit(cfg["kit"], cfg["kw"].get("use_extended", False), cfg["kw"].get("max_flank_errors"))
+
+
+def product_groups(cfg):
+    import barbell_b200 as bb
+    if "panel" in cfg:
+        return bb.GroupSet.from_seqs(panel_specs(cfg))
+    return bb.GroupSet.from_kit(cfg["kit"], cfg["kw"].get("use_extended", False), cfg["kw"].get("max_flank_errors"))
+
+
+def config_dict(name, cfg, n_reads, world):
+    """The `config` object of the JSON line -- the same function serves both arms, so equal workloads give equal objects."""
+    return dict(workload=cfg["workload"], name=name, kit=cfg.get("kit", f"dual-end panel, 2 x {cfg.get('panel')} barcodes"),
+                options=cfg["kw"], reads_per_step=n_reads, read_len=READ_LEN, batch_bytes=n_reads * READ_LEN,
+                l2_policy="batch larger than the 126 MB L2; same batch every step",
+                parallelism=f"reads sharded over {world} GPU(s), no data-path collective")
 
 
 class ClockSampler:
@@ -95,36 +146,97 @@ def make_batch(groups, n_reads, seed):
     return synth.make_reads(groups, n_reads, READ_LEN, seed=seed)
 
 
-def run_reference(args):
-    """The reference arm: the CPU restatement of the same path on all host cores, bounded sample per step."""
+def run_reference(args, name, cfg):
+    """The reference arm: the CPU restatement of the same path on all host cores, bounded sample per step.  Loads
+    oracle/libbarbell_oracle.so only -- the query groups come from oracle/groups_oracle.py, the reads from numpy."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import barbell_b200 as bb
     import oracle_lib as O
-    from barbell_b200 import synth
-    gs = bb.GroupSet.from_kit(KIT)
-    G = gs.as_dicts()
+    from barbell_b200 import synth          # numpy-only module; importing the package does not load the product library
+    G = oracle_groups(cfg)
     threads = O.lib().orc_max_threads()
-    n = args.ref_reads
+    n = args.ref_reads or cfg["ref_reads"]
     bases, offsets, _ = make_batch(G, n, synth.SEED0 + 2)
-    for _ in range(max(1, min(args.warmup, 1))):
-        O.demux_batch(G, bases[:int(offsets[min(n, 64)])], offsets[:min(n, 64) + 1], n_threads=threads)
+    m = min(n, 64)
+    for _ in range(max(1, args.warmup)):         # warm-up: thread pool, page faults, tables (a small slice is enough on the CPU)
+        O.demux_batch(G, bases[:int(offsets[m])], offsets[:m + 1], n_threads=threads)
     t0 = time.perf_counter()
     rows = 0
     for _ in range(args.steps):
         rows += len(O.demux_batch(G, bases, offsets, n_threads=threads))
     dt = time.perf_counter() - t0
     v = n * args.steps / dt
-    sample = f"{n} synthetic 10 kb reads per step x {args.steps} steps, oracle (C restatement, bit-vector scan), {threads} threads"
+    sample = (f"{n} synthetic 10 kb reads per step x {args.steps} steps, oracle (C restatement of the reference's per-read algorithm, "
+              f"scalar bit-vector scan; NOT upstream Rust + sassy AVX2), {threads} threads")
     out = dict(metric="reads_per_s", value=v, unit="reads/s", impl="reference", n_gpus=args.gpus, steps=args.steps,
                warmup=args.warmup, ms_per_step=1e3 * dt / args.steps, higher_is_better=True, scaling="weak",
                vs_baseline=None, dtype="u64 bit-vectors (integer) + f64 score", data="synthetic",
-               gbases_per_s=v * READ_LEN / 1e9,
-               config=dict(workload=WORKLOAD, reads_per_step=n, read_len=READ_LEN, kit=KIT),
+               gbases_per_s=v * READ_LEN / 1e9, config=config_dict(name, cfg, n, args.gpus),
                cpu_baseline=dict(value=v, unit="reads/s", cores=threads, kind="port", sample=sample),
-               e2e=dict(value=v, unit="reads/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), rows=rows)
+               e2e=dict(value=v, unit="reads/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), rows=rows,
+               product_library_loaded=any("libbarbell_b200" in ln for ln in open("/proc/self/maps")))
     print(json.dumps(out), flush=True)
+
+
+def int_issue_roofline(name, n_reads, ms_per_step, sm_mhz):
+    """Integer-issue roofline of the whole step: lane-operations executed per step -- smsp__thread_inst_executed.sum of
+    every kernel of one step from the committed ncu pass (profiles/r2_inst_counts.json, scaled by the read count) -- over the measured
+    step time, against 148 SMs x 4 schedulers x 32 lanes per clock at the SM clock sampled during the timed region."""
+    p = os.path.join(ROOT, "profiles", "r2_inst_counts.json")
+    if not os.path.exists(p) or not sm_mhz:
+        return None
+    d = json.load(open(p)).get(name)
+    if not d:
+        return None
+    scale = n_reads / d["reads"]
+    lane_ops = sum(k["thread_inst"] for k in d["kernels"].values()) * scale
+    peak = 148 * 128 * sm_mhz * 1e6
+    achieved = lane_ops / (ms_per_step / 1e3)
+    top = sorted(d["kernels"].items(), key=lambda kv: -kv[1]["thread_inst"])[:3]
+    return dict(achieved=achieved, peak=peak, unit="lane-ops/s", frac=achieved / peak, lane_ops_per_step=lane_ops,
+                lane_ops_per_base=lane_ops / (n_reads * READ_LEN), source="profiles/r2_inst_counts.json (ncu smsp__thread_inst_executed.sum per kernel)",
+                top_kernels={k: dict(lane_ops_per_step=v["thread_inst"] * scale, share=v["thread_inst"] / max(1, sum(x["thread_inst"] for x in d["kernels"].values())))
+                             for k, v in top},
+                note="every kernel of the step is integer/bit work on the ALU pipe, which issues one warp instruction per 2 clocks per scheduler: "
+                     "an all-ALU instruction stream tops out at 0.5 of this peak")
+
+
+def fastq_leg(cfg, groups, n_reads, passes, threads):
+    """FASTQ text in the page cache -> annotation.tsv through the CLI (`barbell annotate`): the reference's own entry point
+    (bin/main.rs:274-339).  The file is named `passes` times on the command line, so the stream phase is long enough to time;
+    the CLI reports the reads/s of its stream phase (parse -> pinned slots -> GPU -> TSV), set-up excluded."""
+    exe = os.path.join(ROOT, "barbell_b200", "barbell")
+    if "kit" not in cfg or not os.path.exists(exe):
+        return None
+    from barbell_b200 import synth
+    tmp = tempfile.mkdtemp(prefix="bb_fastq_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    try:
+        b, o, _ = make_batch(groups, n_reads, synth.SEED0 + 2)
+        fq = os.path.join(tmp, "reads.fastq")
+        synth.write_fastq(fq, b, o)
+        size = os.path.getsize(fq)
+        cmd = [exe, "annotate", "--kit", cfg["kit"], "-o", os.path.join(tmp, "out.tsv"), "-t", str(threads)]
+        if cfg["kw"].get("max_flank_errors") is not None:
+            cmd += ["--flank-max-errors", str(cfg["kw"]["max_flank_errors"])]
+        if cfg["kw"].get("use_extended"):
+            cmd += ["--use-extended"]
+        cmd += ["-i"] + [fq] * passes
+        t0 = time.perf_counter()
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+        wall = time.perf_counter() - t0
+        m = re.search(r"rows: (\d+), ([0-9.]+) s, ([0-9.]+) reads/s", r.stdout)
+        if r.returncode != 0 or not m:
+            return dict(error=(r.stdout + r.stderr)[-300:])
+        stream_s = float(m.group(2))
+        reads = n_reads * passes
+        return dict(value=reads / stream_s if stream_s > 0 else None, unit="reads/s", reads=reads, fastq_bytes=size * passes,
+                    stream_s=stream_s, wall_s=wall, rows=int(m.group(1)), threads=threads,
+                    gbases_per_s=reads * READ_LEN / stream_s / 1e9 if stream_s > 0 else None,
+                    api="barbell annotate CLI: FASTQ text (page cache) -> parse -> pinned slots -> GPU -> annotation.tsv; stream phase "
+                        "as timed by the CLI, process set-up (CUDA context, pinned allocations) reported in wall_s only")
+    finally:
+        subprocess.run(["rm", "-rf", tmp])
 
 
 def main():
@@ -133,16 +245,22 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--reads", type=int, default=100000, help="reads per device-resident batch (10 kb each: 1 GB)")
-    ap.add_argument("--ref-reads", type=int, default=20000, help="reads per step of the CPU arm (--impl reference)")
-    ap.add_argument("--cpu-reads", type=int, default=40000, help="reads of the batch timed on the host cores for cpu_baseline")
+    ap.add_argument("--config", default="nbd", choices=sorted(CONFIGS))
+    ap.add_argument("--reads", type=int, default=0, help="reads per device-resident batch (10 kb each); 0 = the config's (100000 = 1 GB)")
+    ap.add_argument("--ref-reads", type=int, default=0, help="reads per step of the CPU arm (--impl reference); 0 = the config's")
+    ap.add_argument("--cpu-reads", type=int, default=0, help="reads of the batch timed on the host cores for cpu_baseline; 0 = the config's")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-e2e-fastq", action="store_true")
+    ap.add_argument("--e2e-modes", action="store_true", help="also time the other two wire formats of the end-to-end leg (reported as by_mode)")
     ap.add_argument("--e2e-sub", type=int, default=4, help="sub-batches per step of the end-to-end leg")
     ap.add_argument("--e2e-depth", type=int, default=4, help="sub-batches in flight (<= BB_MAX_INFLIGHT = 4)")
+    ap.add_argument("--fastq-reads", type=int, default=50000)
+    ap.add_argument("--fastq-passes", type=int, default=8)
     args = ap.parse_args()
+    name, cfg = args.config, CONFIGS[args.config]
     if args.impl == "reference":
-        return run_reference(args)
+        return run_reference(args, name, cfg)
     args.warmup = max(args.warmup, 3)
 
     import torch
@@ -156,15 +274,23 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: barbell_b200 has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", world))
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-        # the ranks share the host cores: split them for the host-side packing of the end-to-end leg
-        os.environ.setdefault("BB_PACK_THREADS", str(max(1, (os.cpu_count() or 1) // int(os.environ.get("LOCAL_WORLD_SIZE", world)))))
+        # the ranks share the host cores: give every rank its own contiguous slice (the packing threads of the end-to-end leg inherit it)
+        try:
+            cores = sorted(os.sched_getaffinity(0))
+            per = max(1, len(cores) // local_world)
+            mine = cores[local * per:(local + 1) * per] or cores
+            os.sched_setaffinity(0, mine)
+            os.environ.setdefault("BB_PACK_THREADS", str(len(mine)))
+        except (AttributeError, OSError):
+            os.environ.setdefault("BB_PACK_THREADS", str(max(1, (os.cpu_count() or 1) // local_world)))
 
-    gs = bb.GroupSet.from_kit(KIT)
+    gs = product_groups(cfg)
     G = gs.as_dicts()
     an = bb.Annotator(gs, device=local)
-    n_reads = args.reads
+    n_reads = args.reads or cfg["reads"]
     bases, offsets, _ = make_batch(G, n_reads, synth.SEED0 + 2 + 1000 * rank)
     total = int(offsets[-1])
     algo_bytes = total + 8 * n_reads                       # L + 8 bytes per read
@@ -222,61 +348,57 @@ def main():
             subs.append((hb, ho, hi - lo))
         h2d = sum(hb.numel() + ho.numel() * 8 for hb, ho, _ in subs)
 
-        def e2e_pass(n_steps):
+        def e2e_pass(annot, n_steps):
             rows = 0
             jobs = [(s, i) for s in range(n_steps) for i in range(n_sub)]
             inflight = nxt = 0
             while nxt < len(jobs) or inflight:
                 while nxt < len(jobs) and inflight < depth:
                     hb, ho, nr = subs[jobs[nxt][1]]
-                    an.submit(hb.data_ptr(), ho.data_ptr(), nr, tag=nxt)
+                    annot.submit(hb.data_ptr(), ho.data_ptr(), nr, tag=nxt)
                     nxt += 1; inflight += 1
-                _, _, n = an.collect(copy=False)
+                _, _, n = annot.collect(copy=False)
                 rows += n; inflight -= 1
             return rows
 
         def timed_e2e(annot):
-            nonlocal an
-            an_saved, an = an, annot
-            try:
-                e2e_pass(2)                              # warm-up (the packed mode also settles its head/tail split here)
-                barrier()
-                b0 = annot.h2d_bytes()
-                t0 = time.perf_counter()
-                rows = e2e_pass(args.steps)
-                torch.cuda.synchronize()
-                dt = time.perf_counter() - t0
-                moved = (annot.h2d_bytes() - b0) // args.steps
-            finally:
-                an = an_saved
+            e2e_pass(annot, 2)                       # warm-up (the packed modes also settle their head/tail split here)
+            barrier()
+            b0 = annot.h2d_bytes()
+            t0 = time.perf_counter()
+            rows = e2e_pass(annot, args.steps)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            moved = (annot.h2d_bytes() - b0) // args.steps
             te = torch.tensor([dt], dtype=torch.float64, device="cuda")
             if world > 1:
                 dist.all_reduce(te, op=dist.ReduceOp.MAX)
             return float(te.item()), rows, int(moved)
 
-        dt_plain, rows_e2e, moved_plain = timed_e2e(an)
-        # same call with bb_opts.flags bit 1: the library nibble-packs the HEAD of every batch on the host cores while the tail is
-        # copied as it is (the split adapts to the measured pack and link rates), so PCIe moves fewer bytes
-        an_pack = bb.Annotator(gs, device=local, pack_h2d=True)
-        dt_pack, rows_pack, moved_pack = timed_e2e(an_pack)
-        an_pack.close()
-        # flags bit 2: the denser wire format, 2 bits per base for A/C/G/T + an exception list for every other byte
-        an_crumb = bb.Annotator(gs, device=local, pack_h2d="crumbs")
-        dt_crumb, rows_crumb, moved_crumb = timed_e2e(an_crumb)
-        an_crumb.close()
-        assert rows_pack == rows_e2e and rows_crumb == rows_e2e and moved_plain == h2d
-        modes = {"plain": (dt_plain, moved_plain), "packed": (dt_pack, moved_pack), "crumbs": (dt_crumb, moved_crumb)}
-        best = min(modes, key=lambda k: modes[k][0])
-        dt = modes[best][0]
-        e2e = dict(value=world * n_reads * args.steps / dt, unit="reads/s", h2d_bytes_per_step=modes[best][1],
+        # fixed configuration: flags bit 2 -- the library packs the HEAD of every batch to 2 bits per base (+ an exception list for every
+        # byte that is not A/C/G/T) on the host cores while the tail is copied as it is; expanded on the device.  Lossless for this path.
+        modes = {}
+        an_e = bb.Annotator(gs, device=local, pack_h2d=E2E_MODE)
+        modes[E2E_MODE] = timed_e2e(an_e)
+        an_e.close()
+        if args.e2e_modes:
+            modes["plain"] = timed_e2e(an)
+            assert modes["plain"][2] == h2d
+            an_p = bb.Annotator(gs, device=local, pack_h2d=True)
+            modes["packed"] = timed_e2e(an_p)
+            an_p.close()
+            assert len({v[1] for v in modes.values()}) == 1
+        dt, rows_e2e, moved = modes[E2E_MODE]
+        e2e = dict(value=world * n_reads * args.steps / dt, unit="reads/s", h2d_bytes_per_step=moved,
                    d2h_bytes_per_step=int(rows_e2e // args.steps * 88),
-                   api=f"bb_submit/bb_collect, pinned host buffers, {n_sub} sub-batches per step, {depth} in flight; mode=" + best +
-                       (" (head of every batch packed by the library on the host cores -- " +
-                        ("4 bits per base" if best == "packed" else "2 bits per base + exception list") +
-                        " -- and expanded on the device, tail copied as it is; bytes counted by the library: bb_h2d_bytes)" if best != "plain" else ""),
-                   gbases_per_s=world * total * args.steps / dt / 1e9,
-                   by_mode={k: world * n_reads * args.steps / v[0] for k, v in modes.items()},
-                   h2d_bytes_by_mode={k: v[1] for k, v in modes.items()})
+                   api=f"bb_submit/bb_collect, pinned host buffers (1 byte per base, as the reference consumes them), {n_sub} sub-batches per step, "
+                       f"{depth} in flight; fixed mode={E2E_MODE}: head of every batch packed by the library on the host cores to 2 bits per base + "
+                       "exception list and expanded on the device, tail copied as it is; bytes counted by the library (bb_h2d_bytes)",
+                   gbases_per_s=world * total * args.steps / dt / 1e9, raw_bytes_per_step=h2d,
+                   efficiency_vs_device_resident=(world * n_reads * args.steps / dt) / value)
+        if args.e2e_modes:
+            e2e["by_mode"] = {k: world * n_reads * args.steps / v[0] for k, v in modes.items()}
+            e2e["h2d_bytes_by_mode"] = {k: v[2] for k, v in modes.items()}
 
     counters = an.counters()
     summed = sharding.all_reduce_counters(counters["total"], counters["kept"]) if world > 1 else counters
@@ -289,41 +411,45 @@ def main():
         achieved = algo_bytes / (scan_avg / 1e3) / 1e9
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tp):
+        if os.path.exists(tp) and name in ("nbd", "nbd_ext"):
             try:    # dram__bytes_read+write per launch from the committed ncu --set full capture, scaled to this batch size
                 traffic = json.load(open(tp))["k_flank_scan_dram_bytes_per_algorithmic_byte"] * algo_bytes
             except Exception:
                 traffic = None
+        step_ms = ms_max / args.steps
         out = dict(metric="reads_per_s", value=value, unit="reads/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
-                   ms_per_step=ms_max / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+                   ms_per_step=step_ms, higher_is_better=True, scaling="weak", vs_baseline=None,
                    dtype="u64 bit-vectors (integer) + f64 score", data="synthetic",
-                   gbases_per_s=value * READ_LEN / 1e9,
-                   config=dict(workload=WORKLOAD, kit=KIT, reads_per_step=n_reads, read_len=READ_LEN,
-                               batch_bytes=total, l2_policy="batch (1 GB) larger than the 126 MB L2; same batch every step",
-                               parallelism=f"reads sharded over {world} GPU(s), no data-path collective"),
+                   gbases_per_s=value * READ_LEN / 1e9, config=config_dict(name, cfg, n_reads, world),
                    roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=traffic,
-                                 kernel="flank scan stage (the kernels that stream the bases): k_flank_filter [scan + candidate runs + pre-check] + k_flank_verify (+ chunk index)",
-                                 whole_step=dict(achieved=algo_bytes / (ms_max / args.steps / 1e3) / 1e9, frac=algo_bytes / (ms_max / args.steps / 1e3) / 1e9 / peak,
-                                                 note="same algorithmic bytes over the WHOLE step; the barcode stage (k_barcode, ~60 % of the step) touches < 1 % of the bytes: "
-                                                      "one warp per flank match aligns all 96 barcodes with traceback + Lodhi score, issue/ALU bound"),
+                                 kernel="flank scan stage (the kernels that stream the bases): k_flank_filter [scan + candidate runs + pre-check] + "
+                                        "k_flank_verify, or k_flank_scan when the pre-filter does not apply (+ chunk index)",
+                                 whole_step=dict(achieved=algo_bytes / (step_ms / 1e3) / 1e9, frac=algo_bytes / (step_ms / 1e3) / 1e9 / peak,
+                                                 note="same algorithmic bytes over the WHOLE step; the barcode stage (k_barcode_rows) touches < 1 % of the "
+                                                      "bytes: one warp per flank match aligns every barcode with traceback + Lodhi score, ALU-pipe bound"),
                                  algorithmic_bytes_per_launch=algo_bytes, ms_per_launch=scan_avg, peak_source=peak_src,
-                                 note="integer-issue bound (bit-vector DP, 23 instructions per base for both strands, ALU pipe 77 % active: "
-                                      "profiles/r1_ncu_full_final_kernels.txt), not DRAM bound; see DESIGN.md section 3"),
+                                 int_issue=int_issue_roofline(name, n_reads, step_ms, clocks.get("sm_mhz")),
+                                 note="integer-issue bound (bit-vector DP on the ALU pipe), not DRAM bound: int_issue is the roofline that says how good "
+                                      "the kernels are; see DESIGN.md section 3"),
                    stage_ms_per_step={k: v / args.steps for k, v in stage_acc.items()},
                    e2e=e2e, gpu_launches=int(launches), clocks=clocks, rows_per_step=int(n_rows), counters=summed,
                    label_counts=dict(labels_seen=int((hist[1:] > 0).sum()), rows=int(hist.sum()), flank_only_rows=int(hist[0]),
                                      note="rows per barcode of the last step, all ranks (all_reduce of %d int64)" % len(hist)))
+        if world == 1 and not args.no_e2e_fastq:
+            out["e2e_fastq"] = fastq_leg(cfg, G, args.fastq_reads, args.fastq_passes, min(16, os.cpu_count() or 1))
         if not args.no_cpu_baseline:
             import oracle_lib as O
+            Go = oracle_groups(cfg)
+            assert [(g["flank"], g["k_flank"], g["barcodes"]) for g in Go] == [(g["flank"], g["k_flank"], g["barcodes"]) for g in G]
             threads = O.lib().orc_max_threads()
-            nb = min(args.cpu_reads, n_reads)
+            nb = min(args.cpu_reads or cfg["cpu_reads"], n_reads)
             sb, so = sharding.slice_reads(bases, offsets, 0, nb)
             t0 = time.perf_counter()
-            rows_cpu = O.demux_batch(G, sb, so, n_threads=threads)
+            rows_cpu = O.demux_batch(Go, sb, so, n_threads=threads)
             dt = time.perf_counter() - t0
             out["cpu_baseline"] = dict(value=nb / dt, unit="reads/s", cores=threads, kind="port",
-                                       sample=f"first {nb} reads of the same batch, oracle (C restatement, bit-vector scan), {threads} threads, "
-                                              f"{dt:.2f} s wall = {dt * threads:.0f} core-seconds")
+                                       sample=f"first {nb} reads of the same batch, oracle (C restatement, scalar bit-vector scan; NOT upstream "
+                                              f"Rust + sassy AVX2), {threads} threads, {dt:.2f} s wall = {dt * threads:.0f} core-seconds")
             # the same reads through the GPU path must give the same rows
             chk = an.annotate(sb, so)
             out["cpu_baseline"]["rows_match_gpu"] = bool(chk.tobytes() == rows_cpu.tobytes())

@@ -121,3 +121,39 @@ def test_group_geometry_matches_python_restatement():
         got = bb.GroupSet.from_seqs([(seqs, [f"q{i}" for i in range(len(seqs))], api.FTAG)]).as_dicts()[0]
         for k in want:
             assert got[k] == want[k], k
+
+
+def test_python_group_oracle_equals_the_product_on_every_kit():
+    """oracle/groups_oracle.py (what bench.py's reference arm builds its query groups with, so that arm never loads the product
+    library) restates barcodes.rs:106-197 / kits.rs independently of csrc/host/groups.cpp: both must agree on every preset."""
+    import json, os, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "oracle"))
+    import groups_oracle as GO
+    names = [k for k, _ in json.load(open(os.path.join(root, "barbell_b200", "data", "kits.json")))["kit_names"]]
+    assert len(names) == 39
+    for kit in names:
+        for ext in (False, True):
+            for mfe in (None, 3):
+                a = GO.groups_from_kit(kit, ext, mfe)
+                b = bb.GroupSet.from_kit(kit, ext, mfe).as_dicts()
+                assert len(a) == len(b)
+                for x, y in zip(a, b):
+                    for k in y:
+                        assert x[k] == y[k], (kit, ext, mfe, k)
+    gold = os.path.join(root, "tests", "golden")
+    a = GO.groups_from_fasta([gold + "/ald_left.fasta", gold + "/ald_right.fasta"], [0, 1])
+    b = bb.GroupSet.from_fasta([gold + "/ald_left.fasta", gold + "/ald_right.fasta"], [0, 1]).as_dicts()
+    for x, y in zip(a, b):
+        for k in y:
+            assert x[k] == y[k], k
+
+
+def test_bench_reference_arm_does_not_load_the_product_library():
+    import json, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1", "--ref-reads", "40"],
+                       capture_output=True, text=True, check=True)
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    assert d["impl"] == "reference" and d["product_library_loaded"] is False and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
