@@ -390,6 +390,37 @@ struct Engine {
         static const auto t0 = std::chrono::steady_clock::now();
         return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     }
+    // host buffers that already hold the 2-bit wire format (bb_submit_packed): copy, expand on the device, run, rows to pinned memory
+    int run_host_packed(const uint8_t* crumbs, uint64_t total, const uint64_t* exc, uint64_t n_exc, const uint64_t* offsets, uint32_t n_reads, uint64_t* n_rows) {
+        BB_CUDA(cudaSetDevice(device));
+        *n_rows = 0;
+        if (n_reads == 0 || total == 0) { last_reads = n_reads; last_rows = 0; last_kept = 0; return BB_OK; }
+        const size_t pk = (static_cast<size_t>((total + 3) / 4) + 63) & ~size_t(63);
+        BB_CUDA(d_bases.ensure(((total + 15) & ~15ull) + 16));
+        BB_CUDA(d_offsets.ensure(static_cast<size_t>(n_reads + 1) * 8));
+        BB_CUDA(d_packed.ensure(pk + static_cast<size_t>(n_exc) * 8 + 64));
+        BB_CUDA(cudaMemcpyAsync(d_packed.p, crumbs, static_cast<size_t>((total + 3) / 4), cudaMemcpyHostToDevice, stream));
+        if (n_exc) BB_CUDA(cudaMemcpyAsync(d_packed.as<uint8_t>() + pk, exc, static_cast<size_t>(n_exc) * 8, cudaMemcpyHostToDevice, stream));
+        BB_CUDA(cudaMemcpyAsync(d_offsets.p, offsets, static_cast<size_t>(n_reads + 1) * 8, cudaMemcpyHostToDevice, stream));
+        h2d_bytes += (total + 3) / 4 + n_exc * 8 + static_cast<uint64_t>(n_reads + 1) * 8;
+        k_unpack_crumbs<<<static_cast<unsigned>((total / 16 + 256) / 256), 256, 0, stream>>>(d_packed.as<uint8_t>(), d_bases.as<uint8_t>(), total);
+        launches++;
+        if (n_exc) {
+            k_patch_exceptions<<<static_cast<unsigned>((n_exc + 255) / 256), 256, 0, stream>>>(
+                reinterpret_cast<const uint64_t*>(d_packed.as<uint8_t>() + pk), n_exc, d_bases.as<uint8_t>(), total);
+            launches++;
+        }
+        BB_CUDA(cudaGetLastError());
+        int rc = run(d_bases.as<uint8_t>(), d_offsets.as<uint64_t>(), n_reads, total, stream, n_rows);
+        if (rc != BB_OK) return rc;
+        if (*n_rows) {
+            rc = ensure_host_rows(*n_rows);
+            if (rc != BB_OK) return rc;
+            BB_CUDA(cudaMemcpyAsync(h_rows, d_rows_out.p, *n_rows * sizeof(bb_row), cudaMemcpyDeviceToHost, stream));
+            BB_CUDA(cudaStreamSynchronize(stream));
+        }
+        return BB_OK;
+    }
     // host-buffer form: copy in, run, copy rows to pinned memory
     int run_host(const uint8_t* bases, const uint64_t* offsets, uint32_t n_reads, uint64_t* n_rows) {
         BB_CUDA(cudaSetDevice(device));
@@ -499,6 +530,7 @@ struct Engine {
 struct bb_job {
     const uint8_t* bases; const uint64_t* offsets; uint32_t n_reads; uint64_t tag; int engine;
     int rc = 0; uint64_t n_rows = 0; bool done = false;
+    bool packed = false; uint64_t n_bases = 0; const uint64_t* exc = nullptr; uint64_t n_exc = 0;   // bb_submit_packed: `bases` holds crumbs
 };
 
 struct bb_ctx {
@@ -530,7 +562,8 @@ static void worker_main(bb_ctx* c, int idx) {
             job = c->queue[idx].front();
         }
         uint64_t n_rows = 0;
-        const int rc = c->eng[idx].run_host(job->bases, job->offsets, job->n_reads, &n_rows);
+        const int rc = job->packed ? c->eng[idx].run_host_packed(job->bases, job->n_bases, job->exc, job->n_exc, job->offsets, job->n_reads, &n_rows)
+                                   : c->eng[idx].run_host(job->bases, job->offsets, job->n_reads, &n_rows);
         {
             std::lock_guard<std::mutex> lk(c->mu);
             job->rc = rc; job->n_rows = n_rows; job->done = true;
@@ -833,6 +866,29 @@ int bb_submit(bb_ctx* c, const uint8_t* bases, const uint64_t* offsets, uint32_t
     return BB_OK;
 }
 
+int bb_submit_packed(bb_ctx* c, const uint8_t* crumbs, uint64_t n_bases, const uint64_t* exc, uint64_t n_exc, const uint64_t* offsets,
+                     uint32_t n_reads, uint64_t batch_tag) {
+    if (!c || !offsets || (n_reads && !crumbs) || (n_exc && !exc)) return BB_ERR_INVALID;
+    int rc = validate_offsets(c, offsets, n_reads);
+    if (rc != BB_OK) return rc;
+    if (offsets[0] != 0 || offsets[n_reads] != n_bases) { ctx_error(c, "offsets must start at 0 and end at n_bases"); return BB_ERR_INVALID; }
+    std::unique_lock<std::mutex> lk(c->mu);
+    if (!c->workers_started) {
+        for (int i = 0; i < BB_MAX_INFLIGHT; i++) c->workers[i] = std::thread(worker_main, c, i);
+        c->workers_started = true;
+    }
+    if (c->order.size() >= BB_MAX_INFLIGHT) { ctx_error(c, "too many batches in flight: call bb_collect first"); return BB_ERR_INVALID; }
+    const int idx = static_cast<int>(c->submitted % BB_MAX_INFLIGHT);
+    auto* job = new bb_job{crumbs, offsets, n_reads, batch_tag, idx};
+    job->packed = true; job->n_bases = n_bases; job->exc = exc; job->n_exc = n_exc;
+    c->queue[idx].push_back(job);
+    c->order.push_back(job);
+    c->submitted++;
+    lk.unlock();
+    c->cv.notify_all();
+    return BB_OK;
+}
+
 int bb_collect(bb_ctx* c, uint64_t* batch_tag, const bb_row** rows, uint64_t* n_rows) {
     if (!c || !rows || !n_rows) return BB_ERR_INVALID;
     std::unique_lock<std::mutex> lk(c->mu);
@@ -902,6 +958,14 @@ int bb_pack_crumbs(const uint8_t* src, uint64_t n, uint8_t* dst, uint64_t* exc, 
     bb::pack_crumbs(src, n, dst, exc, exc_cap, &used, &over, bb::kAlpha.code, bb::pack_default_threads());
     *n_exc = used;
     return over ? BB_ERR_OVERFLOW : BB_OK;
+}
+
+int bb_pack_crumbs_append(const uint8_t* src, uint64_t n, uint8_t* dst, uint64_t* pos, uint64_t* exc, uint64_t exc_cap, uint64_t* n_exc) {
+    if ((!src && n) || !dst || !pos || !n_exc || (!exc && exc_cap)) return BB_ERR_INVALID;
+    size_t used = static_cast<size_t>(*n_exc);
+    const bool ok = bb::crumbs_append(src, static_cast<size_t>(n), dst, pos, exc, static_cast<size_t>(exc_cap), &used, bb::kAlpha.code);
+    *n_exc = used;
+    return ok ? BB_OK : BB_ERR_OVERFLOW;
 }
 
 void* bb_host_alloc(size_t bytes) {

@@ -31,9 +31,10 @@ class FastqReader {
             }
             size_t p = pos_;
             const char *l0, *l1, *l2, *l3; size_t n0, n1, n2, n3;
+            if (line(p, l0, n0) && n0 == 0) { pos_ = p; continue; }   // a blank line between records: skip it alone (like the chunk parser)
+            p = pos_;
             if (line(p, l0, n0) && line(p, l1, n1) && line(p, l2, n2) && line(p, l3, n3)) {
                 pos_ = p;
-                if (n0 == 0 && n1 == 0) continue;                 // blank lines between records
                 if (l0[0] != '@' || n2 == 0 || l2[0] != '+') { err = "malformed FASTQ record in " + paths_[file_]; return false; }
                 if (n3 != n1) { err = "truncated FASTQ record (quality length differs from sequence length) in " + paths_[file_]; return false; }
                 auto ws = [](char c) { return c == ' ' || c == '\t' || c == '\v' || c == '\f' || c == '\r'; };

@@ -41,7 +41,7 @@ struct Args {
     std::string dropped, failed_out, only_side, read_pattern_out;
     bool no_label = false, no_orientation = false, no_flanks = false, sort_labels = false, skip_trim = false, flip = false;
     int top_n = 10, bucket_size = 250;
-    bool output_given = false, single_reader = false;
+    bool output_given = false, single_reader = false, no_pack = false;
     size_t chunk_kb = 0;
     double min_score = 0.2, min_score_diff = 0.1;
     float alpha = 0.4f;
@@ -54,7 +54,7 @@ struct Args {
         "barbell (B200 build of the annotate path)\n"
         "  barbell annotate -i <fastq>... [-o output.tsv] (--kit <KIT> | -q <fasta>... [-b Ftag|Rtag ...])\n"
         "                   [-t N] [--flank-max-errors INT] [--min-score F] [--min-score-diff F] [--alpha F]\n"
-        "                   [--use-extended] [--verbose] [--gpus N] [--batch-mb MB]\n"
+        "                   [--use-extended] [--verbose] [--gpus N] [--batch-mb MB] [--no-pack]\n"
         "  barbell kit -k <KIT> -i <fastq>... -o <folder> [--maximize] [--failed-out FILE] [--gzip] [annotate options]\n"
         "  barbell filter -i annotation.tsv -o filtered.tsv -f <pattern file>... [--dropped FILE]\n"
         "  barbell trim -i filtered.tsv -r <fastq>... -o <folder> [--no-label] [--no-orientation] [--no-flanks] [--sort-labels]\n"
@@ -105,6 +105,7 @@ Args parse(int argc, char** argv) {
         else if (f == "--failed-out") a.failed_out = one();
         else if (f == "--verbose") a.verbose = true;
         else if (f == "--single-reader") a.single_reader = true;
+        else if (f == "--no-pack") a.no_pack = true;
         else if (f == "--chunk-kb") a.chunk_kb = static_cast<size_t>(std::atol(one().c_str()));
         else if (f == "--use-extended") a.use_extended = true;
         else if (f == "--maximize") a.maximize = true;
@@ -117,31 +118,54 @@ Args parse(int argc, char** argv) {
 
 using bb::FastqReader;
 
+// One batch of reads in page-locked memory, filled by the FASTQ parsers.  Default form: the bases as the library's 2-bit wire
+// format, built read by read WHILE PARSING (bb_pack_crumbs_append: a sequence line is packed while it is still in the cache,
+// no host core touches the bases again, a quarter of the bytes cross PCIe) + the exception list for every byte that is not
+// A/C/G/T (it grows when a batch holds more than ~3 % such bytes).  --no-pack keeps one byte per base.
 struct Batch {
-    uint8_t* bases = nullptr;
+    uint8_t* bases = nullptr;            // packed: crumbs; plain: bytes
+    uint64_t* exc = nullptr;             // packed only
     uint64_t* offsets = nullptr;
-    size_t cap_bytes = 0, cap_reads = 0, bytes = 0;
+    size_t cap_bytes = 0, cap_reads = 0, cap_exc = 0, bytes = 0;   // bytes = bases in the batch
+    uint64_t n_exc = 0;
     uint32_t n_reads = 0;
     std::vector<char> id_chars;          // read ids back to back
     std::vector<uint32_t> id_off;        // n_reads + 1
-    bool pinned = true;
-    bool alloc(size_t cb, size_t cr, bool pin = true) {
-        cap_bytes = cb; cap_reads = cr; pinned = pin;
-        bases = static_cast<uint8_t*>(pin ? bb_host_alloc(cb + 64) : std::malloc(cb + 64));
-        offsets = static_cast<uint64_t*>(pin ? bb_host_alloc((cr + 1) * sizeof(uint64_t)) : std::malloc((cr + 1) * sizeof(uint64_t)));
-        return bases && offsets;
+    bool pinned = true, packed = true, exc_overflow = false;
+    bool alloc(size_t cb, size_t cr, bool pin, bool pack) {
+        cap_bytes = cb; cap_reads = cr; pinned = pin; packed = pack;
+        auto get = [&](size_t n) { return pin ? bb_host_alloc(n) : std::malloc(n); };
+        bases = static_cast<uint8_t*>(get(pack ? cb / 4 + 128 : cb + 64));
+        offsets = static_cast<uint64_t*>(get((cr + 1) * sizeof(uint64_t)));
+        if (pack) { cap_exc = cb / 32 + 4096; exc = static_cast<uint64_t*>(get(cap_exc * sizeof(uint64_t))); }
+        return bases && offsets && (!pack || exc);
     }
-    void clear() { bytes = 0; n_reads = 0; id_chars.clear(); id_off.assign(1, 0); if (offsets) offsets[0] = 0; }
+    void clear() { bytes = 0; n_reads = 0; n_exc = 0; exc_overflow = false; id_chars.clear(); id_off.assign(1, 0); if (offsets) offsets[0] = 0; }
     void append(const char* id, size_t id_len, const char* seq, size_t seq_len) {
-        std::memcpy(bases + bytes, seq, seq_len);
+        if (packed) {
+            uint64_t pos = bytes, ne = n_exc;
+            while (!exc_overflow && bb_pack_crumbs_append(reinterpret_cast<const uint8_t*>(seq), seq_len, bases, &pos, exc, cap_exc, &ne) != BB_OK) {
+                // N-rich input: the exception list grows (re-appending the read rewrites the same crumbs)
+                const size_t cap2 = cap_exc * 4;
+                uint64_t* e2 = static_cast<uint64_t*>(pinned ? bb_host_alloc(cap2 * sizeof(uint64_t)) : std::malloc(cap2 * sizeof(uint64_t)));
+                if (!e2) { exc_overflow = true; break; }
+                std::memcpy(e2, exc, n_exc * sizeof(uint64_t));
+                if (pinned) bb_host_free(exc); else std::free(exc);
+                exc = e2; cap_exc = cap2; pos = bytes; ne = n_exc;
+            }
+            n_exc = ne;
+        } else {
+            std::memcpy(bases + bytes, seq, seq_len);
+        }
         bytes += seq_len;
         offsets[++n_reads] = bytes;
         id_chars.insert(id_chars.end(), id, id + id_len);
         id_off.push_back(static_cast<uint32_t>(id_chars.size()));
     }
     void release() {
-        if (pinned) { bb_host_free(bases); bb_host_free(offsets); } else { std::free(bases); std::free(offsets); }
-        bases = nullptr; offsets = nullptr;
+        auto put = [&](void* q) { if (pinned) bb_host_free(q); else std::free(q); };
+        put(bases); put(offsets); if (exc) put(exc);
+        bases = nullptr; offsets = nullptr; exc = nullptr;
     }
 };
 
@@ -327,10 +351,15 @@ class ParallelSource : public BatchSource {
             line_at(m, f.size, n0, e1, n1);
             if (n1 >= f.size) { err = "truncated FASTQ record in " + f.path; return false; }
             line_at(m, f.size, n1, e2, n2);
-            if (n2 < f.size) line_at(m, f.size, n2, e3, n3); else { e3 = n2; n3 = n2; }
-            if (m[p] != '@' || e2 == n1 || m[n1] != '+') { err = "malformed FASTQ record in " + f.path; return false; }
-            if (e3 - n2 != e1 - n0) { err = "truncated FASTQ record (quality length differs from sequence length) in " + f.path; return false; }
             const size_t seq_len = e1 - n0;
+            // the quality line is as long as the sequence: step over it without reading it (half of a FASTQ file is never touched)
+            const size_t q_end = n2 + seq_len;
+            if (q_end == f.size) { e3 = q_end; n3 = q_end; }
+            else if (q_end < f.size && m[q_end] == '\n') { e3 = q_end; n3 = q_end + 1; }
+            else if (q_end + 1 < f.size && m[q_end] == '\r' && m[q_end + 1] == '\n') { e3 = q_end; n3 = q_end + 2; }
+            else if (n2 < f.size) line_at(m, f.size, n2, e3, n3); else { e3 = n2; n3 = n2; }
+            if (m[p] != '@' || e2 == n1 || m[n1] != '+') { err = "malformed FASTQ record in " + f.path; return false; }
+            if (e3 - n2 != seq_len) { err = "truncated FASTQ record (quality length differs from sequence length) in " + f.path; return false; }
             if (B.bytes + seq_len > B.cap_bytes || B.n_reads + 1 > B.cap_reads) { err = "read longer than the batch buffer (raise --batch-mb)"; return false; }
             size_t idl = 0;
             const char* id = m + p + 1;
@@ -489,15 +518,16 @@ class MultiFileSource : public BatchSource {
     bool aborted_ = false;
 };
 
-// Slots + source for a run: plain files are cut into chunks of `chunk` FASTQ bytes (<= chunk/2 bases each) and parsed by up to
-// 8 of the -t threads; anything else (gzip, pipes, -t 1, --single-reader) goes through one reader thread.
+// Slots + source for a run: plain files are cut into chunks of `chunk` FASTQ bytes (<= chunk/2 bases each) and parsed by the
+// -t threads (at most 32); anything else (gzip, pipes, -t 1, --single-reader) goes through one reader thread.
 struct Ingest {
     std::vector<Batch> slots;
     std::unique_ptr<BatchSource> source;
     bool parallel = false, multifile = false;
+    std::chrono::steady_clock::time_point t_start;          // when the parsers were started (after the slots were allocated)
     bool open(const Args& a, int in_flight, bool pinned, std::string& err) {
         const size_t cap_bytes = a.batch_mb << 20, cap_reads = 1u << 22;
-        const int parse_threads = std::min(8, std::max(1, a.threads));
+        const int parse_threads = std::min(32, std::max(1, a.threads));
         parallel = parse_threads > 1 && !a.single_reader && ParallelSource::usable(a.input);
         size_t chunk = a.chunk_kb ? a.chunk_kb << 10 : cap_bytes, n_chunks = 0;
         if (parallel) {
@@ -508,8 +538,9 @@ struct Ingest {
         // a chunk holds at most chunk/2 bases plus the tail of the record that straddles its end (16 MB covers the longest reads)
         const size_t slot_bytes = parallel ? std::min(cap_bytes, chunk / 2) + (16u << 20) : cap_bytes;
         slots.resize(n_slots);
-        for (auto& b : slots) if (!b.alloc(slot_bytes, cap_reads, pinned)) { err = pinned ? "pinned host allocation failed" : "host allocation failed"; return false; }
+        for (auto& b : slots) if (!b.alloc(slot_bytes, cap_reads, pinned, !a.no_pack)) { err = pinned ? "pinned host allocation failed" : "host allocation failed"; return false; }
         multifile = !parallel && parse_threads > 1 && !a.single_reader && MultiFileSource::usable(a.input);
+        t_start = std::chrono::steady_clock::now();
         if (parallel) source.reset(new ParallelSource(a.input, slots, chunk, parse_threads));
         else if (multifile) source.reset(new MultiFileSource(a.input, slots, parse_threads));
         else source.reset(new SequentialSource(a.input, slots));
@@ -534,6 +565,25 @@ std::string parent_dir(const std::string& path) {
 }
 
 const char* kTypeNames[] = {"Ftag", "Rtag", "Fflank", "Rflank"};
+
+// annotation.tsv rows are formatted by hand into a large buffer (a row is ~100 bytes; printf per row would cap the writer
+// thread at ~2 M rows/s, below what one GPU produces)
+struct RowWriter {
+    FILE* f; std::vector<char> buf; size_t n = 0; bool failed = false;
+    explicit RowWriter(FILE* file) : f(file), buf(8u << 20) {}
+    void flush() { if (n && std::fwrite(buf.data(), 1, n, f) != n) failed = true; n = 0; }
+    void room(size_t need) { if (n + need > buf.size()) flush(); if (need > buf.size()) buf.resize(need * 2); }
+    void raw(const char* p, size_t len) { room(len); std::memcpy(buf.data() + n, p, len); n += len; }
+    void str(const char* p) { raw(p, std::strlen(p)); }
+    void ch(char c) { buf[n++] = c; }                      // after room()
+    void num(long long v) {                                // after room(24)
+        char tmp[24]; int k = 0;
+        unsigned long long u = v < 0 ? 0ull - static_cast<unsigned long long>(v) : static_cast<unsigned long long>(v);
+        do { tmp[k++] = static_cast<char>('0' + u % 10); u /= 10; } while (u);
+        if (v < 0) buf[n++] = '-';
+        while (k) buf[n++] = tmp[--k];
+    }
+};
 
 int run_annotate(const Args& a, const std::string& out_path) {
     char err[512] = {0};
@@ -579,44 +629,60 @@ int run_annotate(const Args& a, const std::string& out_path) {
     const double ctx_secs = since(t_setup);
     FILE* out = std::fopen(out_path.c_str(), "w");
     if (!out) { std::printf("Error during processing: cannot open %s\n", out_path.c_str()); for (auto* c : ctx) bb_destroy(c); bb_groups_free(gs); return BB_ERR_IO; }
-    static char outbuf[1 << 22];
-    std::setvbuf(out, outbuf, _IOFBF, sizeof outbuf);
+    RowWriter W(out);
 
     Ingest ingest;
     {
         std::string ierr;
-        if (!ingest.open(a, 2 * n_gpus, true, ierr)) { std::printf("Error during processing: %s\n", ierr.c_str()); return BB_ERR_CUDA; }
+        if (!ingest.open(a, 2 * n_gpus, true, ierr)) {
+            std::printf("Error during processing: %s\n", ierr.c_str());
+            ingest.close(); std::fclose(out); for (auto* c : ctx) bb_destroy(c); bb_groups_free(gs);
+            return BB_ERR_CUDA;
+        }
     }
     std::vector<Batch>& slots = ingest.slots;
     BatchSource* source = ingest.source.get();
-    const double setup_secs = since(t_setup);
+    const auto t0 = ingest.t_start;                        // the stream phase starts when the parsers start
+    const double setup_secs = std::chrono::duration<double>(t0 - t_setup).count();
 
     struct Flight { int slot, dev; };
     std::deque<Flight> flight;
     uint64_t total_reads = 0, total_rows = 0, kept = 0, submitted = 0;
     bool header_written = false;
-    auto t0 = std::chrono::steady_clock::now();
-    auto collect_one = [&]() -> int {
+    // labels are looked up once per (group, barcode), not per row
+    std::vector<std::vector<const char*>> labels(n_groups);
+    for (int g = 0; g < n_groups; g++) { labels[g].resize(groups[g].n_barcodes); for (int b = 0; b < groups[g].n_barcodes; b++) labels[g][b] = bb_groups_label(gs, g, b); }
+    auto collect_one = [&](bool write) -> int {
         const Flight f = flight.front(); flight.pop_front();
         uint64_t tag = 0, n_rows = 0; const bb_row* rows = nullptr;
         int r = bb_collect(ctx[f.dev], &tag, &rows, &n_rows);
-        if (r != BB_OK) { std::printf("Error during processing: %s\n", bb_last_error(ctx[f.dev])); return r; }
+        if (r != BB_OK) { if (write) std::printf("Error during processing: %s\n", bb_last_error(ctx[f.dev])); source->release(f.slot); return r; }
+        if (!write) { source->release(f.slot); return BB_OK; }
         const Batch& B = slots[f.slot];
         uint32_t last = UINT32_MAX;
         for (uint64_t i = 0; i < n_rows; i++) {
             const bb_row& w = rows[i];
             if (!header_written) {
-                std::fputs("read_id\tread_len\trel_dist_to_end\tread_start_bar\tread_end_bar\tread_start_flank\tread_end_flank\t"
-                           "bar_start\tbar_end\tmatch_type\tflank_cost\tbarcode_cost\tlabel\tstrand\tcuts\n", out);
+                W.str("read_id\tread_len\trel_dist_to_end\tread_start_bar\tread_end_bar\tread_start_flank\tread_end_flank\t"
+                      "bar_start\tbar_end\tmatch_type\tflank_cost\tbarcode_cost\tlabel\tstrand\tcuts\n");
                 header_written = true;
             }
             if (w.read_idx != last) { kept++; last = w.read_idx; }
-            std::fwrite(B.id_chars.data() + B.id_off[w.read_idx], 1, B.id_off[w.read_idx + 1] - B.id_off[w.read_idx], out);
-            std::fprintf(out, "\t%u\t%lld\t%lld\t%lld\t%lld\t%lld\t%lld\t%lld\t%s\t%d\t%d\t%s\t%s\t\n", w.read_len,
-                         static_cast<long long>(w.rel_dist_to_end), static_cast<long long>(w.read_start_bar), static_cast<long long>(w.read_end_bar),
-                         static_cast<long long>(w.read_start_flank), static_cast<long long>(w.read_end_flank), static_cast<long long>(w.bar_start),
-                         static_cast<long long>(w.bar_end), kTypeNames[w.match_type & 3], w.flank_cost, w.barcode_cost,
-                         bb_groups_label(gs, w.group_idx, w.label_idx), w.strand ? "Rc" : "Fwd");
+            const size_t idl = B.id_off[w.read_idx + 1] - B.id_off[w.read_idx];
+            const char* label = w.label_idx < 0 ? "flank" : labels[w.group_idx][w.label_idx];
+            const size_t ll = std::strlen(label);
+            W.room(idl + ll + 320);
+            W.raw(B.id_chars.data() + B.id_off[w.read_idx], idl);
+            W.ch('\t'); W.num(w.read_len);
+            W.ch('\t'); W.num(w.rel_dist_to_end);
+            W.ch('\t'); W.num(w.read_start_bar); W.ch('\t'); W.num(w.read_end_bar);
+            W.ch('\t'); W.num(w.read_start_flank); W.ch('\t'); W.num(w.read_end_flank);
+            W.ch('\t'); W.num(w.bar_start); W.ch('\t'); W.num(w.bar_end);
+            W.ch('\t'); W.str(kTypeNames[w.match_type & 3]);
+            W.ch('\t'); W.num(w.flank_cost); W.ch('\t'); W.num(w.barcode_cost);
+            W.ch('\t'); W.raw(label, ll);
+            W.ch('\t'); W.str(w.strand ? "Rc" : "Fwd");
+            W.ch('\t'); W.ch('\n');
         }
         total_rows += n_rows;
         source->release(f.slot);
@@ -629,25 +695,35 @@ int run_annotate(const Args& a, const std::string& out_path) {
         if (cur == -1) break;
         if (cur == -2) { std::printf("Error during processing: %s\n", source->error().c_str()); rc = BB_ERR_IO; break; }
         Batch& B = slots[cur];
+        if (B.exc_overflow) {
+            std::printf("Error during processing: out of memory for the list of bases other than A/C/G/T: re-run with --no-pack\n");
+            rc = BB_ERR_INVALID; source->release(cur); break;
+        }
         const int dev = static_cast<int>(submitted % n_gpus);
         size_t on_dev = 0; for (const auto& f : flight) on_dev += f.dev == dev;
-        while (on_dev >= 2 && rc == BB_OK) { const int d0 = flight.front().dev; rc = collect_one(); if (d0 == dev) on_dev--; }   // 2 in flight per GPU
-        if (rc != BB_OK) break;
-        rc = bb_submit(ctx[dev], B.bases, B.offsets, B.n_reads, submitted);
-        if (rc != BB_OK) { std::printf("Error during processing: %s\n", bb_last_error(ctx[dev])); break; }
+        while (on_dev >= 2 && rc == BB_OK) { const int d0 = flight.front().dev; rc = collect_one(true); if (d0 == dev) on_dev--; }   // 2 in flight per GPU
+        if (rc != BB_OK) { source->release(cur); break; }
+        rc = B.packed ? bb_submit_packed(ctx[dev], B.bases, B.bytes, B.exc, B.n_exc, B.offsets, B.n_reads, submitted)
+                      : bb_submit(ctx[dev], B.bases, B.offsets, B.n_reads, submitted);
+        if (rc != BB_OK) { std::printf("Error during processing: %s\n", bb_last_error(ctx[dev])); source->release(cur); break; }
         flight.push_back({cur, dev});
         submitted++;
         total_reads += B.n_reads;
     }
-    while (!flight.empty() && rc == BB_OK) rc = collect_one();
-    if (rc != BB_OK) source->abort();                // unblock the producers
+    while (!flight.empty() && rc == BB_OK) rc = collect_one(true);
+    if (rc != BB_OK) {
+        source->abort();                             // unblock the producers ...
+        while (!flight.empty()) collect_one(false);  // ... and wait for every batch still in flight: its buffers are being read by the workers / the DMA engine
+    }
     source->join();
-    std::fclose(out);
+    W.flush();
+    const bool close_failed = std::fclose(out) != 0;
+    if ((W.failed || close_failed) && rc == BB_OK) { std::printf("Error during processing: write to %s failed\n", out_path.c_str()); rc = BB_ERR_IO; }
     const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     if (rc == BB_OK && a.verbose)
         write_progress_log(parent_dir(out_path), "annotate", {{"Total:", total_reads}, {"Kept:", kept}, {"Dropped:", total_reads - kept}});
     if (rc == BB_OK) {
-        std::printf("Total: %llu  Kept: %llu  Dropped: %llu  (rows: %llu, %.2f s, %.0f reads/s)\n", static_cast<unsigned long long>(total_reads),
+        std::printf("Total: %llu  Kept: %llu  Dropped: %llu  (rows: %llu, %.3f s, %.0f reads/s)\n", static_cast<unsigned long long>(total_reads),
                     static_cast<unsigned long long>(kept), static_cast<unsigned long long>(total_reads - kept),
                     static_cast<unsigned long long>(total_rows), secs, secs > 0 ? total_reads / secs : 0.0);
     }
@@ -676,17 +752,26 @@ int run_fastq_stats(const Args& a) {
         if (cur == -1) break;
         if (cur == -2) { std::printf("Error during processing: %s\n", ingest.source->error().c_str()); rc = 1; ingest.source->abort(); break; }
         const Batch& B = ingest.slots[cur];
+        if (B.exc_overflow) { std::printf("Error during processing: exception list overflow (re-run with --no-pack)\n"); rc = 1; ingest.source->abort(); break; }
+        std::vector<char> text;
+        if (B.packed) {
+            // the packed form decoded the way the device does it (k_unpack_crumbs + k_patch_exceptions): one letter per base set
+            text.resize(B.bytes);
+            for (size_t i = 0; i < B.bytes; i++) text[i] = "ACGT"[(B.bases[i >> 2] >> (2 * (i & 3))) & 3];
+            for (uint64_t q = 0; q < B.n_exc; q++) text[B.exc[q] >> 4] = "XACMGRSVTWYHKDBN"[B.exc[q] & 15];
+        }
+        const char* seqs = B.packed ? text.data() : reinterpret_cast<const char*>(B.bases);
         for (uint32_t r = 0; r < B.n_reads; r++) {
             mix(B.id_chars.data() + B.id_off[r], B.id_off[r + 1] - B.id_off[r]);
-            mix(reinterpret_cast<const char*>(B.bases) + B.offsets[r], B.offsets[r + 1] - B.offsets[r]);
+            mix(seqs + B.offsets[r], B.offsets[r + 1] - B.offsets[r]);
         }
         n += B.n_reads; bases += B.bytes; batches++;
         ingest.source->release(cur);
     }
     const char* kind = ingest.parallel ? "parallel" : ingest.multifile ? "multifile" : "sequential";
     ingest.close();
-    if (rc == 0) std::printf("records=%llu bases=%llu fnv=%016llx batches=%llu reader=%s\n", static_cast<unsigned long long>(n), static_cast<unsigned long long>(bases),
-                             static_cast<unsigned long long>(h), static_cast<unsigned long long>(batches), kind);
+    if (rc == 0) std::printf("records=%llu bases=%llu fnv=%016llx batches=%llu reader=%s form=%s\n", static_cast<unsigned long long>(n), static_cast<unsigned long long>(bases),
+                             static_cast<unsigned long long>(h), static_cast<unsigned long long>(batches), kind, a.no_pack ? "bytes" : "packed");
     return rc;
 }
 

@@ -13,6 +13,7 @@
 #include <chrono>
 #include <condition_variable>
 #include <functional>
+#include <memory>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -66,19 +67,20 @@ constexpr uint64_t kExcEmpty = ~0ull;                             // filler of a
 constexpr size_t kExcBlock = 256;                                 // entries a work item takes from the shared list at a time
 
 struct ExcWriter {
-    uint64_t* buf; size_t cap; std::atomic<uint64_t>* next; std::atomic<bool>* overflow;
+    uint64_t* buf; size_t cap; std::atomic<uint64_t>* next; std::atomic<bool>* overflow;   // next == nullptr: one writer, entries [cur, end) are its own
     size_t cur = 0, end = 0;
     bool dead = false;                                            // the list is full: the batch will be re-packed as nibbles
     void push(uint64_t v) {
         if (dead) return;
         if (cur == end) {
+            if (!next) { dead = true; return; }
             const uint64_t b = next->fetch_add(kExcBlock);
             if (b + kExcBlock > cap) { overflow->store(true); next->fetch_sub(kExcBlock); dead = true; return; }
             cur = static_cast<size_t>(b); end = cur + kExcBlock;
         }
         buf[cur++] = v;
     }
-    void finish() { while (cur < end) buf[cur++] = kExcEmpty; }
+    void finish() { if (next) while (cur < end) buf[cur++] = kExcEmpty; }
 };
 
 // base set -> crumb; 0x80 marks "not a single base": goes to the exception list
@@ -145,47 +147,51 @@ class Pool {
     double run(int n_chunks, const std::function<void(int)>& fn) {
         std::unique_lock<std::mutex> call(call_mu_);              // one parallel region at a time
         const auto t0 = std::chrono::steady_clock::now();
+        // every region has its OWN job object: a worker that drew its last (out-of-range) index from an earlier region and was
+        // preempted before looking at it can only ever touch that earlier region's counters
+        auto job = std::make_shared<Job>();
+        job->fn = &fn; job->total = n_chunks; job->pending.store(n_chunks);
         {
             std::lock_guard<std::mutex> lk(mu_);
-            fn_ = &fn; next_.store(0); total_ = n_chunks; pending_ = n_chunks; gen_++;
+            cur_ = job; gen_++;
         }
         cv_.notify_all();
-        work();
+        work(*job);
         std::unique_lock<std::mutex> lk(mu_);
-        done_cv_.wait(lk, [&] { return pending_ == 0; });
-        fn_ = nullptr;
+        done_cv_.wait(lk, [&] { return job->pending.load() == 0; });
+        cur_.reset();
         return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     }
     int size() const { return static_cast<int>(workers_.size()) + 1; }
 
   private:
-    void work() {
+    struct Job { const std::function<void(int)>* fn = nullptr; std::atomic<int> next{0}; int total = 0; std::atomic<int> pending{0}; };
+    void work(Job& j) {
         for (;;) {
-            const int c = next_.fetch_add(1);
-            if (c >= total_) break;
-            (*fn_)(c);
-            std::lock_guard<std::mutex> lk(mu_);
-            if (--pending_ == 0) done_cv_.notify_all();
+            const int c = j.next.fetch_add(1);
+            if (c >= j.total) break;
+            (*j.fn)(c);
+            if (j.pending.fetch_sub(1) == 1) { std::lock_guard<std::mutex> lk(mu_); done_cv_.notify_all(); }
         }
     }
     void loop() {
         uint64_t seen = 0;
         for (;;) {
+            std::shared_ptr<Job> j;
             {
                 std::unique_lock<std::mutex> lk(mu_);
                 cv_.wait(lk, [&] { return stop_ || gen_ != seen; });
                 if (stop_) return;
                 seen = gen_;
+                j = cur_;
             }
-            work();
+            if (j) work(*j);
         }
     }
     std::vector<std::thread> workers_;
     std::mutex mu_, call_mu_;
     std::condition_variable cv_, done_cv_;
-    const std::function<void(int)>* fn_ = nullptr;
-    std::atomic<int> next_{0};
-    int total_ = 0, pending_ = 0;
+    std::shared_ptr<Job> cur_;
     uint64_t gen_ = 0;
     bool stop_ = false;
 };
@@ -195,6 +201,27 @@ Pool& pool(int threads) {
     return p;
 }
 }  // namespace
+
+bool crumbs_append(const uint8_t* src, size_t n, uint8_t* dst, uint64_t* pos, uint64_t* exc, size_t exc_cap, size_t* n_exc, const uint8_t* code) {
+    static const bool avx2 = __builtin_cpu_supports("avx2");
+    std::atomic<bool> over{false};
+    ExcWriter w{exc, exc_cap, nullptr, &over};
+    w.cur = *n_exc; w.end = exc_cap;
+    size_t p = static_cast<size_t>(*pos), i = 0;
+    // head: fill up the byte the previous read left partly used (its missing crumbs are still zero)
+    for (; i < n && (p & 3); i++, p++) {
+        const uint8_t v = code[src[i]], cr = kCrumbOfSet[v];
+        if (cr & 0x80) w.push(static_cast<uint64_t>(p) << 4 | v);
+        else dst[p >> 2] = static_cast<uint8_t>(dst[p >> 2] | cr << (2 * (p & 3)));
+    }
+    // body: from here on the stream is byte aligned; the tail of this read leaves the last byte partly used (upper crumbs zero)
+    if (i < n) {
+        if (avx2) crumbs_avx2(src + i, p, n - i, dst + (p >> 2), code, w); else crumbs_scalar(src + i, p, n - i, dst + (p >> 2), code, w);
+        p += n - i;
+    }
+    *pos = p; *n_exc = w.cur;
+    return !w.dead;
+}
 
 int pack_default_threads() {
     if (const char* e = std::getenv("BB_PACK_THREADS")) { const int v = std::atoi(e); if (v >= 1) return std::min(v, 64); }   // tuning knob

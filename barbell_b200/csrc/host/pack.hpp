@@ -13,5 +13,9 @@ double pack_nibbles(const uint8_t* src, size_t n, uint8_t* dst, const uint8_t* c
 // *overflow = the list was too small (the output is then unusable).  Returns the packing seconds like pack_nibbles.
 double pack_crumbs(const uint8_t* src, size_t n, uint8_t* dst, uint64_t* exc, size_t exc_cap, size_t* n_exc, bool* overflow,
                    const uint8_t* code, int threads);
+// Appends n bases to a gapless 2-bit stream (base i lives in dst[i >> 2], bits 2 * (i & 3)): *pos = bases in the stream so far, updated;
+// exceptions are appended at exc[*n_exc ...) with their position IN THE STREAM.  One writer per stream; false = exception list full.
+// (For producers that pack while they parse: the bytes of a read are touched once, while they are still in the cache.)
+bool crumbs_append(const uint8_t* src, size_t n, uint8_t* dst, uint64_t* pos, uint64_t* exc, size_t exc_cap, size_t* n_exc, const uint8_t* code);
 int pack_default_threads();
 }  // namespace bb

@@ -146,6 +146,12 @@ int  bb_fetch_rows(bb_ctx *ctx, bb_row *rows, uint64_t rows_cap, uint64_t *n_row
 #define BB_MAX_INFLIGHT 4
 int  bb_submit(bb_ctx *ctx, const uint8_t *bases, const uint64_t *offsets, uint32_t n_reads, uint64_t batch_tag);
 int  bb_collect(bb_ctx *ctx, uint64_t *batch_tag, const bb_row **rows, uint64_t *n_rows);
+/* bb_submit for a host that packs while it parses (the FASTQ reader of `barbell annotate` does: src/io/io.rs:27-32 -> pinned ring):
+   `crumbs` is the 2-bit wire format of the batch's n_bases bases as ONE gapless stream (built read by read with
+   bb_pack_crumbs_append), exc[0, n_exc) its exception entries, offsets[n_reads + 1] the reads' base offsets (offsets[n_reads] ==
+   n_bases).  A quarter of the bytes cross PCIe and no host core touches the bases again.  Ownership as for bb_submit. */
+int  bb_submit_packed(bb_ctx *ctx, const uint8_t *crumbs, uint64_t n_bases, const uint64_t *exc, uint64_t n_exc,
+                      const uint64_t *offsets, uint32_t n_reads, uint64_t batch_tag);
 
 /* ProgressTracker counters (annotator.rs:109-113): out = {total reads, reads with >=1 row, reads with none} */
 int  bb_counters(const bb_ctx *ctx, uint64_t out[3]);
@@ -170,6 +176,10 @@ int  bb_pack_nibbles(const uint8_t *src, uint64_t n, uint8_t *dst);
    A C G T (any case, U as T) = 0 1 2 3, dst holds (n+3)/4 bytes; every other byte has crumb 0 and an entry (position << 4 | set())
    in exc[0, *n_exc), appended in blocks whose unused entries are ~0.  BB_ERR_OVERFLOW when exc_cap entries do not suffice */
 int  bb_pack_crumbs(const uint8_t *src, uint64_t n, uint8_t *dst, uint64_t *exc, uint64_t exc_cap, uint64_t *n_exc);
+/* the same format built incrementally: appends n bases at base position *pos of the stream in dst (base i lives in dst[i >> 2], bits
+   2 * (i & 3); dst bytes past the stream must be zero or unwritten), advances *pos, appends exception entries (stream position << 4 |
+   set()) at exc[*n_exc ...) and advances *n_exc.  One writer per stream.  BB_ERR_OVERFLOW when exc_cap entries do not suffice. */
+int  bb_pack_crumbs_append(const uint8_t *src, uint64_t n, uint8_t *dst, uint64_t *pos, uint64_t *exc, uint64_t exc_cap, uint64_t *n_exc);
 
 /* ---- the stages that consume annotation.tsv (host side, no GPU): filter, inspect, trim -- so that `barbell kit` runs the
  *      reference's whole pipeline, src/kits/use_kit.rs:11-109 ---- */

@@ -120,3 +120,36 @@ def test_pack_crumbs_matches_numpy():
     exc = np.full(cap + 4096, 0x5A5A5A5A5A5A5A5A, np.uint64)
     assert bb.lib().bb_pack_crumbs(src.ctypes.data, n, dst.ctypes.data, exc.ctypes.data, cap, C.byref(n_exc)) == -3
     assert (exc[cap:] == np.uint64(0x5A5A5A5A5A5A5A5A)).all() and n_exc.value <= cap
+
+
+def test_pack_crumbs_append_builds_the_same_stream_read_by_read():
+    """bb_pack_crumbs_append (what the FASTQ reader of the CLI calls per sequence line): reads of every length mod 4 / 32 / 128
+    appended one after the other must give the byte stream and the exception entries of one bb_pack_crumbs call over the
+    concatenation; a full exception list is reported."""
+    import ctypes as C
+    import numpy as np
+    rnd = np.random.default_rng(12)
+    lens = [0, 1, 2, 3, 5, 31, 32, 33, 127, 128, 129, 130, 131, 255, 1000, 4097] + [int(x) for x in rnd.integers(0, 700, 200)]
+    reads = []
+    for n in lens:
+        r = rnd.choice(np.frombuffer(b"ACGTacgt", np.uint8), n)
+        odd = rnd.random(n) < 0.02
+        r[odd] = rnd.choice(np.frombuffer(b"NnRYKM-x*", np.uint8), int(odd.sum()))
+        reads.append(r)
+    allb = np.concatenate(reads)
+    n = len(allb)
+    want = np.zeros((n + 3) // 4 + 1, np.uint8); exc_w = np.zeros(n // 8 + 1024, np.uint64); nw = C.c_uint64(0)
+    assert bb.lib().bb_pack_crumbs(allb.ctypes.data, n, want.ctypes.data, exc_w.ctypes.data, len(exc_w), C.byref(nw)) == 0
+    exc_w = exc_w[:nw.value]; exc_w = np.sort(exc_w[exc_w != np.uint64(0xFFFFFFFFFFFFFFFF)])
+    dst = np.zeros((n + 3) // 4 + 64, np.uint8); exc = np.full(len(exc_w) + 8, 0x5A5A5A5A5A5A5A5A, np.uint64)
+    pos, ne = C.c_uint64(0), C.c_uint64(0)
+    for r in reads:
+        r = np.ascontiguousarray(r)
+        assert bb.lib().bb_pack_crumbs_append(r.ctypes.data if len(r) else None, len(r), dst.ctypes.data, C.byref(pos), exc.ctypes.data, len(exc_w), C.byref(ne)) == 0
+    assert pos.value == n and ne.value == len(exc_w)
+    assert (dst[:(n + 3) // 4] == want[:(n + 3) // 4]).all() and (dst[(n + 3) // 4:] == 0).all()
+    assert (exc[:ne.value] == exc_w).all()                      # appended in stream order
+    assert (exc[len(exc_w):] == np.uint64(0x5A5A5A5A5A5A5A5A)).all()
+    r = np.frombuffer(b"ACGNNNNT", np.uint8).copy()
+    pos, ne = C.c_uint64(0), C.c_uint64(0)
+    assert bb.lib().bb_pack_crumbs_append(r.ctypes.data, 8, dst.ctypes.data, C.byref(pos), exc.ctypes.data, 2, C.byref(ne)) == -3

@@ -24,6 +24,10 @@ def stats(paths, *extra, want_reader=None):
     kv = dict(x.split("=") for x in r.stdout.split())
     if want_reader:
         assert kv["reader"] == want_reader, kv
+    assert kv["form"] == ("bytes" if "--no-pack" in extra else "packed")
+    if "--no-pack" not in extra:
+        # the default form packs every sequence line to 2 bits per base + exceptions while parsing; decoded, it must hash the same
+        assert stats(paths, *extra, "--no-pack", want_reader=want_reader) == (int(kv["records"]), int(kv["bases"]), int(kv["fnv"], 16))
     return int(kv["records"]), int(kv["bases"]), int(kv["fnv"], 16)
 
 
@@ -51,6 +55,11 @@ def test_reader_variants(tmp_path):
     with gzip.open(pb, "wt") as f:
         f.write(text(recs[25:]) + "\n\n")
     assert stats([pa, pb]) == want
+    # blank lines between records (one or several) are skipped by every reader alike
+    p6 = tmp_path / "blank.fastq"
+    p6.write_text(text(recs[:10]) + "\n" + text(recs[10:20]) + "\n\n" + text(recs[20:]) + "\n\n\n")
+    assert stats([p6], "--single-reader", want_reader="sequential") == want
+    assert stats([p6], "--chunk-kb", "2", "-t", "4", want_reader="parallel") == want
     # errors: truncated record, missing file -> message, non-zero exit of this debugging subcommand
     p5 = tmp_path / "bad.fastq"; p5.write_text("@r1\nACGT\n+\n")
     r = subprocess.run([EXE, "fastq-stats", "-i", str(p5)], capture_output=True, text=True)

@@ -458,3 +458,36 @@ def test_global_window_queue_overflow_reruns_the_batch_exactly(monkeypatch):
     finally:
         an.close()
     assert len(want) > 2000
+
+
+def test_submit_packed_equals_submit():
+    """bb_submit_packed: the batch arrives as the 2-bit stream + exception list built read by read (bb_pack_crumbs_append, as the
+    CLI's FASTQ reader does); rows must equal those of the byte form, and the library must move about a quarter of the bytes."""
+    gs = bb.GroupSet.from_kit("SQK-NBD114-96")
+    b, o, _ = synth.make_reads(gs.as_dicts(), 2500, (0, 3000), seed=45, n_frac=0.002)
+    b = b.copy()
+    rnd = np.random.default_rng(8)
+    idx = rnd.integers(0, len(b), 2000)
+    b[idx] = rnd.choice(np.frombuffer(b"acgtnRYKMryU-*x", np.uint8), len(idx))
+    want = O.demux_batch(gs.as_dicts(), b, o)
+    n = len(b)
+    crumbs = np.zeros((n + 3) // 4 + 64, np.uint8); exc = np.zeros(n // 16 + 64, np.uint64)
+    pos, ne = C.c_uint64(0), C.c_uint64(0)
+    for r in range(len(o) - 1):
+        lo, hi = int(o[r]), int(o[r + 1])
+        assert bb.lib().bb_pack_crumbs_append(b[lo:].ctypes.data if hi > lo else None, hi - lo, crumbs.ctypes.data, C.byref(pos), exc.ctypes.data,
+                                              len(exc), C.byref(ne)) == 0
+    assert pos.value == n
+    offs = np.ascontiguousarray(o, dtype=np.uint64)
+    an = _annotator(gs)
+    try:
+        h0 = an.h2d_bytes()
+        an.submit_packed(crumbs.ctypes.data, n, exc.ctypes.data, ne.value, offs.ctypes.data, len(o) - 1, tag=5)
+        tag, got = an.collect()
+        assert tag == 5 and got.tobytes() == want.tobytes()
+        assert an.h2d_bytes() - h0 < 0.3 * n + 8 * len(o) + 64
+        an.submit_packed(crumbs.ctypes.data, 0, None, 0, np.zeros(1, np.uint64).ctypes.data, 0, tag=6)      # empty batch
+        tag, got = an.collect()
+        assert tag == 6 and len(got) == 0
+    finally:
+        an.close()
