@@ -80,7 +80,7 @@ static double lodhi_all_match(int l) {   // reference searcher.rs:229-239 with t
 struct GroupTables {          // device copies for all groups of a ctx (shared by its engines)
     std::vector<DevGroup> host;
     DBuf d_groups, d_blob, d_code;
-    int n = 0, max_trace_cols = 0, max_nw = 1, max_region = 0, max_bar_len = 0, max_own_rows = 0;
+    int n = 0, max_trace_cols = 0, max_nw = 1, max_region = 0, max_bar_len = 0, max_own_rows = 0, max_k = 0;
     void release() { d_groups.release(); d_blob.release(); d_code.release(); host.clear(); n = 0; }
 };
 
@@ -93,8 +93,12 @@ struct Engine {
     uint64_t launches = 0, h2d_bytes = 0;   // kernels launched / bytes copied host -> device by this engine
     // device buffers
     DBuf d_bases, d_offsets, d_nch, d_chunk_base, d_tile_first, d_tile_span, d_windows, d_entries, d_sorted, d_cub, d_flags, d_hitkeys, d_hits, d_hist, d_rows, d_valid, d_rows_out, d_hits6;
-    DBuf d_counters;                     // [0] n_entries (u32) [2] n_selected (u32) [4..5] kept reads (u64)
-    uint32_t entries_cap = 0;
+    DBuf d_counters;                     // u32[16]: [0] n_entries [1] entries after unique [2] n_hits [3] n_rows [4..5] kept reads (u64) [6] n_windows
+                                         //          [7] filter queue overflow [8] hit list overflow [9] entry slot overflow
+    DBuf d_slots, d_slot_cnt, d_nh, d_hit_base;   // slot path: per-read entry slots / counts, reported matches per read, their prefix sum
+    uint32_t entries_cap = 0, hits_cap = 0;
+    int slot_overflows = 0;
+    int glue = 1;                        // 1 = per-read slots, no host round trips (default); 0 = global radix sort path (BB_GLUE=sort; also the fallback)
     bool use_filter = true;              // bb_opts.flags bit 0 disables the pre-filter (exact scan everywhere)
     int pack_mode = 0;                   // bb_opts.flags bit 1: nibble-pack the bases on the host before the PCIe copy (1); bit 2: 2 bits per base
                                          // + an exception list (2; falls back to 1 for good when a batch has too many non-ACGT bytes)
@@ -131,7 +135,7 @@ struct Engine {
     void destroy() {
         cudaSetDevice(device);
         for (DBuf* b : {&d_bases, &d_offsets, &d_nch, &d_chunk_base, &d_tile_first, &d_tile_span, &d_windows, &d_entries, &d_sorted, &d_cub, &d_flags, &d_hitkeys, &d_hits, &d_hist, &d_rows,
-                        &d_valid, &d_rows_out, &d_hits6, &d_counters})
+                        &d_valid, &d_rows_out, &d_hits6, &d_counters, &d_slots, &d_slot_cnt, &d_nh, &d_hit_base})
             b->release();
         if (h_counters) cudaFreeHost(h_counters);
         if (h_rows) cudaFreeHost(h_rows);
@@ -185,11 +189,21 @@ struct Engine {
         *n_rows = 0;
         for (float& f : stage_ms) f = 0.f;
         if (n_reads == 0 || total == 0) return BB_OK;
-        const uint64_t total16 = (total + 15) & ~15ull;
-        uint32_t* d_cnt = d_counters.as<uint32_t>();
-        BB_CUDA(cudaEventRecord(ev[0], st));
+        bool force_exact = false;
+        // slot path unless the slots of this many reads would be out of proportion to the batch (very short reads) or a flank match
+        // alone fills a good part of a read's slots (2k + 1 sub-threshold positions, times overlapping windows: large automatic k)
+        if (glue == 1 && gt->max_k <= 8 && static_cast<uint64_t>(n_reads) * kSlotCap * 8 <= std::max<uint64_t>(total, 64u << 20)) {
+            int redo = 0;
+            const int rc = run_slots(bases, offsets, n_reads, total, st, n_rows, &redo);
+            if (rc != BB_OK || redo == 0) return rc;
+            force_exact = (redo & 1) != 0;           // filter queue overflow: exact scan; slot / hit list overflow: sorted path
+            last_rows = 0; last_hits = 0; last_kept = 0; *n_rows = 0;
+        }
+        return run_sorted(bases, offsets, n_reads, total, st, n_rows, force_exact);
+    }
 
-        // ---- chunk index: reads -> chunks of kChunk bases (a chunk never straddles two reads) ----
+    // chunk index: reads -> chunks of kChunk bases (a chunk never straddles two reads); returns the number of scan tiles
+    int chunk_index(const uint64_t* offsets, uint32_t n_reads, uint64_t total, cudaStream_t st, unsigned* n_tiles_out) {
         const uint64_t max_chunks = total / kChunk + n_reads;
         const unsigned n_tiles = static_cast<unsigned>((max_chunks + kScanThreads - 1) / kScanThreads);
         BB_CUDA(d_nch.ensure(static_cast<size_t>(n_reads + 1) * 4));
@@ -207,10 +221,184 @@ struct Engine {
         k_tile_index<<<(n_tiles + 255) / 256, 256, 0, st>>>(d_chunk_base.as<uint32_t>(), offsets, n_reads, n_tiles, d_tile_first.as<uint32_t>(), d_tile_span.as<uint64_t>());
         launches++;
         BB_CUDA(cudaGetLastError());
+        *n_tiles_out = n_tiles;
+        return BB_OK;
+    }
+
+    // K1 for every group into whatever entry store `A` names; filtered = the pre-filter ran for at least one group
+    int launch_scans(ScanArgs A, unsigned n_tiles, uint64_t total, bool force_exact, cudaStream_t st, bool* filtered_out) {
+        uint32_t* d_cnt = d_counters.as<uint32_t>();
+        bool filtered = false;
+        for (int g = 0; g < gt->n; g++) {
+            const DevGroup& G = gt->host[g];
+            A.group = g; A.strand_xor = (pol & kPolS6RcFirst) ? 1 : 0;
+            if (G.f_on && use_filter && !force_exact) {
+                // pre-filter (both strands in one 32-bit word) + exact verification of the candidate and read-end windows
+                uint32_t win_cap = static_cast<uint32_t>(std::min<uint64_t>(total / 48 + (1u << 20), 1u << 30));
+                if (const char* wc = std::getenv("BB_WIN_CAP")) win_cap = static_cast<uint32_t>(std::max(1, std::atoi(wc)));   // test knob: force the overflow fall-back
+                BB_CUDA(d_windows.ensure(static_cast<size_t>(win_cap) * 8));
+                BB_CUDA(cudaMemsetAsync(d_cnt + 6, 0, 4, st));          // [6] window count ([7] overflow flag is sticky per attempt)
+                int halo_l = 0, halo_r = 0;
+                filter_halos(G, halo_l, halo_r);
+                FilterArgs F{A, d_windows.as<uint64_t>(), d_cnt + 6, win_cap, d_cnt + 7, halo_l, halo_r};
+                const size_t smem = filter_smem_bytes(halo_l, halo_r);
+                BB_CUDA(cudaFuncSetAttribute(k_flank_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+                k_flank_filter<<<n_tiles, kScanThreads, smem, st>>>(F, G);
+                launches++;
+                VerifyArgs V{A, d_windows.as<uint64_t>(), d_cnt + 6, d_cnt + 7, win_cap};
+                if (G.nw == 1) k_flank_verify<1><<<148 * 16, 128, 0, st>>>(V, G);
+                else k_flank_verify<2><<<148 * 16, 128, 0, st>>>(V, G);
+                launches++;
+                filtered = true;
+                BB_CUDA(cudaGetLastError());
+                continue;
+            }
+            const size_t smem = 128 + 2 * 256 * G.nw * sizeof(uint64_t) + static_cast<size_t>(kScanThreads) * kChunk + 2 * static_cast<size_t>(G.warm) + 48;
+            if (G.nw == 1) {
+                BB_CUDA(cudaFuncSetAttribute(k_flank_scan<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+                k_flank_scan<1><<<n_tiles, kScanThreads, smem, st>>>(A, G);
+            } else {
+                BB_CUDA(cudaFuncSetAttribute(k_flank_scan<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+                k_flank_scan<2><<<n_tiles, kScanThreads, smem, st>>>(A, G);
+            }
+            launches++;
+            BB_CUDA(cudaGetLastError());
+        }
+        *filtered_out = filtered;
+        return BB_OK;
+    }
+
+    // K2b .. K4 + ordered row compaction over the hit list d_hitkeys[0, *(d_cnt + 2)); every kernel reads the count on the device,
+    // grids and buffers are sized for `hits_bound` hits
+    int launch_tail(const uint8_t* bases, const uint64_t* offsets, uint32_t hits_bound, cudaStream_t st) {
+        uint32_t* d_cnt = d_counters.as<uint32_t>();
+        BB_CUDA(d_hits.ensure(static_cast<size_t>(hits_bound) * sizeof(Hit)));
+        {
+            TraceArgs T{};
+            const unsigned blocks = std::min<unsigned>((hits_bound + 63) / 64, 148 * 4);
+            T.n_slots = blocks * 64;
+            BB_CUDA(d_hist.ensure(static_cast<size_t>(gt->max_trace_cols + 2) * 2 * gt->max_nw * 8 * T.n_slots));
+            T.bases = bases; T.offsets = offsets; T.hit_keys = d_hitkeys.as<uint64_t>(); T.n_hits = d_cnt + 2;
+            T.groups = d_groups(); T.hist = d_hist.as<uint64_t>(); T.hits = d_hits.as<Hit>(); T.pol = pol;
+            k_trace<<<blocks, 64, 0, st>>>(T);
+            launches++;
+            BB_CUDA(cudaGetLastError());
+        }
+        BB_CUDA(cudaEventRecord(ev[3], st));
+        BB_CUDA(d_rows.ensure(static_cast<size_t>(hits_bound) * sizeof(bb_row)));
+        BB_CUDA(d_valid.ensure(hits_bound));
+        BB_CUDA(cudaMemsetAsync(d_valid.p, 0, hits_bound, st));
+        {
+            BarArgs B{};
+            B.bases = bases; B.offsets = offsets; B.hits = d_hits.as<Hit>(); B.n_hits = d_cnt + 2; B.groups = d_groups();
+            B.code = gt->d_code.as<uint8_t>(); B.prm = prm; B.rows = d_rows.as<bb_row>(); B.row_valid = d_valid.as<uint8_t>();
+            B.sh_rows = gt->max_bar_len; B.pol = pol;
+            // one launch per record format that the geometry can need; each takes the flank matches of its region lengths
+            B.rn_lo = -1; B.rn_hi = 48;
+            int rc = launch_barcode<1, true>(B, hits_bound, st);
+            if (rc != BB_OK) return rc;
+            if (gt->max_region > 48) {
+                B.rn_lo = 48; B.rn_hi = 64;
+                rc = launch_barcode<1, false>(B, hits_bound, st);
+                if (rc != BB_OK) return rc;
+            }
+            if (gt->max_region > 64) {   // large automatic k (custom 115-bp tags)
+                B.rn_lo = 64; B.rn_hi = 1 << 20;
+                rc = launch_barcode<3, false>(B, hits_bound, st);
+                if (rc != BB_OK) return rc;
+            }
+        }
+        BB_CUDA(cudaEventRecord(ev[4], st));
+        unsigned long long* d_kept = reinterpret_cast<unsigned long long*>(d_cnt + 4);
+        k_collapse<<<(hits_bound + 127) / 128, 128, 0, st>>>(d_hits.as<Hit>(), d_cnt + 2, d_rows.as<bb_row>(), d_valid.as<uint8_t>(), d_kept);
+        launches++;
+        BB_CUDA(cudaGetLastError());
+        BB_CUDA(d_rows_out.ensure(static_cast<size_t>(hits_bound) * sizeof(bb_row)));
+        {
+            size_t tmp = 0;
+            cub::DeviceSelect::Flagged(nullptr, tmp, d_rows.as<bb_row>(), d_valid.as<uint8_t>(), d_rows_out.as<bb_row>(), d_cnt + 3, static_cast<int>(hits_bound), st);
+            BB_CUDA(d_cub.ensure(tmp));
+            BB_CUDA(cub::DeviceSelect::Flagged(d_cub.p, tmp, d_rows.as<bb_row>(), d_valid.as<uint8_t>(), d_rows_out.as<bb_row>(), d_cnt + 3, static_cast<int>(hits_bound), st));
+        }
+        return BB_OK;
+    }
+
+    // Slot path: no host round trip before the end of the batch.  *redo: bit 0 = the filter's window queue overflowed (re-run with the
+    // exact scan), bit 1 = a read had more entries than slots or the batch more matches than the hit list holds (re-run sorted).
+    int run_slots(const uint8_t* bases, const uint64_t* offsets, uint32_t n_reads, uint64_t total, cudaStream_t st, uint64_t* n_rows, int* redo) {
+        const uint64_t total16 = (total + 15) & ~15ull;
+        uint32_t* d_cnt = d_counters.as<uint32_t>();
+        BB_CUDA(cudaEventRecord(ev[0], st));
+        unsigned n_tiles = 0;
+        int rc = chunk_index(offsets, n_reads, total, st, &n_tiles);
+        if (rc != BB_OK) return rc;
+        BB_CUDA(d_slots.ensure(static_cast<size_t>(n_reads) * kSlotCap * 8));
+        BB_CUDA(d_slot_cnt.ensure(static_cast<size_t>(n_reads + 1) * 4));
+        BB_CUDA(d_nh.ensure(static_cast<size_t>(n_reads + 1) * 4));
+        BB_CUDA(d_hit_base.ensure(static_cast<size_t>(n_reads + 1) * 4));
+        BB_CUDA(cudaMemsetAsync(d_cnt, 0, 64, st));
+        BB_CUDA(cudaMemsetAsync(d_slot_cnt.p, 0, static_cast<size_t>(n_reads + 1) * 4, st));
+        ScanArgs A{};
+        A.bases = bases; A.offsets = offsets; A.n_reads = n_reads; A.total16 = total16;
+        A.chunk_base = d_chunk_base.as<uint32_t>(); A.tile_first = d_tile_first.as<uint32_t>(); A.tile_span = d_tile_span.as<uint64_t>();
+        A.slots = d_slots.as<uint64_t>(); A.slot_cnt = d_slot_cnt.as<uint32_t>(); A.slot_cap = kSlotCap; A.slot_overflow = d_cnt + 9;
+        uint32_t slot_cap = kSlotCap;
+        if (const char* sc = std::getenv("BB_SLOT_CAP")) slot_cap = static_cast<uint32_t>(std::min(kSlotCap, std::max(1, std::atoi(sc))));   // test knob
+        A.slot_cap = slot_cap;
+        bool filtered = false;
+        rc = launch_scans(A, n_tiles, total, false, st, &filtered);
+        if (rc != BB_OK) return rc;
+        BB_CUDA(cudaEventRecord(ev[1], st));
+        // per-read resolve (sort + unique + local minima inside one warp), prefix sum of the match counts, gather in read order
+        k_read_resolve<<<(n_reads + kResolveWarps - 1) / kResolveWarps, kResolveWarps * 32, 0, st>>>(
+            d_slots.as<uint64_t>(), d_slot_cnt.as<uint32_t>(), n_reads, offsets, d_groups(), d_nh.as<uint32_t>(), pol);
+        launches++;
+        BB_CUDA(cudaMemsetAsync(d_nh.as<uint32_t>() + n_reads, 0, 4, st));
+        {
+            size_t tmp = 0;
+            cub::DeviceScan::ExclusiveSum(nullptr, tmp, d_nh.as<uint32_t>(), d_hit_base.as<uint32_t>(), static_cast<int>(n_reads + 1), st);
+            BB_CUDA(d_cub.ensure(tmp));
+            BB_CUDA(cub::DeviceScan::ExclusiveSum(d_cub.p, tmp, d_nh.as<uint32_t>(), d_hit_base.as<uint32_t>(), static_cast<int>(n_reads + 1), st));
+        }
+        if (hits_cap < n_reads * 4ull + 4096) hits_cap = static_cast<uint32_t>(std::min<uint64_t>(n_reads * 4ull + 4096, 1u << 28));
+        uint32_t cap = hits_cap;
+        if (const char* hc = std::getenv("BB_HITS_CAP")) cap = static_cast<uint32_t>(std::max(1, std::atoi(hc)));   // test knob
+        BB_CUDA(d_hitkeys.ensure(static_cast<size_t>(cap) * 8));
+        k_hits_gather<<<(n_reads + 255) / 256, 256, 0, st>>>(d_slots.as<uint64_t>(), d_nh.as<uint32_t>(), d_hit_base.as<uint32_t>(), n_reads, cap,
+                                                             d_hitkeys.as<uint64_t>(), d_cnt + 2, d_cnt + 8);
+        launches++;
+        BB_CUDA(cudaGetLastError());
+        BB_CUDA(cudaEventRecord(ev[2], st));
+        rc = launch_tail(bases, offsets, cap, st);
+        if (rc != BB_OK) return rc;
+        BB_CUDA(cudaMemcpyAsync(h_counters, d_cnt, 64, cudaMemcpyDeviceToHost, st));
+        rc = finish_timing(st, 5);
+        if (rc != BB_OK) return rc;
+        last_windows = h_counters[6];
+        *redo = ((filtered && h_counters[7]) ? 1 : 0) | ((h_counters[8] || h_counters[9]) ? 2 : 0);
+        if (h_counters[8]) hits_cap = static_cast<uint32_t>(std::min<uint64_t>(static_cast<uint64_t>(hits_cap) * 4, 1u << 28));
+        if (h_counters[9] && ++slot_overflows >= 3) glue = 0;     // repeat-rich input keeps overflowing the slots: stay on the sorted path
+        if (*redo) return BB_OK;
+        last_hits = h_counters[2];
+        last_rows = h_counters[3];
+        std::memcpy(&last_kept, h_counters + 4, 8);
+        *n_rows = last_rows;
+        return BB_OK;
+    }
+
+    // Sorted path: global entry list, radix sort, unique, k_resolve, select -- with a host round trip for every count.  Kept for batches
+    // of very short reads (slots per read would dwarf the batch), BB_GLUE=sort, and as the fall-back when a slot path capacity overflows.
+    int run_sorted(const uint8_t* bases, const uint64_t* offsets, uint32_t n_reads, uint64_t total, cudaStream_t st, uint64_t* n_rows, bool force_exact_in) {
+        const uint64_t total16 = (total + 15) & ~15ull;
+        uint32_t* d_cnt = d_counters.as<uint32_t>();
+        BB_CUDA(cudaEventRecord(ev[0], st));
+        unsigned n_tiles = 0;
+        int rc = chunk_index(offsets, n_reads, total, st, &n_tiles);
+        if (rc != BB_OK) return rc;
 
         // ---- K1: flank scan, one launch per group ----
         uint32_t n_entries = 0;
-        bool force_exact = false, any_filtered = false;
+        bool force_exact = force_exact_in, any_filtered = false;
         for (int attempt = 0; attempt < 5; attempt++) {
             if (entries_cap == 0) {
                 uint64_t want = std::max<uint64_t>(1u << 20, static_cast<uint64_t>(n_reads) * 32);
@@ -218,48 +406,12 @@ struct Engine {
             }
             BB_CUDA(d_entries.ensure(static_cast<size_t>(entries_cap) * 8));
             BB_CUDA(cudaMemsetAsync(d_cnt, 0, 64, st));
-            bool filtered = false;
-            for (int g = 0; g < gt->n; g++) {
-                const DevGroup& G = gt->host[g];
-                ScanArgs A{};
-                A.bases = bases; A.offsets = offsets; A.n_reads = n_reads; A.total16 = total16;
-                A.chunk_base = d_chunk_base.as<uint32_t>(); A.tile_first = d_tile_first.as<uint32_t>(); A.tile_span = d_tile_span.as<uint64_t>();
-                A.group = g; A.strand_xor = (pol & kPolS6RcFirst) ? 1 : 0;
-                A.entries = d_entries.as<uint64_t>(); A.n_entries = d_cnt; A.cap = entries_cap;
-                if (G.f_on && use_filter && !force_exact) {
-                    // pre-filter (both strands in one 32-bit word) + exact verification of the candidate and read-end windows
-                    uint32_t win_cap = static_cast<uint32_t>(std::min<uint64_t>(total / 48 + (1u << 20), 1u << 30));
-                    if (const char* wc = std::getenv("BB_WIN_CAP")) win_cap = static_cast<uint32_t>(std::max(1, std::atoi(wc)));   // test knob: force the overflow fall-back
-                    BB_CUDA(d_windows.ensure(static_cast<size_t>(win_cap) * 8));
-                    BB_CUDA(cudaMemsetAsync(d_cnt + 6, 0, 4, st));          // [6] window count ([7] overflow flag is sticky per attempt)
-                    int halo_l = 0, halo_r = 0;
-                    filter_halos(G, halo_l, halo_r);
-                    FilterArgs F{A, d_windows.as<uint64_t>(), d_cnt + 6, win_cap, d_cnt + 7, halo_l, halo_r};
-                    const size_t smem = filter_smem_bytes(halo_l, halo_r);
-                    BB_CUDA(cudaFuncSetAttribute(k_flank_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-                    // scan + candidate runs + pre-check with the second N-free run (all on the shared text tile) -> windows
-                    k_flank_filter<<<n_tiles, kScanThreads, smem, st>>>(F, G);
-                    launches++;
-                    VerifyArgs V{A, d_windows.as<uint64_t>(), d_cnt + 6, d_cnt + 7, win_cap};
-                    if (G.nw == 1) k_flank_verify<1><<<148 * 16, 128, 0, st>>>(V, G);
-                    else k_flank_verify<2><<<148 * 16, 128, 0, st>>>(V, G);
-                    launches++;
-                    filtered = true;
-                    BB_CUDA(cudaGetLastError());
-                    continue;
-                }
-                const size_t smem = 128 + 2 * 256 * G.nw * sizeof(uint64_t) + static_cast<size_t>(kScanThreads) * kChunk + 2 * static_cast<size_t>(G.warm) + 48;
-                if (G.nw == 1) {
-                    BB_CUDA(cudaFuncSetAttribute(k_flank_scan<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-                    k_flank_scan<1><<<n_tiles, kScanThreads, smem, st>>>(A, G);
-                } else {
-                    BB_CUDA(cudaFuncSetAttribute(k_flank_scan<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-                    k_flank_scan<2><<<n_tiles, kScanThreads, smem, st>>>(A, G);
-                }
-                launches++;
-                BB_CUDA(cudaGetLastError());
-            }
-            any_filtered = filtered;
+            ScanArgs A{};
+            A.bases = bases; A.offsets = offsets; A.n_reads = n_reads; A.total16 = total16;
+            A.chunk_base = d_chunk_base.as<uint32_t>(); A.tile_first = d_tile_first.as<uint32_t>(); A.tile_span = d_tile_span.as<uint64_t>();
+            A.entries = d_entries.as<uint64_t>(); A.n_entries = d_cnt; A.cap = entries_cap;
+            rc = launch_scans(A, n_tiles, total, force_exact, st, &any_filtered);
+            if (rc != BB_OK) return rc;
             BB_CUDA(cudaMemcpyAsync(h_counters + 6, d_cnt + 6, 8, cudaMemcpyDeviceToHost, st));
             BB_CUDA(cudaMemcpyAsync(h_counters, d_cnt, 4, cudaMemcpyDeviceToHost, st));
             BB_CUDA(cudaStreamSynchronize(st));
@@ -314,60 +466,11 @@ struct Engine {
         BB_CUDA(cudaEventRecord(ev[2], st));
         if (n_hits == 0) { return finish_timing(st, 2); }
 
-        // ---- K2b: traceback of the flank matches ----
-        BB_CUDA(d_hits.ensure(static_cast<size_t>(n_hits) * sizeof(Hit)));
-        {
-            TraceArgs T{};
-            const unsigned blocks = std::min<unsigned>((n_hits + 63) / 64, 148 * 4);
-            T.n_slots = blocks * 64;
-            BB_CUDA(d_hist.ensure(static_cast<size_t>(gt->max_trace_cols + 2) * 2 * gt->max_nw * 8 * T.n_slots));
-            T.bases = bases; T.offsets = offsets; T.hit_keys = d_hitkeys.as<uint64_t>(); T.n_hits = n_hits;
-            T.groups = d_groups(); T.hist = d_hist.as<uint64_t>(); T.hits = d_hits.as<Hit>(); T.pol = pol;
-            k_trace<<<blocks, 64, 0, st>>>(T);
-            launches++;
-            BB_CUDA(cudaGetLastError());
-        }
-        BB_CUDA(cudaEventRecord(ev[3], st));
-
-        // ---- K3: barcode stage ----
-        BB_CUDA(d_rows.ensure(static_cast<size_t>(n_hits) * sizeof(bb_row)));
-        BB_CUDA(d_valid.ensure(n_hits));
-        {
-            BarArgs B{};
-            B.bases = bases; B.offsets = offsets; B.hits = d_hits.as<Hit>(); B.n_hits = d_cnt + 2; B.groups = d_groups();
-            B.code = gt->d_code.as<uint8_t>(); B.prm = prm; B.rows = d_rows.as<bb_row>(); B.row_valid = d_valid.as<uint8_t>();
-            B.sh_rows = gt->max_bar_len; B.pol = pol;
-            // one launch per record format that the geometry can need; each takes the flank matches of its region lengths
-            B.rn_lo = -1; B.rn_hi = 48;
-            int rc = launch_barcode<1, true>(B, n_hits, st);
-            if (rc != BB_OK) return rc;
-            if (gt->max_region > 48) {
-                B.rn_lo = 48; B.rn_hi = 64;
-                rc = launch_barcode<1, false>(B, n_hits, st);
-                if (rc != BB_OK) return rc;
-            }
-            if (gt->max_region > 64) {   // large automatic k (custom 115-bp tags)
-                B.rn_lo = 64; B.rn_hi = 1 << 20;
-                rc = launch_barcode<3, false>(B, n_hits, st);
-                if (rc != BB_OK) return rc;
-            }
-        }
-        BB_CUDA(cudaEventRecord(ev[4], st));
-
-        // ---- K4: collapse + ordered compaction ----
-        unsigned long long* d_kept = reinterpret_cast<unsigned long long*>(d_cnt + 4);
-        k_collapse<<<(n_hits + 127) / 128, 128, 0, st>>>(d_hits.as<Hit>(), n_hits, d_rows.as<bb_row>(), d_valid.as<uint8_t>(), d_kept);
-        launches++;
-        BB_CUDA(cudaGetLastError());
-        BB_CUDA(d_rows_out.ensure(static_cast<size_t>(n_hits) * sizeof(bb_row)));
-        {
-            size_t tmp = 0;
-            cub::DeviceSelect::Flagged(nullptr, tmp, d_rows.as<bb_row>(), d_valid.as<uint8_t>(), d_rows_out.as<bb_row>(), d_cnt + 3, static_cast<int>(n_hits), st);
-            BB_CUDA(d_cub.ensure(tmp));
-            BB_CUDA(cub::DeviceSelect::Flagged(d_cub.p, tmp, d_rows.as<bb_row>(), d_valid.as<uint8_t>(), d_rows_out.as<bb_row>(), d_cnt + 3, static_cast<int>(n_hits), st));
-        }
+        // ---- K2b traceback, K3 barcode stage, K4 collapse + ordered compaction ----
+        rc = launch_tail(bases, offsets, n_hits, st);
+        if (rc != BB_OK) return rc;
         BB_CUDA(cudaMemcpyAsync(h_counters + 3, d_cnt + 3, 12, cudaMemcpyDeviceToHost, st));
-        int rc = finish_timing(st, 5);
+        rc = finish_timing(st, 5);
         if (rc != BB_OK) return rc;
         last_rows = h_counters[3];
         std::memcpy(&last_kept, h_counters + 4, 8);
@@ -599,6 +702,7 @@ int bb_create(const bb_opts* opts, bb_ctx** out, char* err, size_t errlen) {
         c->eng[i].pack_threads = bb::pack_default_threads();
         c->eng[i].pol = static_cast<int>(opts->policy) & bb::kPolMask;
         if (const char* e = std::getenv("BB_K3_MITM")) c->eng[i].k3_mitm = std::atoi(e) != 0;
+        if (const char* e = std::getenv("BB_GLUE")) c->eng[i].glue = std::strcmp(e, "sort") == 0 ? 0 : 1;
     }
     *out = c;
     return BB_OK;
@@ -797,6 +901,7 @@ int bb_set_groups(bb_ctx* c, const bb_group* groups, int32_t n_groups) {
     cudaError_t e3 = cudaMemcpy(T.d_code.p, kAlpha.code, 256, cudaMemcpyHostToDevice);
     if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) return (ctx_error(c, "cudaMemcpy of the pattern tables failed"), BB_ERR_CUDA);
     T.host = hg; T.n = n_groups; T.max_trace_cols = max_trace; T.max_nw = max_nw; T.max_region = max_region; T.max_bar_len = max_bar_len; T.max_own_rows = max_own_rows;
+    T.max_k = 0; for (int g = 0; g < n_groups; g++) T.max_k = std::max(T.max_k, groups[g].k_flank);
     return BB_OK;
 }
 

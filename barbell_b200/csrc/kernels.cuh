@@ -148,9 +148,13 @@ struct ScanArgs {
     uint64_t total16;            // readable bytes of `bases` (total rounded up to 16)
     int group;
     int strand_xor;              // policy S6: 1 = the key's strand bit is inverted so that Rc matches sort before forward ones
-    uint64_t* entries;
+    uint64_t* entries;           // global entry list (sorted path) ...
     uint32_t* n_entries;
     uint32_t cap;
+    uint64_t* slots;             // ... or, when non-null, per-read entry slots [n_reads][slot_cap] + per-read counts (slot path)
+    uint32_t* slot_cnt;
+    uint32_t slot_cap;
+    uint32_t* slot_overflow;     // set when a read has more entries than slots (the batch is then re-run on the sorted path)
 };
 
 // chunks per read (thread per read; entry n_reads is 0 so the exclusive scan yields the total)
@@ -231,8 +235,15 @@ __device__ __forceinline__ int col_step_top(Col<NW>& c, const uint64_t* __restri
 }
 
 __device__ __forceinline__ void scan_emit(const ScanArgs& A, uint32_t r, int strand, uint32_t pos, int cost) {
+    const uint64_t key = make_key(r, A.group, strand ^ A.strand_xor, pos, cost);
+    if (A.slots) {
+        const uint32_t idx = atomicAdd(A.slot_cnt + r, 1u);
+        if (idx < A.slot_cap) A.slots[static_cast<size_t>(r) * A.slot_cap + idx] = key;
+        else atomicExch(A.slot_overflow, 1u);
+        return;
+    }
     const uint32_t idx = atomicAdd(A.n_entries, 1u);
-    if (idx < A.cap) A.entries[idx] = make_key(r, A.group, strand ^ A.strand_xor, pos, cost);
+    if (idx < A.cap) A.entries[idx] = key;
 }
 
 template <int NW>
@@ -773,13 +784,119 @@ __global__ void k_resolve(const uint64_t* __restrict__ keys, const uint32_t* __r
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// K2a, slot path: one WARP per read does what the global radix sort + unique + k_resolve + select do on the sorted path --
+// the read's sub-threshold entries (a few dozen at most, duplicates from overlapping verification windows included) are
+// ranked in shared memory (distinct keys in ascending order = sassy's order: group, forward before reverse-complement,
+// ascending end position), the local-minimum rule (policy S1) is applied to the sorted run, and the reported matches are
+// written back to the front of the read's slots.  No host round trip: the match counts are prefix-summed on the device.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kSlotCap = 128;        // entry slots per read (k_read_resolve holds them in shared memory)
+constexpr int kResolveWarps = 4;
+
+__global__ void __launch_bounds__(kResolveWarps * 32) k_read_resolve(uint64_t* __restrict__ slots, const uint32_t* __restrict__ slot_cnt, uint32_t n_reads,
+                                                                      const uint64_t* __restrict__ offsets, const DevGroup* __restrict__ groups,
+                                                                      uint32_t* __restrict__ n_hits_read, int pol) {
+    __shared__ uint64_t s_raw[kResolveWarps][kSlotCap], s_sorted[kResolveWarps][kSlotCap];
+    __shared__ uint8_t s_first[kResolveWarps][kSlotCap];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const uint32_t r = blockIdx.x * kResolveWarps + wib;
+    if (r >= n_reads) return;
+    const uint32_t n = min(__ldg(slot_cnt + r), static_cast<uint32_t>(kSlotCap));
+    if (n == 0) { if (lane == 0) n_hits_read[r] = 0; return; }
+    uint64_t* mine = slots + static_cast<size_t>(r) * kSlotCap;
+    uint64_t* raw = s_raw[wib]; uint64_t* sorted = s_sorted[wib]; uint8_t* first = s_first[wib];
+    for (uint32_t q = lane; q < n; q += 32) raw[q] = mine[q];
+    __syncwarp();
+    // first occurrence of every distinct key
+    for (uint32_t q = lane; q < n; q += 32) {
+        const uint64_t k = raw[q];
+        bool f = true;
+        for (uint32_t j = 0; j < q; j++) if (raw[j] == k) { f = false; break; }
+        first[q] = f ? 1 : 0;
+    }
+    __syncwarp();
+    // rank among the distinct keys
+    uint32_t nd_local = 0;
+    for (uint32_t q = lane; q < n; q += 32) {
+        if (!first[q]) continue;
+        const uint64_t k = raw[q];
+        uint32_t rank = 0;
+        for (uint32_t j = 0; j < n; j++) rank += (first[j] && raw[j] < k) ? 1u : 0u;
+        sorted[rank] = k;
+        nd_local++;
+    }
+    uint32_t nd = nd_local;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) nd += __shfl_xor_sync(0xffffffffu, nd, off);
+    __syncwarp();
+    // local-minimum rule on the sorted run (same walk as k_resolve), then ordered compaction of the reported matches
+    const uint32_t len = static_cast<uint32_t>(offsets[r + 1] - offsets[r]);
+    uint32_t out = 0;
+    for (uint32_t base = 0; base < nd; base += 32) {
+        const uint32_t e = base + lane;
+        bool rep = false;
+        uint64_t key = 0;
+        if (e < nd) {
+            key = sorted[e];
+            const uint64_t id = key >> kKeyPosShift;
+            const int cost = static_cast<int>(key & 0xff);
+            const int g = static_cast<int>((key >> kKeyGroupShift) & 7);
+            const uint32_t pos = static_cast<uint32_t>((key >> kKeyPosShift) & ((1u << 28) - 1));
+            const uint32_t last = len + groups[g].m;
+            bool dec = true, firstp = true;
+            uint64_t cur = id;
+            for (uint32_t q = e; q > 0; q--) {
+                const uint64_t pk = sorted[q - 1];
+                if ((pk >> kKeyPosShift) != cur - 1) break;
+                const int pc = static_cast<int>(pk & 0xff);
+                if (pc > cost) break;
+                if (pc < cost) { dec = false; break; }
+                cur--; firstp = false;
+            }
+            bool up = true, lastp = true;
+            cur = id;
+            uint32_t p = pos;
+            for (uint32_t q = e; p != last && q + 1 < nd; q++) {
+                const uint64_t nk = sorted[q + 1];
+                if ((nk >> kKeyPosShift) != cur + 1) break;
+                const int nc = static_cast<int>(nk & 0xff);
+                if (nc > cost) break;
+                if (nc < cost) { up = false; break; }
+                cur++; p++; lastp = false;
+                if (!(pol & kPolS1Left)) break;
+            }
+            rep = up && dec && ((pol & kPolS1Left) ? firstp : lastp);
+        }
+        const uint32_t m = __ballot_sync(0xffffffffu, rep);
+        if (rep) mine[out + __popc(m & ((1u << lane) - 1u))] = key;
+        out += __popc(m);
+    }
+    if (lane == 0) n_hits_read[r] = out;
+}
+
+// the reads' reported matches (front of their slots) -> one list in read order; thread per read
+__global__ void k_hits_gather(const uint64_t* __restrict__ slots, const uint32_t* __restrict__ n_hits_read, const uint32_t* __restrict__ hit_base,
+                              uint32_t n_reads, uint32_t hits_cap, uint64_t* __restrict__ hit_keys, uint32_t* __restrict__ n_hits_out, uint32_t* __restrict__ overflow) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r == 0) {
+        const uint32_t total = hit_base[n_reads];
+        if (total > hits_cap) { atomicExch(overflow, 1u); *n_hits_out = 0; } else *n_hits_out = total;
+    }
+    if (r >= n_reads) return;
+    const uint32_t n = n_hits_read[r], b = hit_base[r];
+    if (b + n > hits_cap) return;
+    const uint64_t* src = slots + static_cast<size_t>(r) * kSlotCap;
+    for (uint32_t q = 0; q < n; q++) hit_keys[b + q] = src[q];
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // K2b: traceback of the reported flank matches (oracle policies S2-S4) + barcode region
 // ---------------------------------------------------------------------------------------------------------------
 struct TraceArgs {
     const uint8_t* bases;
     const uint64_t* offsets;
     const uint64_t* hit_keys;
-    uint32_t n_hits;
+    const uint32_t* n_hits;  // device-side count
     const DevGroup* groups;
     uint64_t* hist;          // [col][2*NW][slot]
     uint32_t n_slots;
@@ -872,7 +989,8 @@ __device__ void trace_one(const TraceArgs& A, const DevGroup& G, uint32_t h, uin
 
 __global__ void __launch_bounds__(64) k_trace(const TraceArgs A) {
     const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
-    for (uint32_t h = slot; h < A.n_hits; h += A.n_slots) {
+    const uint32_t n_hits = __ldg(A.n_hits);
+    for (uint32_t h = slot; h < n_hits; h += A.n_slots) {
         const int g = static_cast<int>((A.hit_keys[h] >> kKeyGroupShift) & 7);
         const DevGroup& G = A.groups[g];
         if (G.nw == 1) trace_one<1>(A, G, h, slot); else trace_one<2>(A, G, h, slot);
@@ -1094,8 +1212,9 @@ __device__ __forceinline__ bool row_better(const bb_row& a, const bb_row& b) {
     return (a.read_end_flank - a.read_start_flank) > (b.read_end_flank - b.read_start_flank);
 }
 
-__global__ void k_collapse(const Hit* __restrict__ hits, uint32_t n_hits, bb_row* rows, uint8_t* row_valid,
+__global__ void k_collapse(const Hit* __restrict__ hits, const uint32_t* __restrict__ n_hits_p, bb_row* rows, uint8_t* row_valid,
                            unsigned long long* kept_reads) {
+    const uint32_t n_hits = __ldg(n_hits_p);
     const uint32_t h0 = blockIdx.x * blockDim.x + threadIdx.x;
     if (h0 >= n_hits) return;
     const uint32_t read = hits[h0].read;

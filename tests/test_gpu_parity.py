@@ -491,3 +491,37 @@ def test_submit_packed_equals_submit():
         assert tag == 6 and len(got) == 0
     finally:
         an.close()
+
+
+def test_slot_path_overflows_fall_back_to_the_sorted_path(monkeypatch):
+    """The default engine keeps every read's sub-threshold entries in per-read slots and resolves them with one warp per read (no
+    radix sort, no host round trip).  Too few slots for a read, or too small a hit list, re-run the batch on the global-sort
+    path; BB_GLUE=sort selects that path outright.  Same rows and flank hits in every case, repeat-rich reads included."""
+    gs = bb.GroupSet.from_kit("SQK-NBD114-96")
+    g = gs.as_dicts()[0]
+    b, o, _ = synth.make_reads(gs.as_dicts(), 1500, (300, 4000), seed=77)
+    # a few reads made of many tags in a row: dozens of sub-threshold positions per read
+    tags = synth.full_tags(g)
+    rng = np.random.default_rng(78)
+    extra = []
+    for r in range(6):
+        extra.append(np.concatenate([synth.mutate(rng, tags[(7 * r + q) % len(tags)], 0.03) for q in range(25)] + [rng.choice(np.frombuffer(b"ACGT", np.uint8), 500)]))
+    bases = np.concatenate([b] + extra)
+    offsets = np.concatenate([o, o[-1] + np.cumsum([len(x) for x in extra]).astype(np.uint64)])
+    want = O.demux_batch(gs.as_dicts(), bases, offsets, cap_per_read=256)
+    want_h = O.flank_hits_batch(gs.as_dicts(), bases, offsets, cap_per_read=256)
+
+    def run():
+        an = _annotator(gs)
+        try:
+            rows = an.annotate(bases, offsets)
+            return rows, an.flank_hits()
+        finally:
+            an.close()
+    rows, hits = run()
+    assert rows.tobytes() == want.tobytes() and (hits == want_h).all()
+    for key, val in (("BB_SLOT_CAP", "8"), ("BB_HITS_CAP", "100"), ("BB_GLUE", "sort")):
+        monkeypatch.setenv(key, val)
+        rows2, hits2 = run()
+        monkeypatch.delenv(key)
+        assert rows2.tobytes() == want.tobytes() and (hits2 == want_h).all(), key
