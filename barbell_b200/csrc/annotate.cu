@@ -751,7 +751,6 @@ int bb_set_groups(bb_ctx* c, const bb_group* groups, int32_t n_groups) {
         if (S.n_barcodes < 1 || S.n_barcodes > 32 * kMaxBarRounds) return bad("1..512 barcodes per group");
         if (S.k_flank < 0 || S.k_flank > 120) return bad("flank threshold must be 0..120");
         const int ov_m = over_cost(m);
-        if (S.k_flank >= ov_m - 1) return bad("flank threshold too large for the overhang cost: need k < floor(alpha*len)-1");
         if (S.bar1 - S.bar0 + 1 + S.k_flank + 2 * kPadding > kRegionMax) return bad("barcode region (mask + k + 20) exceeds 160 characters");
         if (S.bar0 < 0 || S.bar1 < S.bar0 || S.bar1 >= m || S.pad0 < 0 || S.pad0 > S.bar0) return bad("inconsistent bar/pad regions");
         D.m = m; D.nw = (m + 63) / 64; D.last_bit = (m - 1) & 63; D.k = S.k_flank;

@@ -21,6 +21,7 @@ def _check(gs, bases, offsets, **kw):
     """Both scan paths (lossless pre-filter + window verification, and the exact full-length scan) against the oracle."""
     out = []
     kw = dict(kw)
+    cap_override = kw.pop("_cap", None)
     for use_filter in (True, False):
         an = _annotator(gs, use_filter=use_filter, **kw)
         try:
@@ -30,7 +31,7 @@ def _check(gs, bases, offsets, **kw):
     assert out[0][0].tobytes() == out[1][0].tobytes(), "pre-filter path differs from the exact scan"
     rows, hits = out[0]
     G = gs.as_dicts()
-    cap = max(16, int(len(bases) // 100 // max(1, len(offsets) - 1)))      # rows / hits per read the oracle buffers may hold
+    cap = cap_override or max(16, int(len(bases) // 100 // max(1, len(offsets) - 1)))      # rows / hits per read the oracle buffers may hold
     want = O.demux_batch(G, bases, offsets, alpha=kw.get("alpha", 0.4), min_score=kw.get("min_score", 0.2),
                          min_score_diff=kw.get("min_score_diff", 0.1), cap_per_read=cap)
     want_h = O.flank_hits_batch(G, bases, offsets, alpha=kw.get("alpha", 0.4), cap_per_read=2 * cap)
@@ -269,9 +270,23 @@ def test_full_size_properties():
 
 
 def test_set_groups_rejects_unsupported_geometry():
-    gs = bb.GroupSet.from_kit("SQK-NBD114-96", max_flank_errors=30)     # k >= floor(0.4*46)-1
+    """What bb_set_groups still refuses: a flank threshold beyond 120, and -- checked on the host side by
+    bb_groups_add -- nothing the shipped kits or the reference's example FASTAs need."""
+    gs = bb.GroupSet.from_kit("SQK-NBD114-96", max_flank_errors=121)
     with pytest.raises(bb.BarbellError):
         _annotator(gs)
+
+
+@pytest.mark.parametrize("kit,k", [("SQK-NBD114-96", 16), ("SQK-NBD114-96", 17), ("SQK-NBD114-96", 18), ("SQK-NBD114-96", 23), ("SQK-RBK114-96", 36)])
+def test_flank_threshold_at_and_above_the_full_overhang_cost(kit, k, monkeypatch):
+    """--flank-max-errors takes any usize in the reference (bin/main.rs:90-91, annotator.rs:216-229).  From k = floor(alpha * len) on
+    the flank hanging over a read end completely is itself a match (cost floor(alpha * len) <= k), so every read end reports
+    matches on both strands; the GPU path must degrade exactly like the oracle does -- rows and flank hits."""
+    monkeypatch.setenv("ORC_PER_READ", "4096")           # such thresholds match almost everywhere: hundreds of flank matches per read
+    gs = bb.GroupSet.from_kit(kit, max_flank_errors=k)
+    b, o, _ = synth.make_reads(gs.as_dicts(), 40, (0, 400), seed=300 + k)
+    rows = _check(gs, b, o, _cap=2048)
+    assert len(rows) > 0
 
 
 def test_cli_fastq_to_annotation_tsv(tmp_path):
@@ -525,3 +540,32 @@ def test_slot_path_overflows_fall_back_to_the_sorted_path(monkeypatch):
         rows2, hits2 = run()
         monkeypatch.delenv(key)
         assert rows2.tobytes() == want.tobytes() and (hits2 == want_h).all(), key
+
+
+def test_cli_in_process_multi_gpu(tmp_path):
+    """`barbell annotate --gpus 2`: one process, batches dealt round-robin to one context per GPU, rows written in input order --
+    byte-identical to the single-GPU output (needs two visible GPUs: gpurun --gpus 2)."""
+    import os
+    import subprocess
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    exe = os.path.join(os.path.dirname(bb.lib_path()), "barbell")
+    gs = bb.GroupSet.from_kit("SQK-NBD114-96")
+    b, o, _ = synth.make_reads(gs.as_dicts(), 30000, (500, 6000), seed=91)
+    fq = tmp_path / "r.fastq"
+    synth.write_fastq(str(fq), b, o)
+    outs = []
+    for gpus in (1, 2):
+        out = tmp_path / f"a{gpus}.tsv"
+        r = subprocess.run([exe, "annotate", "--kit", "SQK-NBD114-96", "-i", str(fq), "-o", str(out), "-t", "8", "--batch-mb", "8", "--gpus", str(gpus)],
+                           capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0 and "Annotation complete!" in r.stdout, r.stdout + r.stderr
+        outs.append(open(out).read())
+    assert outs[0] == outs[1] and outs[0].count("\n") > 20000
+    ids = [f"read_{i}" for i in range(len(o) - 1)]
+    an = _annotator(gs)
+    try:
+        assert bb.rows_to_tsv(an.annotate(b, o), gs, ids) == outs[0]
+    finally:
+        an.close()
