@@ -46,6 +46,7 @@ struct Args {
     double min_score = 0.2, min_score_diff = 0.1;
     float alpha = 0.4f;
     size_t batch_mb = 256;
+    unsigned policy = 0;                 // bb_opts.policy (BB_POL_*): the sassy choices the reference's tests do not pin
 };
 
 [[noreturn]] void usage(const char* msg) {
@@ -54,7 +55,7 @@ struct Args {
         "barbell (B200 build of the annotate path)\n"
         "  barbell annotate -i <fastq>... [-o output.tsv] (--kit <KIT> | -q <fasta>... [-b Ftag|Rtag ...])\n"
         "                   [-t N] [--flank-max-errors INT] [--min-score F] [--min-score-diff F] [--alpha F]\n"
-        "                   [--use-extended] [--verbose] [--gpus N] [--batch-mb MB] [--no-pack]\n"
+        "                   [--use-extended] [--verbose] [--gpus N] [--batch-mb MB] [--no-pack] [--policy BITS]\n"
         "  barbell kit -k <KIT> -i <fastq>... -o <folder> [--maximize] [--failed-out FILE] [--gzip] [annotate options]\n"
         "  barbell filter -i annotation.tsv -o filtered.tsv -f <pattern file>... [--dropped FILE]\n"
         "  barbell trim -i filtered.tsv -r <fastq>... -o <folder> [--no-label] [--no-orientation] [--no-flanks] [--sort-labels]\n"
@@ -106,6 +107,7 @@ Args parse(int argc, char** argv) {
         else if (f == "--verbose") a.verbose = true;
         else if (f == "--single-reader") a.single_reader = true;
         else if (f == "--no-pack") a.no_pack = true;
+        else if (f == "--policy") a.policy = static_cast<unsigned>(std::atoi(one().c_str()));
         else if (f == "--chunk-kb") a.chunk_kb = static_cast<size_t>(std::atol(one().c_str()));
         else if (f == "--use-extended") a.use_extended = true;
         else if (f == "--maximize") a.maximize = true;
@@ -620,7 +622,7 @@ int run_annotate(const Args& a, const std::string& out_path) {
     auto since = [](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t).count(); };
     for (int d = 0; d < n_gpus; d++) {
         bb_opts o{};
-        o.device = d; o.alpha = a.alpha; o.min_score = a.min_score; o.min_score_diff = a.min_score_diff;
+        o.device = d; o.alpha = a.alpha; o.min_score = a.min_score; o.min_score_diff = a.min_score_diff; o.policy = a.policy;
         rc = bb_create(&o, &ctx[d], err, sizeof err);
         if (rc == BB_OK) { rc = bb_set_groups(ctx[d], groups, n_groups); if (rc != BB_OK) std::snprintf(err, sizeof err, "%s", bb_last_error(ctx[d])); }
         if (rc != BB_OK) { std::printf("Error during processing: %s\n", err); for (auto* c : ctx) bb_destroy(c); bb_groups_free(gs); return rc; }

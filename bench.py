@@ -194,12 +194,18 @@ def int_issue_roofline(name, n_reads, ms_per_step, sm_mhz):
     peak = 148 * 128 * sm_mhz * 1e6
     achieved = lane_ops / (ms_per_step / 1e3)
     top = sorted(d["kernels"].items(), key=lambda kv: -kv[1]["thread_inst"])[:3]
+    pipes = {}
+    pp = os.path.join(ROOT, "profiles", "r2_kernel_pipes.json")
+    if os.path.exists(pp):
+        pipes = json.load(open(pp))
     return dict(achieved=achieved, peak=peak, unit="lane-ops/s", frac=achieved / peak, lane_ops_per_step=lane_ops,
                 lane_ops_per_base=lane_ops / (n_reads * READ_LEN), source="profiles/r2_inst_counts.json (ncu smsp__thread_inst_executed.sum per kernel)",
-                top_kernels={k: dict(lane_ops_per_step=v["thread_inst"] * scale, share=v["thread_inst"] / max(1, sum(x["thread_inst"] for x in d["kernels"].values())))
+                top_kernels={k: dict(lane_ops_per_step=v["thread_inst"] * scale, share=v["thread_inst"] / max(1, sum(x["thread_inst"] for x in d["kernels"].values())),
+                                     **{a: b for a, b in pipes.get(k.replace("bb::", ""), {}).items()})
                              for k, v in top},
                 note="every kernel of the step is integer/bit work on the ALU pipe, which issues one warp instruction per 2 clocks per scheduler: "
-                     "an all-ALU instruction stream tops out at 0.5 of this peak")
+                     "an all-ALU instruction stream tops out at 0.5 of this peak; alu_pipe_active_pct (ncu --set full, profiles/r2_ncu_full_kernels.txt) "
+                     "is the utilisation of that pipe per kernel")
 
 
 def fastq_leg(cfg, groups, n_reads, passes, threads):
@@ -256,7 +262,7 @@ def main():
     ap.add_argument("--e2e-sub", type=int, default=4, help="sub-batches per step of the end-to-end leg")
     ap.add_argument("--e2e-depth", type=int, default=4, help="sub-batches in flight (<= BB_MAX_INFLIGHT = 4)")
     ap.add_argument("--fastq-reads", type=int, default=50000)
-    ap.add_argument("--fastq-passes", type=int, default=8)
+    ap.add_argument("--fastq-passes", type=int, default=20)
     args = ap.parse_args()
     name, cfg = args.config, CONFIGS[args.config]
     if args.impl == "reference":
