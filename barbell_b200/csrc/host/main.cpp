@@ -46,7 +46,7 @@ struct Args {
     double min_score = 0.2, min_score_diff = 0.1;
     float alpha = 0.4f;
     size_t batch_mb = 256;
-    unsigned policy = 0;                 // bb_opts.policy (BB_POL_*): the sassy choices the reference's tests do not pin
+    unsigned policy = BB_POL_DEFAULT;    // bb_opts.policy (BB_POL_*): the sassy choices the reference's tests do not pin
 };
 
 [[noreturn]] void usage(const char* msg) {

@@ -90,6 +90,9 @@ enum {
     BB_POL_S3_ROUND = 16,      /* overhang cost of t rows = round-to-nearest(t*alpha) (default: floor) */
     BB_POL_S3_CEIL = 32        /* ... = ceil(t*alpha) */
 };
+/* the setting hosts should pass unless they know better; the one constant to change (with g_policy in oracle/barbell_oracle.c) once
+   tools/ref_parity.sh --policy auto has been run against upstream */
+#define BB_POL_DEFAULT 0u
 
 typedef struct bb_ctx bb_ctx;
 typedef struct bb_groupset bb_groupset;

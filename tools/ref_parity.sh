@@ -12,7 +12,7 @@
 # `barbell annotate --policy BITS`, include/barbell_b200.h BB_POL_*) and of the oracle (orc_policy.flags): 1 = S1 left end of a
 # plateau, 2 = S2 pattern-only before text-only, 4 = S5 last of equal minima, 8 = S6 Rc matches first, 16 / 32 = S3 round / ceil.
 #   --policy BITS   run this build under that setting;   --policy auto   try all 48 settings and report the ones that match.
-# A matching setting becomes the default by changing ONE constant (kPolDefault in barbell_b200/csrc/barcode_rows.cuh and
+# A matching setting becomes the default by changing ONE constant per side (BB_POL_DEFAULT in include/barbell_b200.h and
 # g_policy in oracle/barbell_oracle.c) -- no kernel is touched; the GPU == oracle suite already runs under every setting.
 set -euo pipefail
 REF=${1:?path to a checkout of rickbeeloo/barbell}
