@@ -1016,6 +1016,9 @@ struct BarArgs {
 };
 
 constexpr int kMaxBarRounds = 16;   // up to 512 barcodes per group
+#ifndef BB_K3_MIN_CTAS
+#define BB_K3_MIN_CTAS 16            // resident warps (= CTAs) per SM the register allocation of k_barcode_rows aims at
+#endif
 
 __device__ __forceinline__ int64_t rel_dist_to_end(int64_t pos, int64_t read_len) {   // searcher.rs:183-199
     if (pos < 0) return 1;
@@ -1060,7 +1063,7 @@ __host__ __device__ inline size_t barcode_rows_smem(int sh_rows, int own_rows) {
 // Launches: regions of <= 48 bases with 12-byte records (PACKED), 49..64 with 16-byte records, longer ones with three text words.
 // MITM = only half of the own rows' records are resident (more warps in flight for some replayed forward rows).
 template <int NWT, bool PACKED, bool S2PAT, bool MITM>
-__global__ void __launch_bounds__(32) k_barcode_rows(const BarArgs A) {
+__global__ void __launch_bounds__(32, NWT == 1 ? BB_K3_MIN_CTAS : 1) k_barcode_rows(const BarArgs A) {
     extern __shared__ __align__(16) unsigned char bar_smem[];
     const int lane = threadIdx.x;
     uint32_t* lut = reinterpret_cast<uint32_t*>(bar_smem);                                 // [256] bottom-row scan table
