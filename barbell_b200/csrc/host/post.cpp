@@ -595,10 +595,20 @@ class FastqOut {                                         // plain or gzip writer
         else { f_ = std::fopen(path.c_str(), "w"); if (!f_) { err = "Failed to create output file '" + path + "': " + std::strerror(errno) + (errno == EMFILE ? "\nTry setting ulimit higher: \"ulimit -n 65000\"" : ""); return false; } std::setvbuf(f_, nullptr, _IOFBF, 1 << 18); }
         return true;
     }
-    void write(const std::string& s) { if (gz_mode_) gzwrite(g_, s.data(), static_cast<unsigned>(s.size())); else std::fwrite(s.data(), 1, s.size(), f_); }
-    ~FastqOut() { if (g_) gzclose(g_); if (f_) std::fclose(f_); }
+    // the reference aborts on a failed write (`expect("Failed to write ...")`, trim.rs:420-445): errors are remembered and reported by close()
+    void write(const std::string& s) {
+        if (s.empty()) return;
+        if (gz_mode_) { if (gzwrite(g_, s.data(), static_cast<unsigned>(s.size())) != static_cast<int>(s.size())) bad_ = true; }
+        else if (std::fwrite(s.data(), 1, s.size(), f_) != s.size()) bad_ = true;
+    }
+    bool close() {                                       // false when any write or the close itself failed (disk full, I/O error)
+        if (g_) { if (gzclose(g_) != Z_OK) bad_ = true; g_ = nullptr; }
+        if (f_) { if (std::fclose(f_) != 0) bad_ = true; f_ = nullptr; }
+        return !bad_;
+    }
+    ~FastqOut() { close(); }
   private:
-    bool gz_mode_ = false; gzFile g_ = nullptr; FILE* f_ = nullptr;
+    bool gz_mode_ = false, bad_ = false; gzFile g_ = nullptr; FILE* f_ = nullptr;
 };
 
 }  // namespace
@@ -706,7 +716,7 @@ int bb_trim(const char* filtered, const char* const* fastq, int32_t n_fastq, con
         if (it == by_read.end()) continue;
         const std::vector<TrimmedRead> results = process_read_and_anno(v.seq, v.qual, v.seq_len, it->second, o);
         if (!results.empty()) trimmed++;
-        else { failed_n++; if (failed) std::fprintf(failed, "%s\n", read_id.c_str()); }
+        else { failed_n++; if (failed && std::fprintf(failed, "%s\n", read_id.c_str()) < 0) { e = std::string("Failed to write ") + o.failed_out; rc = BB_ERR_IO; } }
         if (results.size() > 1) split++;
         for (const TrimmedRead& t : results) {
             auto w = writers.find(t.label);
@@ -723,8 +733,10 @@ int bb_trim(const char* filtered, const char* const* fastq, int32_t n_fastq, con
         }
         if (rc != BB_OK) break;
     }
-    if (failed) std::fclose(failed);
+    if (failed && std::fclose(failed) != 0 && rc == BB_OK) { e = std::string("Failed to write ") + o.failed_out; rc = BB_ERR_IO; }
     if (rc == BB_OK && !e.empty()) rc = BB_ERR_IO;
+    for (auto& w : writers)                              // every per-label file is closed here, so that a truncated output is an error, not a count
+        if (!w.second->close() && rc == BB_OK) { e = "Failed to write trimmed reads of label '" + w.first + "' in " + out_dir; rc = BB_ERR_IO; }
     if (rc != BB_OK) { set_err(err, errlen, e); return rc; }
     if (counts) { counts[0] = total; counts[1] = trimmed; counts[2] = split; counts[3] = failed_n; }
     return BB_OK;

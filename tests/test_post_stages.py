@@ -373,3 +373,24 @@ def test_python_mirror_of_the_post_stages(tmp_path, capfd):
     assert c["total"] == n_reads and c["trimmed"] + c["failed"] == len({r.read_id for r in kept}) and c["trimmed"] > 10
     with pytest.raises(bb.BarbellError, match="ambiguous"):
         post.trim_matches(tmp_path / "f.tsv", [tmp_path / "r.fastq"], tmp_path / "out2", sort_labels=True, only_side="left")
+
+
+def test_trim_reports_failed_writes(lib, tmp_path):
+    """A per-label output that cannot be written (here: a symlink to /dev/full, i.e. ENOSPC on flush) must make bb_trim fail with
+    BB_ERR_IO instead of returning full counts over truncated files -- the reference aborts (`expect("Failed to write ...")`,
+    trim.rs:420-445)."""
+    if not os.path.exists("/dev/full"):
+        pytest.skip("/dev/full not available")
+    seq, qual = "CCCCCCCCAAAACCCCCCCCCCCC", "________IIII____________"
+    rows = [row(4, 8, label="Fbar", read_id="read1", read_len=24, cuts=[(("After", 0), 8)]),
+            row(12, 16, "Rtag", label="Rbar", read_id="read1", read_len=24, cuts=[(("Before", 0), 12)])]
+    tsv, fq, out = tmp_path / "filtered.tsv", tmp_path / "reads.fastq", tmp_path / "trimmed"
+    tsv.write_text(P.to_tsv(rows))
+    fq.write_text(f"@read1\n{seq}\n+\n{qual}\n")
+    out.mkdir()
+    os.symlink("/dev/full", out / "Fbar_fw__Rbar_fw.trimmed.fastq")
+    o = TrimOpts(1, 1, 1, 1, 0, 1, 0, 0, 0, None)
+    paths = (C.c_char_p * 1)(str(fq).encode())
+    counts, err = (C.c_uint64 * 4)(), C.create_string_buffer(1024)
+    rc = lib.bb_trim(str(tsv).encode(), paths, 1, str(out).encode(), C.byref(o), counts, err, len(err))
+    assert rc == -6 and b"Failed to write" in err.value, (rc, err.value)
