@@ -86,4 +86,71 @@ class FastqReader {
     bool eof_ = false, patched_ = false;
 };
 
+// ---- helpers for readers that map a plain FASTQ file and parse it in chunks on several threads (the CLI's ParallelSource, bb_trim) ----
+// one line [p, e) without its terminator; next = start of the following line
+inline void fastq_line_at(const char* m, size_t size, size_t p, size_t& e, size_t& next) {
+    const char* nl = static_cast<const char*>(std::memchr(m + p, '\n', size - p));
+    e = nl ? static_cast<size_t>(nl - m) : size;
+    next = nl ? e + 1 : size;
+    if (e > p && m[e - 1] == '\r') e--;
+}
+// first record start at or after pos: a line "@..." whose third line starts with '+' and whose fourth line is as long as
+// its second (a quality line may start with '@' too, but then the line two below is a sequence, never a '+' line)
+inline size_t fastq_record_start(const char* m, size_t size, size_t pos) {
+    if (pos == 0) return 0;
+    if (pos >= size) return size;
+    size_t p = pos;
+    if (m[pos - 1] != '\n') {
+        const char* nl = static_cast<const char*>(std::memchr(m + pos, '\n', size - pos));
+        if (!nl) return size;
+        p = static_cast<size_t>(nl - m) + 1;
+    }
+    while (p < size) {
+        size_t e0, n0, e1, n1, e2, n2, e3, n3;
+        fastq_line_at(m, size, p, e0, n0);
+        if (m[p] == '@' && n0 < size) {
+            fastq_line_at(m, size, n0, e1, n1);
+            if (n1 < size) {
+                fastq_line_at(m, size, n1, e2, n2);
+                if (e2 > n1 && m[n1] == '+' && n2 <= size) {
+                    if (n2 < size) fastq_line_at(m, size, n2, e3, n3); else { e3 = n2; n3 = n2; }
+                    if (e3 - n2 == e1 - n0) return p;
+                }
+            }
+        }
+        p = n0;
+    }
+    return size;
+}
+// One record at p (p < end of the mapped file): views into the map; the quality line is stepped over by its length when it has
+// the sequence's length (half of the file is then never read).  Returns 0 = ok (p advanced), 1 = blank line skipped, -1 = error.
+struct FastqRec { const char* head; size_t head_len; const char* seq; size_t seq_len; const char* qual; };
+inline int fastq_record_at(const char* m, size_t size, size_t& p, FastqRec& r, const char*& what) {
+    size_t e0, n0, e1, n1, e2, n2, e3, n3;
+    fastq_line_at(m, size, p, e0, n0);
+    if (e0 == p) { p = n0; return 1; }
+    if (n0 >= size) { what = "truncated FASTQ record"; return -1; }
+    fastq_line_at(m, size, n0, e1, n1);
+    if (n1 >= size) { what = "truncated FASTQ record"; return -1; }
+    fastq_line_at(m, size, n1, e2, n2);
+    const size_t seq_len = e1 - n0, q_end = n2 + seq_len;
+    if (q_end == size) { e3 = q_end; n3 = q_end; }
+    else if (q_end < size && m[q_end] == '\n') { e3 = q_end; n3 = q_end + 1; }
+    else if (q_end + 1 < size && m[q_end] == '\r' && m[q_end + 1] == '\n') { e3 = q_end; n3 = q_end + 2; }
+    else if (n2 < size) fastq_line_at(m, size, n2, e3, n3); else { e3 = n2; n3 = n2; }
+    if (m[p] != '@' || e2 == n1 || m[n1] != '+') { what = "malformed FASTQ record"; return -1; }
+    if (e3 - n2 != seq_len) { what = "truncated FASTQ record (quality length differs from sequence length)"; return -1; }
+    r.head = m + p + 1; r.head_len = e0 - p - 1; r.seq = m + n0; r.seq_len = seq_len; r.qual = m + n2;
+    p = n3;
+    return 0;
+}
+// id = header up to the first whitespace, desc = the rest without leading whitespace (split_fastq_header, io.rs:5-16)
+inline void fastq_split_header(const char* head, size_t n, size_t& id_len, size_t& desc_off) {
+    auto ws = [](char c) { return c == ' ' || c == '\t' || c == '\v' || c == '\f' || c == '\r'; };
+    id_len = 0;
+    while (id_len < n && !ws(head[id_len])) id_len++;
+    desc_off = id_len;
+    while (desc_off < n && ws(head[desc_off])) desc_off++;
+}
+
 }  // namespace bb

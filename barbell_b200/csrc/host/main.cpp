@@ -306,69 +306,19 @@ class ParallelSource : public BatchSource {
   private:
     struct File { std::string path; int fd = -1; size_t size = 0; const char* map = nullptr; size_t first_chunk = 0; };
 
-    // one line [p, e) without its terminator; next = start of the following line
-    static void line_at(const char* m, size_t size, size_t p, size_t& e, size_t& next) {
-        const char* nl = static_cast<const char*>(std::memchr(m + p, '\n', size - p));
-        e = nl ? static_cast<size_t>(nl - m) : size;
-        next = nl ? e + 1 : size;
-        if (e > p && m[e - 1] == '\r') e--;
-    }
-    // first record start at or after pos: a line "@..." whose third line starts with '+' and whose fourth line is as long as
-    // its second (a quality line may start with '@' too, but then the line two below is a sequence, never a '+' line)
-    static size_t record_start(const char* m, size_t size, size_t pos) {
-        if (pos == 0) return 0;
-        if (pos >= size) return size;
-        size_t p = pos;
-        if (m[pos - 1] != '\n') {
-            const char* nl = static_cast<const char*>(std::memchr(m + pos, '\n', size - pos));
-            if (!nl) return size;
-            p = static_cast<size_t>(nl - m) + 1;
-        }
-        while (p < size) {
-            size_t e0, n0, e1, n1, e2, n2, e3, n3;
-            line_at(m, size, p, e0, n0);
-            if (m[p] == '@' && n0 < size) {
-                line_at(m, size, n0, e1, n1);
-                if (n1 < size) {
-                    line_at(m, size, n1, e2, n2);
-                    if (e2 > n1 && m[n1] == '+' && n2 <= size) {
-                        if (n2 < size) line_at(m, size, n2, e3, n3); else { e3 = n2; n3 = n2; }
-                        if (e3 - n2 == e1 - n0) return p;
-                    }
-                }
-            }
-            p = n0;
-        }
-        return size;
-    }
     bool parse_chunk(const File& f, size_t k, Batch& B, std::string& err) {
         const char* m = f.map;
-        const size_t begin = record_start(m, f.size, k * chunk_), end = record_start(m, f.size, std::min(f.size, (k + 1) * chunk_));
+        const size_t begin = bb::fastq_record_start(m, f.size, k * chunk_), end = bb::fastq_record_start(m, f.size, std::min(f.size, (k + 1) * chunk_));
         size_t p = begin;
         while (p < end) {
-            size_t e0, n0, e1, n1, e2, n2, e3, n3;
-            line_at(m, f.size, p, e0, n0);
-            if (e0 == p) { p = n0; continue; }                     // blank line between records
-            if (n0 >= f.size) { err = "truncated FASTQ record in " + f.path; return false; }
-            line_at(m, f.size, n0, e1, n1);
-            if (n1 >= f.size) { err = "truncated FASTQ record in " + f.path; return false; }
-            line_at(m, f.size, n1, e2, n2);
-            const size_t seq_len = e1 - n0;
-            // the quality line is as long as the sequence: step over it without reading it (half of a FASTQ file is never touched)
-            const size_t q_end = n2 + seq_len;
-            if (q_end == f.size) { e3 = q_end; n3 = q_end; }
-            else if (q_end < f.size && m[q_end] == '\n') { e3 = q_end; n3 = q_end + 1; }
-            else if (q_end + 1 < f.size && m[q_end] == '\r' && m[q_end + 1] == '\n') { e3 = q_end; n3 = q_end + 2; }
-            else if (n2 < f.size) line_at(m, f.size, n2, e3, n3); else { e3 = n2; n3 = n2; }
-            if (m[p] != '@' || e2 == n1 || m[n1] != '+') { err = "malformed FASTQ record in " + f.path; return false; }
-            if (e3 - n2 != seq_len) { err = "truncated FASTQ record (quality length differs from sequence length) in " + f.path; return false; }
-            if (B.bytes + seq_len > B.cap_bytes || B.n_reads + 1 > B.cap_reads) { err = "read longer than the batch buffer (raise --batch-mb)"; return false; }
-            size_t idl = 0;
-            const char* id = m + p + 1;
-            auto ws = [](char c) { return c == ' ' || c == '\t' || c == '\v' || c == '\f' || c == '\r'; };
-            while (idl < e0 - p - 1 && !ws(id[idl])) idl++;
-            B.append(id, idl, m + n0, seq_len);
-            p = n3;
+            bb::FastqRec r; const char* what = nullptr;
+            const int st = bb::fastq_record_at(m, f.size, p, r, what);
+            if (st == 1) continue;                                 // blank line between records
+            if (st < 0) { err = std::string(what) + " in " + f.path; return false; }
+            if (B.bytes + r.seq_len > B.cap_bytes || B.n_reads + 1 > B.cap_reads) { err = "read longer than the batch buffer (raise --batch-mb)"; return false; }
+            size_t idl, doff;
+            bb::fastq_split_header(r.head, r.head_len, idl, doff);
+            B.append(r.head, idl, r.seq, r.seq_len);
         }
         return true;
     }
@@ -587,7 +537,9 @@ struct RowWriter {
     }
 };
 
-int run_annotate(const Args& a, const std::string& out_path) {
+// teardown (optional): the release of the pinned slots and of the GPU contexts is handed to this thread, so that `barbell kit` can
+// start the stages that consume annotation.tsv while the driver unpins ~1 GB and destroys the contexts
+int run_annotate(const Args& a, const std::string& out_path, std::thread* teardown = nullptr) {
     char err[512] = {0};
     bb_groupset* gs = nullptr;
     int rc;
@@ -730,12 +682,18 @@ int run_annotate(const Args& a, const std::string& out_path) {
                     static_cast<unsigned long long>(total_rows), secs, secs > 0 ? total_reads / secs : 0.0);
     }
     const auto t_down = std::chrono::steady_clock::now();
-    ingest.close();
-    for (auto* c : ctx) bb_destroy(c);
-    bb_groups_free(gs);
+    if (teardown) {
+        ingest.source->join(); ingest.source.reset();        // (the source refers to the slot vector: it goes first, here)
+        auto held = std::make_shared<std::vector<Batch>>(std::move(ingest.slots));
+        *teardown = std::thread([held, ctx, gs]() { for (auto& b : *held) b.release(); for (auto* c : ctx) bb_destroy(c); bb_groups_free(gs); });
+    } else {
+        ingest.close();
+        for (auto* c : ctx) bb_destroy(c);
+        bb_groups_free(gs);
+    }
     // (pinning the slots on a second thread beside the context set-up was tried: the driver serialises the two, no gain)
-    if (a.verbose) std::fprintf(stderr, "[timing] setup %.2f s (CUDA context + engine %.2f s, pinned batch slots %.2f s), stream %.2f s, teardown %.2f s\n",
-                                setup_secs, ctx_secs, setup_secs - ctx_secs, secs, since(t_down));
+    if (a.verbose) std::fprintf(stderr, "[timing] setup %.2f s (CUDA context + engine %.2f s, pinned batch slots %.2f s), stream %.2f s, teardown %.2f s%s\n",
+                                setup_secs, ctx_secs, setup_secs - ctx_secs, secs, since(t_down), teardown ? " (continues in the background)" : "");
     return rc;
 }
 
@@ -830,6 +788,7 @@ bb_trim_opts trim_opts_from(const Args& a, bool kit_defaults) {
     }
     o.gzip = a.gzip;
     o.failed_out = a.failed_out.empty() ? nullptr : a.failed_out.c_str();
+    o.threads = std::min(16, std::max(1, a.threads));     // the reference's trim reads on one thread (trim.rs:375-383); the output is the same
     return o;
 }
 
@@ -861,18 +820,24 @@ int run_kit(const Args& a) {
     for (size_t p = 0; p < r.size();) { size_t q = r.find("; ", p); if (q == std::string::npos) q = r.size(); std::printf("Barcodes: %s\n", r.substr(p, q - p).c_str()); p = q + 2; }
     std::printf("\nAnnotating reads...\n");
     const std::string anno = a.output + "/annotation.tsv", filtered = a.output + "/filtered.tsv";
-    int rc = run_annotate(a, anno);
+    std::thread teardown;
+    struct Join { std::thread& t; ~Join() { if (t.joinable()) t.join(); } } join_teardown{teardown};
+    int rc = run_annotate(a, anno, &teardown);
     if (rc != BB_OK) { std::printf("Demultiplexing failed: annotate stage\n"); return 0; }
-    std::printf("\nTop 10 most common patterns\n");
-    rc = bb_inspect(anno.c_str(), 10, (a.output + "/pattern_per_read.tsv").c_str(), 250, err, sizeof err);
-    if (rc != BB_OK) { std::printf("Demultiplexing failed: %s\n", err); return 0; }
-    std::printf("Want to see more patterns? Run: `barbell inspect %s/annotation.tsv -n 100`\n", a.output.c_str());
-    std::printf("\nFiltering reads...\n");
+    // inspect and filter both only read annotation.tsv: the filter runs beside the inspection (its messages are printed in the reference's order)
     const char* const* pats = nullptr; int32_t n_pats = 0;
     bb_kit_filter_patterns(dbl, a.maximize, &pats, &n_pats);
     uint64_t counts[3] = {0, 0, 0};
-    rc = bb_filter(anno.c_str(), filtered.c_str(), nullptr, pats, n_pats, counts, err, sizeof err);
+    char ferr[1024] = {0};
+    int frc = BB_OK;
+    std::thread filt([&] { frc = bb_filter(anno.c_str(), filtered.c_str(), nullptr, pats, n_pats, counts, ferr, sizeof ferr); });
+    std::printf("\nTop 10 most common patterns\n");
+    rc = bb_inspect(anno.c_str(), 10, (a.output + "/pattern_per_read.tsv").c_str(), 250, err, sizeof err);
+    filt.join();
     if (rc != BB_OK) { std::printf("Demultiplexing failed: %s\n", err); return 0; }
+    std::printf("Want to see more patterns? Run: `barbell inspect %s/annotation.tsv -n 100`\n", a.output.c_str());
+    std::printf("\nFiltering reads...\n");
+    if (frc != BB_OK) { std::printf("Demultiplexing failed: %s\n", ferr); return 0; }
     if (a.verbose) write_progress_log(a.output, "filter", {{"Total:", counts[0]}, {"Kept:", counts[1]}, {"Dropped:", counts[2]}});
     std::printf("Total: %llu  Kept: %llu  Dropped: %llu reads\n", static_cast<unsigned long long>(counts[0]),
                 static_cast<unsigned long long>(counts[1]), static_cast<unsigned long long>(counts[2]));

@@ -7,6 +7,8 @@
 //   inspect                  src/inspect/inspect.rs:9-208      bb_inspect()
 //   trim                     src/trim/trim.rs:31-480           bb_trim()
 //   kit pattern sets         src/kits/kits.rs:175-236          bb_kit_filter_patterns()
+#include <fcntl.h>
+#include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
 #include <zlib.h>
@@ -16,7 +18,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
+#include <condition_variable>
 #include <map>
+#include <mutex>
+#include <thread>
 #include <memory>
 #include <string>
 #include <unordered_map>
@@ -706,32 +712,116 @@ int bb_trim(const char* filtered, const char* const* fastq, int32_t n_fastq, con
     std::map<std::string, std::unique_ptr<FastqOut>> writers;
     uint64_t total = 0, trimmed = 0, split = 0, failed_n = 0;
     std::vector<std::string> paths(fastq, fastq + n_fastq);
-    bb::FastqReader reader(paths);
-    bb::FastqReader::View v;
     int rc = BB_OK;
-    while (reader.next(v, e)) {
-        total++;
-        const std::string read_id(v.id, v.id_len);
+    // one record -> its trimmed reads appended to per-label text buffers (the reference's per-record body, trim.rs:375-417)
+    struct Out { std::vector<std::pair<std::string, std::string>> by_label; std::string failed_ids; uint64_t total = 0, trimmed = 0, split = 0, failed = 0; };
+    auto one_record = [&](const char* id, size_t id_len, const char* desc, size_t desc_len, const char* seq, const char* qual, size_t seq_len, Out& O) {
+        O.total++;
+        const std::string read_id(id, id_len);
         auto it = by_read.find(read_id);
-        if (it == by_read.end()) continue;
-        const std::vector<TrimmedRead> results = process_read_and_anno(v.seq, v.qual, v.seq_len, it->second, o);
-        if (!results.empty()) trimmed++;
-        else { failed_n++; if (failed && std::fprintf(failed, "%s\n", read_id.c_str()) < 0) { e = std::string("Failed to write ") + o.failed_out; rc = BB_ERR_IO; } }
-        if (results.size() > 1) split++;
+        if (it == by_read.end()) return;
+        const std::vector<TrimmedRead> results = process_read_and_anno(seq, qual, seq_len, it->second, o);
+        if (!results.empty()) O.trimmed++;
+        else { O.failed++; O.failed_ids += read_id; O.failed_ids += '\n'; }
+        if (results.size() > 1) O.split++;
         for (const TrimmedRead& t : results) {
-            auto w = writers.find(t.label);
+            std::string* dst = nullptr;
+            for (auto& kv : O.by_label) if (kv.first == t.label) { dst = &kv.second; break; }
+            if (!dst) { O.by_label.emplace_back(t.label, std::string()); dst = &O.by_label.back().second; }
+            *dst += '@'; *dst += read_id; *dst += t.suffix;
+            if (o.write_full_header && desc_len) { *dst += ' '; dst->append(desc, desc_len); }
+            *dst += '\n'; *dst += t.seq; *dst += "\n+\n"; *dst += t.qual; *dst += '\n';
+        }
+    };
+    // buffers of one chunk / stretch of records -> the per-label files, in input order (files are created in first-use order)
+    auto flush = [&](Out& O) {
+        total += O.total; trimmed += O.trimmed; split += O.split; failed_n += O.failed;
+        if (failed && !O.failed_ids.empty() && std::fwrite(O.failed_ids.data(), 1, O.failed_ids.size(), failed) != O.failed_ids.size()) { e = std::string("Failed to write ") + o.failed_out; rc = BB_ERR_IO; }
+        for (auto& kv : O.by_label) {
+            auto w = writers.find(kv.first);
             if (w == writers.end()) {
                 auto fo = std::make_unique<FastqOut>();
-                const std::string path = std::string(out_dir) + "/" + t.label + (o.gzip ? ".trimmed.fastq.gz" : ".trimmed.fastq");
-                if (!fo->open(path, o.gzip != 0, e)) { rc = BB_ERR_IO; break; }
-                w = writers.emplace(t.label, std::move(fo)).first;
+                const std::string path = std::string(out_dir) + "/" + kv.first + (o.gzip ? ".trimmed.fastq.gz" : ".trimmed.fastq");
+                if (!fo->open(path, o.gzip != 0, e)) { rc = BB_ERR_IO; return; }
+                w = writers.emplace(kv.first, std::move(fo)).first;
             }
-            std::string rec = "@" + read_id + t.suffix;
-            if (o.write_full_header && v.desc_len) { rec += " "; rec.append(v.desc, v.desc_len); }
-            rec += "\n" + t.seq + "\n+\n" + t.qual + "\n";
-            w->second->write(rec);
+            w->second->write(kv.second);
         }
+        O = Out();
+    };
+    // Plain regular files are mapped, cut into chunks at record boundaries and cut/trimmed by several threads (the annotations are
+    // read-only by now); the calling thread appends the chunks' buffers in input order, so every output file holds exactly what
+    // the reference's single-threaded loop writes.  Anything else (gzip, pipes) goes through one reader.
+    int n_threads = o.threads > 0 ? o.threads : static_cast<int>(std::min(16u, std::max(1u, std::thread::hardware_concurrency())));
+    for (const std::string& path : paths) {
         if (rc != BB_OK) break;
+        int fd = -1; const char* map = nullptr; size_t size = 0;
+        if (n_threads > 1) {
+            fd = ::open(path.c_str(), O_RDONLY);
+            struct stat st;
+            unsigned char magic[2] = {0, 0};
+            if (fd >= 0 && fstat(fd, &st) == 0 && S_ISREG(st.st_mode) && st.st_size > 0 && pread(fd, magic, 2, 0) == 2 && !(magic[0] == 0x1f && magic[1] == 0x8b)) {
+                void* mm = mmap(nullptr, static_cast<size_t>(st.st_size), PROT_READ, MAP_PRIVATE, fd, 0);
+                if (mm != MAP_FAILED) { map = static_cast<const char*>(mm); size = static_cast<size_t>(st.st_size); madvise(mm, size, MADV_SEQUENTIAL); }
+            }
+        }
+        if (map) {
+            size_t chunk = 16u << 20;
+            if (const char* ck = std::getenv("BB_TRIM_CHUNK_KB")) chunk = static_cast<size_t>(std::max(1, std::atoi(ck))) << 10;   // test knob
+            const size_t n_chunks = (size + chunk - 1) / chunk, window = static_cast<size_t>(2 * n_threads);
+            std::vector<Out> outs(n_chunks);
+            std::vector<uint8_t> done(n_chunks, 0);              // 1 = parsed, 2 = error
+            std::vector<std::string> errs(n_chunks);
+            std::atomic<size_t> claim{0};
+            std::mutex mu; std::condition_variable cv;
+            size_t consumed = 0; bool stop = false;
+            auto worker = [&]() {
+                for (;;) {
+                    const size_t c = claim.fetch_add(1);
+                    if (c >= n_chunks) return;
+                    { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return stop || c < consumed + window; }); if (stop) return; }
+                    const size_t begin = bb::fastq_record_start(map, size, c * chunk), end = bb::fastq_record_start(map, size, std::min(size, (c + 1) * chunk));
+                    size_t p = begin; bool ok = true;
+                    while (p < end) {
+                        bb::FastqRec r; const char* what = nullptr;
+                        const int st = bb::fastq_record_at(map, size, p, r, what);
+                        if (st == 1) continue;
+                        if (st < 0) { errs[c] = std::string(what) + " in " + path; ok = false; break; }
+                        size_t idl, doff;
+                        bb::fastq_split_header(r.head, r.head_len, idl, doff);
+                        one_record(r.head, idl, r.head + doff, r.head_len - doff, r.seq, r.qual, r.seq_len, outs[c]);
+                    }
+                    { std::lock_guard<std::mutex> lk(mu); done[c] = ok ? 1 : 2; }
+                    cv.notify_all();
+                }
+            };
+            std::vector<std::thread> pool;
+            for (int t = 0; t < n_threads; t++) pool.emplace_back(worker);
+            for (size_t c = 0; c < n_chunks && rc == BB_OK; c++) {
+                { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return done[c] != 0; }); }
+                if (done[c] == 2) { e = errs[c]; rc = BB_ERR_IO; }
+                else flush(outs[c]);
+                { std::lock_guard<std::mutex> lk(mu); consumed = c + 1; }
+                cv.notify_all();
+            }
+            { std::lock_guard<std::mutex> lk(mu); stop = true; }
+            cv.notify_all();
+            for (auto& t : pool) t.join();
+            munmap(const_cast<char*>(map), size);
+            ::close(fd);
+            continue;
+        }
+        if (fd >= 0) ::close(fd);
+        bb::FastqReader reader(std::vector<std::string>{path});
+        bb::FastqReader::View v;
+        Out O;
+        std::string re;
+        while (rc == BB_OK && reader.next(v, re)) {
+            one_record(v.id, v.id_len, v.desc, v.desc_len, v.seq, v.qual, v.seq_len, O);
+            if (O.total >= 4096) flush(O);
+        }
+        if (rc == BB_OK) flush(O);
+        if (rc == BB_OK && !re.empty()) { e = re; rc = BB_ERR_IO; }
     }
     if (failed && std::fclose(failed) != 0 && rc == BB_OK) { e = std::string("Failed to write ") + o.failed_out; rc = BB_ERR_IO; }
     if (rc == BB_OK && !e.empty()) rc = BB_ERR_IO;

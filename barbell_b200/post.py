@@ -13,7 +13,7 @@ from .api import BarbellError, lib
 class _TrimOpts(C.Structure):
     _fields_ = [("add_labels", C.c_int32), ("add_orientation", C.c_int32), ("add_flank", C.c_int32), ("sort_labels", C.c_int32),
                 ("only_side", C.c_int32), ("write_full_header", C.c_int32), ("skip_trim", C.c_int32), ("flip", C.c_int32),
-                ("gzip", C.c_int32), ("failed_out", C.c_char_p)]
+                ("gzip", C.c_int32), ("failed_out", C.c_char_p), ("threads", C.c_int32)]
 
 
 def _enc(s):

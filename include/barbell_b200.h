@@ -207,6 +207,7 @@ typedef struct {
     int32_t only_side;          /* 0 = none, 1 = LabelSide::Left, 2 = LabelSide::Right (trim.rs:25-29) */
     int32_t write_full_header, skip_trim, flip, gzip;
     const char *failed_out;     /* ids of reads with annotations but no slice; NULL = not written */
+    int32_t threads;            /* plain FASTQ inputs are cut into chunks and trimmed by this many threads (0 = up to 16), output order unchanged */
 } bb_trim_opts;
 /* trim_matches, src/trim/trim.rs:317-480: cuts every read of the FASTQ files that has rows in filtered.tsv and writes
  * <out_dir>/<label>.trimmed.fastq[.gz].  counts = {total, trimmed, trimmed_split, failed} reads (trim.rs:19-22). */

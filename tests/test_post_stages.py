@@ -20,7 +20,7 @@ import barbell_b200 as bb  # noqa: E402
 class TrimOpts(C.Structure):
     _fields_ = [("add_labels", C.c_int32), ("add_orientation", C.c_int32), ("add_flank", C.c_int32), ("sort_labels", C.c_int32),
                 ("only_side", C.c_int32), ("write_full_header", C.c_int32), ("skip_trim", C.c_int32), ("flip", C.c_int32),
-                ("gzip", C.c_int32), ("failed_out", C.c_char_p)]
+                ("gzip", C.c_int32), ("failed_out", C.c_char_p), ("threads", C.c_int32)]
 
 
 @pytest.fixture(scope="module")
@@ -315,6 +315,16 @@ def test_trim_random_equals_oracle(lib, tmp_path, kw):
     assert files == {k: "".join(v) for k, v in want.items()}
     assert counts == [len(reads), n_trim, n_split, n_fail] and n_trim > 20
     assert len(failed.split()) == n_fail
+    # the FASTQ is cut into chunks that several threads trim; the files must not depend on the chunking (1 KB chunks: records straddle
+    # chunks, chunks without a record start) nor on the input being gzip (one sequential reader)
+    os.environ["BB_TRIM_CHUNK_KB"] = "1"
+    try:
+        files2, counts2, failed2 = c_trim(lib, tmp_path, kept, reads, **kw)
+    finally:
+        del os.environ["BB_TRIM_CHUNK_KB"]
+    assert files2 == files and counts2 == counts and failed2 == failed
+    files3, counts3, failed3 = c_trim(lib, tmp_path, kept, reads, gz_in=True, **kw)
+    assert files3 == files and counts3 == counts and failed3 == failed
 
 
 def test_cli_filter_inspect_trim(tmp_path):
@@ -392,5 +402,6 @@ def test_trim_reports_failed_writes(lib, tmp_path):
     o = TrimOpts(1, 1, 1, 1, 0, 1, 0, 0, 0, None)
     paths = (C.c_char_p * 1)(str(fq).encode())
     counts, err = (C.c_uint64 * 4)(), C.create_string_buffer(1024)
-    rc = lib.bb_trim(str(tsv).encode(), paths, 1, str(out).encode(), C.byref(o), counts, err, len(err))
+    lib.bb_trim.argtypes = None                          # (another module may have bound its own struct class to this symbol)
+    rc = lib.bb_trim(str(tsv).encode(), paths, 1, str(out).encode(), C.byref(o), counts, err, C.c_size_t(len(err)))
     assert rc == -6 and b"Failed to write" in err.value, (rc, err.value)
