@@ -117,6 +117,10 @@ struct Engine {
     uint32_t last_hits = 0;
     uint64_t last_rows = 0, last_reads = 0, last_kept = 0;
 
+    static double now_ms() {
+        static const auto t0 = std::chrono::steady_clock::now();
+        return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    }
     void set_error(const char* fmt, ...) {
         char buf[512];
         va_list ap; va_start(ap, fmt); std::vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
@@ -489,15 +493,13 @@ struct Engine {
         return BB_OK;
     }
 
-    static double now_ms() {
-        static const auto t0 = std::chrono::steady_clock::now();
-        return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-    }
     // host buffers that already hold the 2-bit wire format (bb_submit_packed): copy, expand on the device, run, rows to pinned memory
     int run_host_packed(const uint8_t* crumbs, uint64_t total, const uint64_t* exc, uint64_t n_exc, const uint64_t* offsets, uint32_t n_reads, uint64_t* n_rows) {
         BB_CUDA(cudaSetDevice(device));
         *n_rows = 0;
         if (n_reads == 0 || total == 0) { last_reads = n_reads; last_rows = 0; last_kept = 0; return BB_OK; }
+        static const bool trace = std::getenv("BB_TRACE") != nullptr;        // one line of host timestamps per batch on stderr
+        const double tr0 = now_ms();
         const size_t pk = (static_cast<size_t>((total + 3) / 4) + 63) & ~size_t(63);
         BB_CUDA(d_bases.ensure(((total + 15) & ~15ull) + 16));
         BB_CUDA(d_offsets.ensure(static_cast<size_t>(n_reads + 1) * 8));
@@ -514,14 +516,19 @@ struct Engine {
             launches++;
         }
         BB_CUDA(cudaGetLastError());
+        const double tr1 = now_ms();
         int rc = run(d_bases.as<uint8_t>(), d_offsets.as<uint64_t>(), n_reads, total, stream, n_rows);
         if (rc != BB_OK) return rc;
+        const double tr2 = now_ms();
         if (*n_rows) {
             rc = ensure_host_rows(*n_rows);
             if (rc != BB_OK) return rc;
             BB_CUDA(cudaMemcpyAsync(h_rows, d_rows_out.p, *n_rows * sizeof(bb_row), cudaMemcpyDeviceToHost, stream));
             BB_CUDA(cudaStreamSynchronize(stream));
         }
+        if (trace)
+            std::fprintf(stderr, "[bb trace] eng %p packed batch: start %.2f queued +%.2f kernels-done +%.2f rows-home +%.2f ms  (%u reads, device stages %.2f ms)\n",
+                         static_cast<void*>(this), tr0, tr1 - tr0, tr2 - tr0, now_ms() - tr0, n_reads, stage_ms[0] + stage_ms[1] + stage_ms[2] + stage_ms[3] + stage_ms[4]);
         return BB_OK;
     }
     // host-buffer form: copy in, run, copy rows to pinned memory
