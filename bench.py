@@ -82,7 +82,8 @@ def product_groups(cfg):
 
 
 def config_dict(name, cfg, n_reads, world):
-    """The `config` object of the JSON line -- the same function serves both arms, so equal workloads give equal objects."""
+    """The `config` object of the JSON line -- the same function serves both arms, so equal workloads give equal objects.
+    (The read counts BASELINE.json names -- 10 M, 50 M, 100 M -- are reached by looping the batch: reads/s does not depend on it.)"""
     return dict(workload=cfg["workload"], name=name, kit=cfg.get("kit", f"dual-end panel, 2 x {cfg.get('panel')} barcodes"),
                 options=cfg["kw"], reads_per_step=n_reads, read_len=READ_LEN, batch_bytes=n_reads * READ_LEN,
                 l2_policy="batch larger than the 126 MB L2; same batch every step",
@@ -483,7 +484,7 @@ def main():
                                      note="rows per barcode of the last step, all ranks (all_reduce of %d int64)" % len(hist)))
         if world == 1 and not args.no_e2e_fastq:
             out["e2e_fastq"] = fastq_leg(cfg, G, args.fastq_reads, args.fastq_passes, min(16, os.cpu_count() or 1))
-        if not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline:       # (rank 0 at N = 1 only)
             import oracle_lib as O
             Go = oracle_groups(cfg)
             assert [(g["flank"], g["k_flank"], g["barcodes"]) for g in Go] == [(g["flank"], g["k_flank"], g["barcodes"]) for g in G]
