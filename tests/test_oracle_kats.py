@@ -13,11 +13,17 @@ def rc(s):
     return bytes({65: 84, 84: 65, 67: 71, 71: 67}.get(c, 78) for c in reversed(s))
 
 
-@pytest.fixture(params=[1, 0], ids=["bitvector", "naive"])
+# both DP back-ends of the oracle x every setting of the search policies that the reference's tests leave open (S1 plateau side,
+# S2 text-only vs pattern-only, S5, S6, S3 rounding): the five known-answer tests must hold under ALL of them -- they are what
+# makes a setting admissible, and they are why those policies are switches and not facts
+POLICY_FLAGS = [0, 1, 2, 4, 8, 16, 32, 1 | 2, 1 | 2 | 4 | 8, 1 | 2 | 4 | 8 | 16, 1 | 2 | 4 | 8 | 32]
+
+
+@pytest.fixture(params=[(m, f) for m in (1, 0) for f in POLICY_FLAGS], ids=lambda p: f"{'bitvector' if p[0] else 'naive'}-pol{p[1]}")
 def mode(request):
-    O.set_policy(request.param)
+    O.set_policy(request.param[0], request.param[1])
     yield request.param
-    O.set_policy(1)
+    O.set_policy(1, 0)
 
 
 # ---- reference src/annotate/cigar_parse.rs:104-176 (the only KATs at the sassy boundary) ----
@@ -107,7 +113,8 @@ def test_bottom_row_is_edit_distance():
 
 
 def test_matches_are_valid_alignments(mode):
-    rnd = random.Random(2 + mode)
+    rnd = random.Random(2 + mode[0])
+    pol = mode[1]
     for it in range(60):
         m = rnd.choice([8, 20, 46, 70, 115])
         p = bytes(rnd.choice(b"ACGTN") if rnd.random() < 0.3 else rnd.choice(b"ACGT") for _ in range(m))
@@ -137,8 +144,11 @@ def test_matches_are_valid_alignments(mode):
             over = mt.pattern_start + (m - mt.pattern_end)
             if alpha >= 0:
                 import math
-                extra = math.floor(np.float32(mt.pattern_start) * np.float32(alpha)) + \
-                    math.floor(np.float32(m - mt.pattern_end) * np.float32(alpha))
+
+                def over_cost(t):                     # policy S3: floor (default) / round-to-nearest / ceil of the f32 product
+                    v = np.float32(t) * np.float32(alpha)
+                    return math.floor(v + np.float32(0.5)) if pol & O.POL_S3_ROUND else math.ceil(v) if pol & O.POL_S3_CEIL else math.floor(v)
+                extra = over_cost(mt.pattern_start) + over_cost(m - mt.pattern_end)
             else:
                 extra = 0
                 assert over == 0
@@ -153,10 +163,11 @@ def test_backends_agree_on_random_and_adversarial_text():
         for p in pats:
             for k in (0, 2, 6):
                 for alpha in (-1.0, 0.4):
-                    O.set_policy(1); a = [repr(m) for m in O.search(p, t, k, alpha=alpha)]
-                    O.set_policy(0); b = [repr(m) for m in O.search(p, t, k, alpha=alpha)]
-                    O.set_policy(1)
-                    assert a == b, (t[:20], p[:20], k, alpha)
+                    for pol in (0, 1 | 2 | 4 | 8 | 16):
+                        O.set_policy(1, pol); a = [repr(m) for m in O.search(p, t, k, alpha=alpha)]
+                        O.set_policy(0, pol); b = [repr(m) for m in O.search(p, t, k, alpha=alpha)]
+                        O.set_policy(1, 0)
+                        assert a == b, (t[:20], p[:20], k, alpha, pol)
 
 
 def test_rc_search_is_forward_search_of_reverse_complement():
