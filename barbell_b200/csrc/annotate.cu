@@ -355,7 +355,7 @@ struct Engine {
         BB_CUDA(cudaEventRecord(ev[1], st));
         // per-read resolve (sort + unique + local minima inside one warp), prefix sum of the match counts, gather in read order
         k_read_resolve<<<(n_reads + kResolveWarps - 1) / kResolveWarps, kResolveWarps * 32, 0, st>>>(
-            d_slots.as<uint64_t>(), d_slot_cnt.as<uint32_t>(), n_reads, offsets, d_groups(), d_nh.as<uint32_t>(), pol);
+            d_slots.as<uint64_t>(), d_slot_cnt.as<uint32_t>(), n_reads, offsets, d_groups(), d_nh.as<uint32_t>(), pol, slot_cap);
         launches++;
         BB_CUDA(cudaMemsetAsync(d_nh.as<uint32_t>() + n_reads, 0, 4, st));
         {

@@ -99,29 +99,30 @@ void crumbs_scalar(const uint8_t* src, size_t pos0, size_t n, uint8_t* dst, cons
     }
 }
 
-// 128 input bytes -> 32 output bytes per iteration
+// 128 input bytes -> 32 output bytes per iteration.  A C G T (any case; U as T) are told apart arithmetically: with x = c >> 1 and
+// y = c >> 2 the two low bits of x ^ y are 0 1 2 3 for A C G T; a byte is one of those letters iff (c | 0x20) equals the letter its
+// low nibble stands for (1 a, 3 c, 4 t, 5 u, 7 g).  Everything else gets crumb 0 and an exception entry with its 4-bit base set.
 __attribute__((target("avx2"))) void crumbs_avx2(const uint8_t* src, size_t pos0, size_t n, uint8_t* dst, const uint8_t* code, ExcWriter& w) {
-    alignas(32) uint8_t tl[32], th[32];
-    for (int i = 0; i < 16; i++) { tl[i] = tl[i + 16] = code[0x40 + i]; th[i] = th[i + 16] = code[0x50 + i]; }
-    const __m256i TL = _mm256_load_si256(reinterpret_cast<const __m256i*>(tl));
-    const __m256i TH = _mm256_load_si256(reinterpret_cast<const __m256i*>(th));
-    const __m256i S = _mm256_load_si256(reinterpret_cast<const __m256i*>(kCrumbOfSet));
-    const __m256i three = _mm256_set1_epi8(3);
+    alignas(32) static const uint8_t kLetter[32] = {0, 'a', 0, 'c', 't', 'u', 0, 'g', 0, 0, 0, 0, 0, 0, 0, 0,
+                                                    0, 'a', 0, 'c', 't', 'u', 0, 'g', 0, 0, 0, 0, 0, 0, 0, 0};
+    const __m256i L = _mm256_load_si256(reinterpret_cast<const __m256i*>(kLetter));
+    const __m256i three = _mm256_set1_epi8(3), low4 = _mm256_set1_epi8(0x0f), lower = _mm256_set1_epi8(0x20);
     const __m256i mul4 = _mm256_set1_epi16(0x0401), mul16 = _mm256_set1_epi16(0x1001);
     const bool aligned = (reinterpret_cast<uintptr_t>(dst) & 31) == 0;
     size_t i = 0;
     for (; i + 128 <= n; i += 128) {
         __m256i c[4];
         for (int q = 0; q < 4; q++) {
-            const __m256i v = codes32(_mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + i + 32 * q)), TL, TH);
-            const __m256i s = _mm256_shuffle_epi8(S, v);
-            uint32_t m = static_cast<uint32_t>(_mm256_movemask_epi8(s));
+            const __m256i v = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + i + 32 * q));
+            const __m256i ok = _mm256_cmpeq_epi8(_mm256_or_si256(v, lower), _mm256_shuffle_epi8(L, _mm256_and_si256(v, low4)));
+            uint32_t m = ~static_cast<uint32_t>(_mm256_movemask_epi8(ok));
             while (m) {                                                     // rare: bytes that are not a single base
                 const int t = __builtin_ctz(m); m &= m - 1;
                 const size_t at = i + 32 * q + t;
                 w.push(static_cast<uint64_t>(pos0 + at) << 4 | code[src[at]]);
             }
-            c[q] = _mm256_and_si256(s, three);
+            const __m256i x = _mm256_xor_si256(_mm256_srli_epi16(v, 1), _mm256_srli_epi16(v, 2));   // (bits shifted in from the neighbour byte land above bit 1)
+            c[q] = _mm256_and_si256(_mm256_and_si256(x, three), ok);
         }
         const __m256i n01 = _mm256_permute4x64_epi64(_mm256_packus_epi16(_mm256_maddubs_epi16(c[0], mul4), _mm256_maddubs_epi16(c[1], mul4)), 0xD8);
         const __m256i n23 = _mm256_permute4x64_epi64(_mm256_packus_epi16(_mm256_maddubs_epi16(c[2], mul4), _mm256_maddubs_epi16(c[3], mul4)), 0xD8);

@@ -795,13 +795,13 @@ constexpr int kResolveWarps = 4;
 
 __global__ void __launch_bounds__(kResolveWarps * 32) k_read_resolve(uint64_t* __restrict__ slots, const uint32_t* __restrict__ slot_cnt, uint32_t n_reads,
                                                                       const uint64_t* __restrict__ offsets, const DevGroup* __restrict__ groups,
-                                                                      uint32_t* __restrict__ n_hits_read, int pol) {
+                                                                      uint32_t* __restrict__ n_hits_read, int pol, uint32_t slot_cap) {
     __shared__ uint64_t s_raw[kResolveWarps][kSlotCap], s_sorted[kResolveWarps][kSlotCap];
     __shared__ uint8_t s_first[kResolveWarps][kSlotCap];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const uint32_t r = blockIdx.x * kResolveWarps + wib;
     if (r >= n_reads) return;
-    const uint32_t n = min(__ldg(slot_cnt + r), static_cast<uint32_t>(kSlotCap));
+    const uint32_t n = min(__ldg(slot_cnt + r), slot_cap);     // (a read that overflowed its slots: the batch is re-run, only written slots are read)
     if (n == 0) { if (lane == 0) n_hits_read[r] = 0; return; }
     uint64_t* mine = slots + static_cast<size_t>(r) * kSlotCap;
     uint64_t* raw = s_raw[wib]; uint64_t* sorted = s_sorted[wib]; uint8_t* first = s_first[wib];
