@@ -348,7 +348,7 @@ struct Engine {
         A.slots = d_slots.as<uint64_t>(); A.slot_cnt = d_slot_cnt.as<uint32_t>(); A.slot_cap = kSlotCap; A.slot_overflow = d_cnt + 9;
         uint32_t slot_cap = kSlotCap;
         if (const char* sc = std::getenv("BB_SLOT_CAP")) slot_cap = static_cast<uint32_t>(std::min(kSlotCap, std::max(1, std::atoi(sc))));   // test knob
-        A.slot_cap = slot_cap;
+        A.slot_cap = slot_cap; A.slot_stride = kSlotCap;
         bool filtered = false;
         rc = launch_scans(A, n_tiles, total, false, st, &filtered);
         if (rc != BB_OK) return rc;

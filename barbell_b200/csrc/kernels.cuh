@@ -153,7 +153,7 @@ struct ScanArgs {
     uint32_t cap;
     uint64_t* slots;             // ... or, when non-null, per-read entry slots [n_reads][slot_cap] + per-read counts (slot path)
     uint32_t* slot_cnt;
-    uint32_t slot_cap;
+    uint32_t slot_cap, slot_stride;   // slots usable per read (<= stride; a test knob lowers it) / distance between two reads' slots
     uint32_t* slot_overflow;     // set when a read has more entries than slots (the batch is then re-run on the sorted path)
 };
 
@@ -238,7 +238,7 @@ __device__ __forceinline__ void scan_emit(const ScanArgs& A, uint32_t r, int str
     const uint64_t key = make_key(r, A.group, strand ^ A.strand_xor, pos, cost);
     if (A.slots) {
         const uint32_t idx = atomicAdd(A.slot_cnt + r, 1u);
-        if (idx < A.slot_cap) A.slots[static_cast<size_t>(r) * A.slot_cap + idx] = key;
+        if (idx < A.slot_cap) A.slots[static_cast<size_t>(r) * A.slot_stride + idx] = key;
         else atomicExch(A.slot_overflow, 1u);
         return;
     }
