@@ -41,7 +41,7 @@ struct Args {
     std::string dropped, failed_out, only_side, read_pattern_out;
     bool no_label = false, no_orientation = false, no_flanks = false, sort_labels = false, skip_trim = false, flip = false;
     int top_n = 10, bucket_size = 250;
-    bool output_given = false, single_reader = false, no_pack = false;
+    bool output_given = false, single_reader = false, no_pack = false, count_only = false;
     size_t chunk_kb = 0;
     double min_score = 0.2, min_score_diff = 0.1;
     float alpha = 0.4f;
@@ -107,6 +107,7 @@ Args parse(int argc, char** argv) {
         else if (f == "--verbose") a.verbose = true;
         else if (f == "--single-reader") a.single_reader = true;
         else if (f == "--no-pack") a.no_pack = true;
+        else if (f == "--count-only") a.count_only = true;
         else if (f == "--policy") a.policy = static_cast<unsigned>(std::atoi(one().c_str()));
         else if (f == "--chunk-kb") a.chunk_kb = static_cast<size_t>(std::atol(one().c_str()));
         else if (f == "--use-extended") a.use_extended = true;
@@ -714,6 +715,7 @@ int run_fastq_stats(const Args& a) {
         const Batch& B = ingest.slots[cur];
         if (B.exc_overflow) { std::printf("Error during processing: exception list overflow (re-run with --no-pack)\n"); rc = 1; ingest.source->abort(); break; }
         std::vector<char> text;
+        if (a.count_only) { n += B.n_reads; bases += B.bytes; batches++; ingest.source->release(cur); continue; }   // parser throughput only
         if (B.packed) {
             // the packed form decoded the way the device does it (k_unpack_crumbs + k_patch_exceptions): one letter per base set
             text.resize(B.bytes);

@@ -535,7 +535,7 @@ def test_slot_path_overflows_fall_back_to_the_sorted_path(monkeypatch):
             an.close()
     rows, hits = run()
     assert rows.tobytes() == want.tobytes() and (hits == want_h).all()
-    for key, val in (("BB_SLOT_CAP", "8"), ("BB_HITS_CAP", "100"), ("BB_GLUE", "sort")):
+    for key, val in (("BB_SLOT_CAP", "8"), ("BB_SLOT_CAP", "120"), ("BB_HITS_CAP", "100"), ("BB_GLUE", "sort")):
         monkeypatch.setenv(key, val)
         rows2, hits2 = run()
         monkeypatch.delenv(key)
