@@ -114,7 +114,10 @@ class ClockSampler:
     def mark(self):
         return time.time()
 
-    def stop(self, t0=None, t1=None):
+    def count(self, t0):
+        return sum(1 for ts, _ in self.lines if ts >= t0)
+
+    def stop(self, t0=None, t1=None, window="timed region"):
         if not self.proc:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
         self.proc.terminate()
@@ -124,10 +127,6 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], None, set()
         lines = [ln for ts, ln in self.lines if t0 is None or (t0 <= ts <= t1 + 0.05)]
-        window = "timed region"
-        if len(lines) < 3:                      # region shorter than the sampling period: use warm-up + timed region (same load)
-            lines = [ln for ts, ln in self.lines]
-            window = "warm-up + timed region"
         for ln in lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
@@ -294,6 +293,8 @@ def main():
         except (AttributeError, OSError):
             os.environ.setdefault("BB_PACK_THREADS", str(max(1, (os.cpu_count() or 1) // local_world)))
 
+    sampler = ClockSampler(local)
+    sampler.start()                                         # early: nvidia-smi takes a few hundred ms to deliver its first line
     gs = product_groups(cfg)
     G = gs.as_dicts()
     an = bb.Annotator(gs, device=local)
@@ -313,8 +314,6 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    sampler = ClockSampler(local)
-    sampler.start()
     for _ in range(args.warmup):
         n_rows = step()
     barrier()
@@ -332,8 +331,19 @@ def main():
             stage_acc[k] = stage_acc.get(k, 0.0) + v
     ev1.record(stream)
     barrier()
-    clocks = sampler.stop(t_mark0, sampler.mark())
     launches = an.kernel_launches() - l0
+    t_mark1 = sampler.mark()
+    window = "timed region"
+    if sampler.count(t_mark0) < 5:
+        # the timed region is shorter than a few sampling periods (20 ms each): keep the SAME load running, untimed, until five
+        # samples under load exist (at most 2 s), and say so
+        t_lim = time.time() + 2.0
+        while sampler.count(t_mark0) < 5 and time.time() < t_lim:
+            step()
+        torch.cuda.synchronize()
+        t_mark1 = sampler.mark()
+        window = "timed region + identical untimed steps right after it (region shorter than five 20 ms samples)"
+    clocks = sampler.stop(t_mark0, t_mark1, window)
     ms = ev0.elapsed_time(ev1)
     hist_local = sharding.label_histogram(an.fetch_rows(int(n_rows)), G)     # rows of the last timed step (outside the timed region)
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
