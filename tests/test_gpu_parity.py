@@ -569,3 +569,27 @@ def test_cli_in_process_multi_gpu(tmp_path):
         assert bb.rows_to_tsv(an.annotate(b, o), gs, ids) == outs[0]
     finally:
         an.close()
+
+
+def test_barcodes_with_ambiguity_codes_in_the_patterns():
+    """Custom query sets may carry IUPAC codes inside the barcodes themselves (README custom-primer example): the barcode stage's
+    text masks are indexed by the pattern character's 4-bit base set, so R / Y / N rows match two / two / four bases.  Also a
+    panel whose barcodes share their first bases (the shared leading rows then reach into the barcode)."""
+    rnd = np.random.default_rng(123)
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    pre, suf = b"GGTCTAGACCATGCTAGGAT", b"TTGACCGATTCAGGCATCAA"
+    seqs = []
+    for i in range(40):
+        core = bytearray(bytes(rnd.choice(acgt, 24)))
+        core[0:3] = b"ACG"                                            # common first barcode bases: more shared rows
+        core[3] = b"ACGT"[i % 4]
+        core[-1] = b"ACGT"[(i // 4) % 4]
+        for pos, ch in ((7, b"R"), (12, b"Y"), (15, b"N"), (18, b"K")):
+            if (i + pos) % 3 == 0:
+                core[pos] = ch[0]
+        seqs.append(pre + bytes(core) + suf)
+    gs = bb.GroupSet.from_seqs([(seqs, [f"I{i}" for i in range(40)], 0)])
+    assert gs.as_dicts()[0]["bar_region"][0] == len(pre) + 3          # the common barcode prefix moved into the flank (barcodes.rs LCP)
+    b, o, _ = synth.make_reads(gs.as_dicts(), 800, (200, 2500), seed=124)
+    rows = _check(gs, b, o)
+    assert (rows["match_type"] < 2).sum() > 200
