@@ -80,52 +80,86 @@ bool parse_i64(const std::string& s, int64_t& v) {
 // ---------------------------------------------------------------------------------------------------------------
 // TSV reader / writer (csv crate, tab delimiter, header row; fields of this format never need quoting)
 // ---------------------------------------------------------------------------------------------------------------
+// The file is mapped and every line is parsed in place (field = pointer + length; no per-field strings): annotation.tsv of a large
+// run holds tens of millions of rows, and filter, inspect and trim each read all of it.
 class TsvReader {
   public:
     bool open(const std::string& path, std::string& err) {
-        f_ = std::fopen(path.c_str(), "r");
-        if (!f_) { err = path + ": " + std::strerror(errno); return false; }
-        std::string line;
-        if (!getline(line)) { empty_ = true; return true; }           // 0-byte file: a run without hits (annotator.rs:20-24)
-        std::vector<std::string> h = split(line);
+        fd_ = ::open(path.c_str(), O_RDONLY);
+        struct stat st;
+        if (fd_ < 0 || fstat(fd_, &st) != 0) { err = path + ": " + std::strerror(errno); return false; }
+        size_ = static_cast<size_t>(st.st_size);
+        if (size_ == 0) { empty_ = true; return true; }               // 0-byte file: a run without hits (annotator.rs:20-24)
+        void* m = mmap(nullptr, size_, PROT_READ, MAP_PRIVATE, fd_, 0);
+        if (m == MAP_FAILED) {                                       // not mappable (a pipe): read it all
+            owned_.clear();
+            char buf[1 << 16];
+            ssize_t n;
+            while ((n = ::read(fd_, buf, sizeof buf)) > 0) owned_.append(buf, static_cast<size_t>(n));
+            data_ = owned_.data(); size_ = owned_.size();
+            if (size_ == 0) { empty_ = true; return true; }
+        } else {
+            data_ = static_cast<const char*>(m); mapped_ = true;
+            madvise(m, size_, MADV_SEQUENTIAL);
+        }
+        Field f[kMaxCols]; int nf;
+        if (!next_line(f, nf)) { empty_ = true; return true; }
         for (int c = 0; c < 15; c++) {
             col_[c] = -1;
-            for (size_t i = 0; i < h.size(); i++) if (h[i] == kHeader[c]) col_[c] = static_cast<int>(i);
+            const size_t hl = std::strlen(kHeader[c]);
+            for (int i = 0; i < nf; i++) if (f[i].n == hl && std::memcmp(f[i].p, kHeader[c], hl) == 0) col_[c] = i;
             if (col_[c] < 0) { err = "CSV deserialize error: missing field `" + std::string(kHeader[c]) + "`"; return false; }
         }
         return true;
     }
-    ~TsvReader() { if (f_) std::fclose(f_); }
+    ~TsvReader() { if (mapped_) munmap(const_cast<char*>(data_), size_); if (fd_ >= 0) ::close(fd_); }
     // 1 = row, 0 = end, -1 = error
     int next(Row& r, std::string& err) {
         if (empty_) return 0;
-        std::string line;
+        Field f[kMaxCols]; int nf;
         for (;;) {
-            if (!getline(line)) return 0;
-            if (!line.empty()) break;
+            if (!next_line(f, nf)) return 0;
+            if (!(nf == 1 && f[0].n == 0)) break;                    // blank line
         }
         lineno_++;
-        const std::vector<std::string> f = split(line);
-        auto get = [&](int c) -> const std::string& { static const std::string none; return col_[c] < static_cast<int>(f.size()) ? f[col_[c]] : none; };
-        auto bad = [&](int c) { err = "CSV deserialize error: record " + std::to_string(lineno_) + ": field `" + kHeader[c] + "`: invalid value `" + get(c) + "`"; return -1; };
-        r = Row();
-        r.read_id = get(0);
-        if (!parse_u64(get(1), r.read_len)) return bad(1);
-        if (!parse_i64(get(2), r.rel_dist_to_end)) return bad(2);
+        static const Field none{"", 0};
+        auto get = [&](int c) -> const Field& { return col_[c] < nf ? f[col_[c]] : none; };
+        auto bad = [&](int c) { err = "CSV deserialize error: record " + std::to_string(lineno_) + ": field `" + kHeader[c] + "`: invalid value `" + std::string(get(c).p, get(c).n) + "`"; return -1; };
+        auto u64 = [](const Field& x, uint64_t& v) {
+            if (x.n == 0) return false;
+            size_t i = x.p[0] == '+' ? 1 : 0;
+            if (i >= x.n) return false;
+            v = 0;
+            for (; i < x.n; i++) { const unsigned d = static_cast<unsigned char>(x.p[i]) - '0'; if (d > 9) return false; v = v * 10 + d; }
+            return true;
+        };
+        auto i64 = [&](const Field& x, int64_t& v) {
+            if (x.n == 0) return false;
+            const bool neg = x.p[0] == '-';
+            uint64_t u;
+            if (!u64(neg ? Field{x.p + 1, x.n - 1} : x, u)) return false;
+            v = neg ? -static_cast<int64_t>(u) : static_cast<int64_t>(u);
+            return true;
+        };
+        auto is = [](const Field& x, const char* lit) { const size_t n = std::strlen(lit); return x.n == n && std::memcmp(x.p, lit, n) == 0; };
+        r.read_id.assign(get(0).p, get(0).n);
+        r.cuts.clear();
+        if (!u64(get(1), r.read_len)) return bad(1);
+        if (!i64(get(2), r.rel_dist_to_end)) return bad(2);
         uint64_t* u[] = {&r.read_start_bar, &r.read_end_bar, &r.read_start_flank, &r.read_end_flank, &r.bar_start, &r.bar_end};
-        for (int c = 3; c <= 8; c++) if (!parse_u64(get(c), *u[c - 3])) return bad(c);
+        for (int c = 3; c <= 8; c++) if (!u64(get(c), *u[c - 3])) return bad(c);
         r.match_type = -1;
-        for (int t = 0; t < 4; t++) if (get(9) == kTypeNames[t]) r.match_type = t;
+        for (int t = 0; t < 4; t++) if (is(get(9), kTypeNames[t])) r.match_type = t;
         if (r.match_type < 0) return bad(9);
         int64_t v;
-        if (!parse_i64(get(10), v)) return bad(10);
+        if (!i64(get(10), v)) return bad(10);
         r.flank_cost = static_cast<int32_t>(v);
-        if (!parse_i64(get(11), v)) return bad(11);
+        if (!i64(get(11), v)) return bad(11);
         r.barcode_cost = static_cast<int32_t>(v);
-        r.label = get(12);
-        if (get(13) == "Fwd") r.strand = 0; else if (get(13) == "Rc") r.strand = 1; else { err = "Invalid strand: " + get(13); return -1; }
+        r.label.assign(get(12).p, get(12).n);
+        if (is(get(13), "Fwd")) r.strand = 0; else if (is(get(13), "Rc")) r.strand = 1; else { err = "Invalid strand: " + std::string(get(13).p, get(13).n); return -1; }
         // cuts: "After(0):1,Before(0):2" (searcher.rs:105-142)
-        const std::string& cs = get(14);
+        const std::string cs(get(14).p, get(14).n);
         size_t p = 0;
         while (p < cs.size()) {
             size_t q = cs.find(',', p);
@@ -150,68 +184,79 @@ class TsvReader {
     }
 
   private:
-    bool getline(std::string& out) {
-        out.clear();
-        char buf[4096];
-        bool any = false;
-        while (std::fgets(buf, sizeof buf, f_)) {
-            any = true;
-            const size_t n = std::strlen(buf);
-            out.append(buf, n);
-            if (n && buf[n - 1] == '\n') break;
-        }
-        while (!out.empty() && (out.back() == '\n' || out.back() == '\r')) out.pop_back();
-        return any;
-    }
-    static std::vector<std::string> split(const std::string& line) {
-        std::vector<std::string> f;
-        size_t p = 0;
+    struct Field { const char* p; size_t n; };
+    static constexpr int kMaxCols = 64;
+    // the fields of the next line (quotes around a whole field are dropped, like the csv crate does); false at the end of the file
+    bool next_line(Field* f, int& nf) {
+        if (pos_ >= size_) return false;
+        const char* s = data_ + pos_;
+        const char* nl = static_cast<const char*>(std::memchr(s, '\n', size_ - pos_));
+        const char* e = nl ? nl : data_ + size_;
+        pos_ = static_cast<size_t>(e - data_) + (nl ? 1 : 0);
+        while (e > s && (e[-1] == '\r' || e[-1] == '\n')) e--;
+        nf = 0;
+        const char* p = s;
         for (;;) {
-            const size_t q = line.find('\t', p);
-            std::string v = line.substr(p, q == std::string::npos ? std::string::npos : q - p);
-            if (v.size() >= 2 && v.front() == '"' && v.back() == '"') v = v.substr(1, v.size() - 2);
-            f.push_back(v);
-            if (q == std::string::npos) break;
-            p = q + 1;
+            const char* t = static_cast<const char*>(std::memchr(p, '\t', static_cast<size_t>(e - p)));
+            const char* fe = t ? t : e;
+            Field x{p, static_cast<size_t>(fe - p)};
+            if (x.n >= 2 && x.p[0] == '"' && x.p[x.n - 1] == '"') { x.p++; x.n -= 2; }
+            if (nf < kMaxCols) f[nf++] = x;
+            if (!t) break;
+            p = t + 1;
         }
-        return f;
+        return true;
     }
-    FILE* f_ = nullptr;
+    int fd_ = -1;
+    const char* data_ = nullptr;
+    size_t size_ = 0, pos_ = 0;
+    bool mapped_ = false;
+    std::string owned_;
     int col_[15];
     bool empty_ = false;
     uint64_t lineno_ = 0;
 };
 
-class TsvWriter {
+class TsvWriter {                                        // rows are formatted by hand into a large buffer
   public:
     bool open(const std::string& path, std::string& err) {
         f_ = std::fopen(path.c_str(), "w");
         if (!f_) { err = path + ": " + std::strerror(errno); return false; }
-        std::setvbuf(f_, nullptr, _IOFBF, 1 << 20);
+        buf_.reserve(4u << 20);
         return true;
     }
-    ~TsvWriter() { if (f_) std::fclose(f_); }
+    ~TsvWriter() { close(); }
     void write(const Row& r) {
         if (!header_) {               // the csv writer emits the header with the first serialised row
-            for (int c = 0; c < 15; c++) std::fprintf(f_, "%s%s", kHeader[c], c == 14 ? "\n" : "\t");
+            for (int c = 0; c < 15; c++) { buf_ += kHeader[c]; buf_ += c == 14 ? '\n' : '\t'; }
             header_ = true;
         }
-        std::fprintf(f_, "%s\t%llu\t%lld\t%llu\t%llu\t%llu\t%llu\t%llu\t%llu\t%s\t%d\t%d\t%s\t%s\t", r.read_id.c_str(),
-                     static_cast<unsigned long long>(r.read_len), static_cast<long long>(r.rel_dist_to_end),
-                     static_cast<unsigned long long>(r.read_start_bar), static_cast<unsigned long long>(r.read_end_bar),
-                     static_cast<unsigned long long>(r.read_start_flank), static_cast<unsigned long long>(r.read_end_flank),
-                     static_cast<unsigned long long>(r.bar_start), static_cast<unsigned long long>(r.bar_end), kTypeNames[r.match_type],
-                     r.flank_cost, r.barcode_cost, r.label.c_str(), r.strand ? "Rc" : "Fwd");
-        for (size_t i = 0; i < r.cuts.size(); i++)
-            std::fprintf(f_, "%s%s(%llu):%llu", i ? "," : "", r.cuts[i].first.after ? "After" : "Before",
-                         static_cast<unsigned long long>(r.cuts[i].first.group_id), static_cast<unsigned long long>(r.cuts[i].second));
-        std::fputc('\n', f_);
+        buf_ += r.read_id; tab(); u(r.read_len); tab(); i(r.rel_dist_to_end); tab();
+        u(r.read_start_bar); tab(); u(r.read_end_bar); tab(); u(r.read_start_flank); tab(); u(r.read_end_flank); tab(); u(r.bar_start); tab(); u(r.bar_end); tab();
+        buf_ += kTypeNames[r.match_type]; tab(); i(r.flank_cost); tab(); i(r.barcode_cost); tab(); buf_ += r.label; tab(); buf_ += r.strand ? "Rc" : "Fwd"; tab();
+        for (size_t k = 0; k < r.cuts.size(); k++) {
+            if (k) buf_ += ',';
+            buf_ += r.cuts[k].first.after ? "After(" : "Before("; u(r.cuts[k].first.group_id); buf_ += "):"; u(r.cuts[k].second);
+        }
+        buf_ += '\n';
+        if (buf_.size() > (3u << 20)) flush();
     }
-    bool close() { const bool ok = !f_ || std::fclose(f_) == 0; f_ = nullptr; return ok; }
+    bool close() {
+        if (!f_) return ok_;
+        flush();
+        if (std::fclose(f_) != 0) ok_ = false;
+        f_ = nullptr;
+        return ok_;
+    }
 
   private:
+    void tab() { buf_ += '\t'; }
+    void u(uint64_t v) { char t[24]; int k = 0; do { t[k++] = static_cast<char>('0' + v % 10); v /= 10; } while (v); while (k) buf_ += t[--k]; }
+    void i(int64_t v) { if (v < 0) { buf_ += '-'; u(0ull - static_cast<uint64_t>(v)); } else u(static_cast<uint64_t>(v)); }
+    void flush() { if (!buf_.empty() && std::fwrite(buf_.data(), 1, buf_.size(), f_) != buf_.size()) ok_ = false; buf_.clear(); }
     FILE* f_ = nullptr;
-    bool header_ = false;
+    std::string buf_;
+    bool header_ = false, ok_ = true;
 };
 
 // ---------------------------------------------------------------------------------------------------------------
