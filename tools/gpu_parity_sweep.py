@@ -34,17 +34,19 @@ for kit in names:
                                    n_frac=float(rng.choice([0.0, 0.001, 0.02])))
         prm = dict(alpha=float(rng.choice([0.4, 0.5, 1.0, 0.25])), min_score=float(rng.choice([0.2, 0.0, 0.5])),
                    min_score_diff=float(rng.choice([0.1, 0.0, 0.3])))
+        pol = int(rng.choice([0, 0, 0, int(rng.integers(0, 16)) | int(rng.choice([0, 16, 32]))]))     # search-policy bits (oracle and product alike)
         try:
-            an = bb.Annotator(gs, **prm)
+            an = bb.Annotator(gs, policy=pol, **prm)
         except bb.BarbellError as e:
             print(f"[{kit} ext={ext} {kw}] rejected by bb_set_groups: {e}")
             continue
         rows_g = an.annotate(b, o); hits_g = an.flank_hits(); an.close()
-        rows_o = O.demux_batch(G, b, o, cap_per_read=32, **prm)
-        hits_o = O.flank_hits_batch(G, b, o, alpha=prm["alpha"], cap_per_read=64)
+        with O.policy(pol):
+            rows_o = O.demux_batch(G, b, o, cap_per_read=32, **prm)
+            hits_o = O.flank_hits_batch(G, b, o, alpha=prm["alpha"], cap_per_read=64)
         ok = rows_o.tobytes() == rows_g.tobytes() and hits_o.shape == hits_g.shape and (hits_o == hits_g).all()
         done += 1
-        print(f"[{kit} ext={ext} {kw} {prm}] groups={len(G)} k={[g['k_flank'] for g in G]} rows={len(rows_g)} hits={len(hits_g)} {'OK' if ok else 'MISMATCH'}", flush=True)
+        print(f"[{kit} ext={ext} {kw} {prm} policy={pol}] groups={len(G)} k={[g['k_flank'] for g in G]} rows={len(rows_g)} hits={len(hits_g)} {'OK' if ok else 'MISMATCH'}", flush=True)
         if not ok:
             bad.append((kit, ext, kw, prm))
 print(f"{done} cases, {len(bad)} mismatches, {time.time() - t0:.0f} s")
