@@ -360,7 +360,7 @@ def test_prefilter_queue_overflow_falls_back_to_exact_verification():
 
 
 def test_long_barcodes_unpacked_history_and_odd_counts():
-    """Custom panel with 40-base barcodes (padded patterns of 60 rows: the 16-byte column history of k_barcode), 37 barcodes
+    """Custom panel with 40-base barcodes (padded patterns of 60 rows, regions past 48 bases: the 16-byte row records of k_barcode_rows), 37 barcodes
     (not a multiple of 32), one-sided short flanks, mixed with an exact-scan-only group."""
     rnd = np.random.default_rng(33)
     acgt = np.frombuffer(b"ACGT", np.uint8)

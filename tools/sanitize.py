@@ -15,7 +15,7 @@ for kit, kw in (("SQK-NBD114-96", {}), ("SQK-RBK114-96", {}), ("SQK-RBK114-96", 
         print(kit, kw, "filter" if uf else "exact", len(rows), "rows")
         an.close()
 
-# the barcode stage's other variants: 60-row patterns (16-byte column history), a barcode count that is not a multiple of 32,
+# the barcode stage's other variants: 60-row patterns (regions of more than 48 bases: 16-byte row records), a barcode count that is not a multiple of 32,
 # regions with ambiguity codes / garbage bytes (general variant), long insertions (replayed Lodhi recurrence), packed H2D copy
 rnd = np.random.default_rng(33)
 acgt = np.frombuffer(b"ACGT", np.uint8)
