@@ -36,7 +36,7 @@ EXPORTS = ["bb_groups_from_kit", "bb_groups_from_fasta", "bb_groups_add", "bb_gr
            "bb_groups_count", "bb_groups_data", "bb_groups_label", "bb_groups_free", "bb_edit_cut_off", "bb_label_range",
            "bb_lookup_barcode_seq", "bb_create",
            "bb_destroy", "bb_last_error", "bb_set_groups", "bb_annotate", "bb_annotate_device", "bb_fetch_rows",
-           "bb_submit", "bb_submit_packed", "bb_pack_crumbs_append", "bb_collect", "bb_counters", "bb_host_alloc", "bb_host_free", "bb_pack_nibbles", "bb_pack_crumbs", "bb_last_stage_ms", "bb_kernel_launches", "bb_h2d_bytes", "bb_fetch_flank_hits",
+           "bb_submit", "bb_submit_packed", "bb_reserve", "bb_pack_crumbs_append", "bb_pack_crumbs_append_line", "bb_collect", "bb_counters", "bb_host_alloc", "bb_host_free", "bb_pack_nibbles", "bb_pack_crumbs", "bb_last_stage_ms", "bb_kernel_launches", "bb_h2d_bytes", "bb_fetch_flank_hits",
            "bb_kit_info", "bb_kit_filter_patterns", "bb_pattern_parse", "bb_filter", "bb_inspect", "bb_trim",
            "bb_abi_version"]
 
@@ -79,7 +79,9 @@ def lib():
     L.bb_submit.argtypes = [vp, vp, vp, u32, u64]
     L.bb_collect.argtypes = [vp, C.POINTER(u64), C.POINTER(vp), C.POINTER(u64)]
     L.bb_submit_packed.argtypes = [vp, vp, u64, vp, u64, vp, u32, u64]
+    L.bb_reserve.argtypes = [vp, C.c_uint32, u64]
     L.bb_pack_crumbs_append.argtypes = [vp, u64, vp, C.POINTER(u64), vp, u64, C.POINTER(u64)]
+    L.bb_pack_crumbs_append_line.argtypes = [vp, u64, vp, C.POINTER(u64), vp, u64, C.POINTER(u64), C.POINTER(u64), C.POINTER(C.c_int)]
     L.bb_counters.argtypes = [vp, C.POINTER(u64)]
     L.bb_last_stage_ms.argtypes = [vp, C.POINTER(C.c_float)]
     L.bb_kernel_launches.argtypes = [vp]; L.bb_kernel_launches.restype = u64
@@ -252,6 +254,10 @@ class Annotator:
 
     def submit(self, bases_ptr, offsets_ptr, n_reads, tag=0):
         self._check(lib().bb_submit(self._ctx, bases_ptr, offsets_ptr, n_reads, tag))
+
+    def reserve(self, max_reads, max_bases):
+        """Optional: allocate every engine's buffers for batches of this shape and load the kernels before the first submit."""
+        self._check(lib().bb_reserve(self._ctx, max_reads, max_bases))
 
     def submit_packed(self, crumbs_ptr, n_bases, exc_ptr, n_exc, offsets_ptr, n_reads, tag=0):
         self._check(lib().bb_submit_packed(self._ctx, crumbs_ptr, n_bases, exc_ptr, n_exc, offsets_ptr, n_reads, tag))

@@ -531,6 +531,33 @@ struct Engine {
                          static_cast<void*>(this), tr0, tr1 - tr0, tr2 - tr0, now_ms() - tr0, n_reads, stage_ms[0] + stage_ms[1] + stage_ms[2] + stage_ms[3] + stage_ms[4]);
         return BB_OK;
     }
+    // bb_reserve: an all-'A' batch of the given shape through the whole path -- every buffer whose size follows from the shape of a batch
+    // (all of them on the slot path) is allocated and every kernel is loaded before the first real batch arrives
+    int warm(uint32_t n_reads, uint64_t total) {
+        BB_CUDA(cudaSetDevice(device));
+        if (n_reads == 0 || total == 0) return BB_OK;
+        const size_t pk = (static_cast<size_t>((total + 3) / 4) + 63) & ~size_t(63);
+        BB_CUDA(d_bases.ensure(((total + 15) & ~15ull) + 16));
+        BB_CUDA(d_offsets.ensure(static_cast<size_t>(n_reads + 1) * 8));
+        BB_CUDA(d_packed.ensure(pk + static_cast<size_t>(total / 128) * 8 + 64));
+        std::vector<uint64_t> off(static_cast<size_t>(n_reads) + 1);
+        for (uint32_t i = 0; i <= n_reads; i++) off[i] = static_cast<uint64_t>((static_cast<unsigned __int128>(total) * i) / n_reads);
+        BB_CUDA(cudaMemcpyAsync(d_offsets.p, off.data(), off.size() * 8, cudaMemcpyHostToDevice, stream));
+        BB_CUDA(cudaMemsetAsync(d_packed.p, 0, pk + 64, stream));
+        k_unpack_crumbs<<<static_cast<unsigned>((total / 16 + 256) / 256), 256, 0, stream>>>(d_packed.as<uint8_t>(), d_bases.as<uint8_t>(), total);
+        k_patch_exceptions<<<1, 256, 0, stream>>>(reinterpret_cast<const uint64_t*>(d_packed.as<uint8_t>() + pk), 0, d_bases.as<uint8_t>(), total);
+        BB_CUDA(cudaGetLastError());
+        BB_CUDA(cudaStreamSynchronize(stream));                  // (off is read by the copy)
+        uint64_t n_rows = 0;
+        const uint64_t launches0 = launches;
+        int rc = run(d_bases.as<uint8_t>(), d_offsets.as<uint64_t>(), n_reads, total, stream, &n_rows);
+        if (rc != BB_OK) return rc;
+        rc = ensure_host_rows(static_cast<uint64_t>(n_reads) + n_reads / 2 + 1024);
+        if (rc != BB_OK) return rc;
+        BB_CUDA(cudaStreamSynchronize(stream));
+        launches = launches0; last_reads = 0; last_rows = 0; last_kept = 0; last_hits = 0;   // not a batch of the caller's
+        return BB_OK;
+    }
     // host-buffer form: copy in, run, copy rows to pinned memory
     int run_host(const uint8_t* bases, const uint64_t* offsets, uint32_t n_reads, uint64_t* n_rows) {
         BB_CUDA(cudaSetDevice(device));
@@ -641,6 +668,7 @@ struct bb_job {
     const uint8_t* bases; const uint64_t* offsets; uint32_t n_reads; uint64_t tag; int engine;
     int rc = 0; uint64_t n_rows = 0; bool done = false;
     bool packed = false; uint64_t n_bases = 0; const uint64_t* exc = nullptr; uint64_t n_exc = 0;   // bb_submit_packed: `bases` holds crumbs
+    bool warm = false;                                                                               // bb_reserve: no data, n_reads x n_bases only
 };
 
 struct bb_ctx {
@@ -672,7 +700,8 @@ static void worker_main(bb_ctx* c, int idx) {
             job = c->queue[idx].front();
         }
         uint64_t n_rows = 0;
-        const int rc = job->packed ? c->eng[idx].run_host_packed(job->bases, job->n_bases, job->exc, job->n_exc, job->offsets, job->n_reads, &n_rows)
+        const int rc = job->warm ? c->eng[idx].warm(job->n_reads, job->n_bases)
+                     : job->packed ? c->eng[idx].run_host_packed(job->bases, job->n_bases, job->exc, job->n_exc, job->offsets, job->n_reads, &n_rows)
                                    : c->eng[idx].run_host(job->bases, job->offsets, job->n_reads, &n_rows);
         {
             std::lock_guard<std::mutex> lk(c->mu);
@@ -1000,6 +1029,38 @@ int bb_submit_packed(bb_ctx* c, const uint8_t* crumbs, uint64_t n_bases, const u
     return BB_OK;
 }
 
+int bb_reserve(bb_ctx* c, uint32_t max_reads, uint64_t max_bases) {
+    if (!c) return BB_ERR_INVALID;
+    if (!c->gt.n) { ctx_error(c, "bb_reserve: no query groups set"); return BB_ERR_INVALID; }
+    {
+        std::unique_lock<std::mutex> lk(c->mu);
+        if (!c->order.empty()) { ctx_error(c, "bb_reserve: batches in flight"); return BB_ERR_INVALID; }
+        if (!c->workers_started) {
+            for (int i = 0; i < BB_MAX_INFLIGHT; i++) c->workers[i] = std::thread(worker_main, c, i);
+            c->workers_started = true;
+        }
+        for (int i = 0; i < BB_MAX_INFLIGHT; i++) {               // one per engine, all at once
+            const int idx = static_cast<int>(c->submitted % BB_MAX_INFLIGHT);
+            auto* job = new bb_job{nullptr, nullptr, max_reads, 0, idx};
+            job->warm = true; job->n_bases = max_bases;
+            c->queue[idx].push_back(job);
+            c->order.push_back(job);
+            c->submitted++;
+        }
+    }
+    c->cv.notify_all();
+    int rc = BB_OK;
+    std::unique_lock<std::mutex> lk(c->mu);
+    while (!c->order.empty()) {
+        bb_job* job = c->order.front();
+        c->cv.wait(lk, [&] { return job->done; });
+        c->order.pop_front();
+        if (job->rc != BB_OK && rc == BB_OK) { rc = job->rc; c->err = c->eng[job->engine].err; }
+        delete job;
+    }
+    return rc;
+}
+
 int bb_collect(bb_ctx* c, uint64_t* batch_tag, const bb_row** rows, uint64_t* n_rows) {
     if (!c || !rows || !n_rows) return BB_ERR_INVALID;
     std::unique_lock<std::mutex> lk(c->mu);
@@ -1010,7 +1071,7 @@ int bb_collect(bb_ctx* c, uint64_t* batch_tag, const bb_row** rows, uint64_t* n_
     const int idx = job->engine, rc = job->rc;
     if (batch_tag) *batch_tag = job->tag;
     *n_rows = job->n_rows;
-    *rows = c->eng[idx].h_rows;      // valid until the next bb_submit / bb_collect on this ctx
+    *rows = c->eng[idx].h_rows;      // this engine's buffer: rewritten when the engine runs its next batch (BB_MAX_INFLIGHT submits later)
     if (rc == BB_OK) { c->total_reads += job->n_reads; c->kept_reads += c->eng[idx].last_kept; c->last_engine = idx; }
     else c->err = c->eng[idx].err;
     delete job;
@@ -1076,6 +1137,15 @@ int bb_pack_crumbs_append(const uint8_t* src, uint64_t n, uint8_t* dst, uint64_t
     size_t used = static_cast<size_t>(*n_exc);
     const bool ok = bb::crumbs_append(src, static_cast<size_t>(n), dst, pos, exc, static_cast<size_t>(exc_cap), &used, bb::kAlpha.code);
     *n_exc = used;
+    return ok ? BB_OK : BB_ERR_OVERFLOW;
+}
+
+int bb_pack_crumbs_append_line(const uint8_t* src, uint64_t n, uint8_t* dst, uint64_t* pos, uint64_t* exc, uint64_t exc_cap, uint64_t* n_exc,
+                               uint64_t* line_len, int* found) {
+    if ((!src && n) || !dst || !pos || !n_exc || !line_len || !found || (!exc && exc_cap)) return BB_ERR_INVALID;
+    size_t used = static_cast<size_t>(*n_exc), len = 0; bool nl = false;
+    const bool ok = bb::crumbs_append_line(src, static_cast<size_t>(n), dst, pos, exc, static_cast<size_t>(exc_cap), &used, bb::kAlpha.code, &len, &nl);
+    *n_exc = used; *line_len = len; *found = nl ? 1 : 0;
     return ok ? BB_OK : BB_ERR_OVERFLOW;
 }
 

@@ -124,13 +124,18 @@ inline size_t fastq_record_start(const char* m, size_t size, size_t pos) {
 }
 // One record at p (p < end of the mapped file): views into the map; the quality line is stepped over by its length when it has
 // the sequence's length (half of the file is then never read).  Returns 0 = ok (p advanced), 1 = blank line skipped, -1 = error.
+// seq_line(head, head_len, start, e, next) scans the sequence line that starts at `start` (e = its end without the terminator,
+// next = start of the following line; false + what = error): the plain form is a memchr; a reader that packs the bases while
+// it looks for the end of the line (the CLI's) passes its own and touches every base once.
 struct FastqRec { const char* head; size_t head_len; const char* seq; size_t seq_len; const char* qual; };
-inline int fastq_record_at(const char* m, size_t size, size_t& p, FastqRec& r, const char*& what) {
+template <class SeqLine>
+inline int fastq_record_at(const char* m, size_t size, size_t& p, FastqRec& r, const char*& what, SeqLine&& seq_line) {
     size_t e0, n0, e1, n1, e2, n2, e3, n3;
     fastq_line_at(m, size, p, e0, n0);
     if (e0 == p) { p = n0; return 1; }
     if (n0 >= size) { what = "truncated FASTQ record"; return -1; }
-    fastq_line_at(m, size, n0, e1, n1);
+    if (m[p] != '@') { what = "malformed FASTQ record"; return -1; }
+    if (!seq_line(m + p + 1, e0 - p - 1, n0, e1, n1)) return -1;
     if (n1 >= size) { what = "truncated FASTQ record"; return -1; }
     fastq_line_at(m, size, n1, e2, n2);
     const size_t seq_len = e1 - n0, q_end = n2 + seq_len;
@@ -138,11 +143,14 @@ inline int fastq_record_at(const char* m, size_t size, size_t& p, FastqRec& r, c
     else if (q_end < size && m[q_end] == '\n') { e3 = q_end; n3 = q_end + 1; }
     else if (q_end + 1 < size && m[q_end] == '\r' && m[q_end + 1] == '\n') { e3 = q_end; n3 = q_end + 2; }
     else if (n2 < size) fastq_line_at(m, size, n2, e3, n3); else { e3 = n2; n3 = n2; }
-    if (m[p] != '@' || e2 == n1 || m[n1] != '+') { what = "malformed FASTQ record"; return -1; }
+    if (e2 == n1 || m[n1] != '+') { what = "malformed FASTQ record"; return -1; }
     if (e3 - n2 != seq_len) { what = "truncated FASTQ record (quality length differs from sequence length)"; return -1; }
     r.head = m + p + 1; r.head_len = e0 - p - 1; r.seq = m + n0; r.seq_len = seq_len; r.qual = m + n2;
     p = n3;
     return 0;
+}
+inline int fastq_record_at(const char* m, size_t size, size_t& p, FastqRec& r, const char*& what) {
+    return fastq_record_at(m, size, p, r, what, [&](const char*, size_t, size_t start, size_t& e, size_t& next) { fastq_line_at(m, size, start, e, next); return true; });
 }
 // id = header up to the first whitespace, desc = the rest without leading whitespace (split_fastq_header, io.rs:5-16)
 inline void fastq_split_header(const char* head, size_t n, size_t& id_len, size_t& desc_off) {

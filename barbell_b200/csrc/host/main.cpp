@@ -7,6 +7,7 @@
 // `kit` chains annotate -> inspect -> filter -> trim with the reference's fixed file names (src/kits/use_kit.rs:11-109).
 #include <fcntl.h>
 #include <sys/mman.h>
+#include <sys/resource.h>
 #include <sys/stat.h>
 #include <unistd.h>
 #include <zlib.h>
@@ -20,6 +21,7 @@
 #include <algorithm>
 #include <condition_variable>
 #include <deque>
+#include <functional>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -45,7 +47,7 @@ struct Args {
     size_t chunk_kb = 0;
     double min_score = 0.2, min_score_diff = 0.1;
     float alpha = 0.4f;
-    size_t batch_mb = 256;
+    size_t batch_mb = 128;
     unsigned policy = BB_POL_DEFAULT;    // bb_opts.policy (BB_POL_*): the sassy choices the reference's tests do not pin
 };
 
@@ -132,6 +134,7 @@ struct Batch {
     size_t cap_bytes = 0, cap_reads = 0, cap_exc = 0, bytes = 0;   // bytes = bases in the batch
     uint64_t n_exc = 0;
     uint32_t n_reads = 0;
+    std::vector<bb_row> rows;            // the batch's result rows (copied out of the engine's buffer for the writer thread)
     std::vector<char> id_chars;          // read ids back to back
     std::vector<uint32_t> id_off;        // n_reads + 1
     bool pinned = true, packed = true, exc_overflow = false;
@@ -140,30 +143,63 @@ struct Batch {
         auto get = [&](size_t n) { return pin ? bb_host_alloc(n) : std::malloc(n); };
         bases = static_cast<uint8_t*>(get(pack ? cb / 4 + 128 : cb + 64));
         offsets = static_cast<uint64_t*>(get((cr + 1) * sizeof(uint64_t)));
-        if (pack) { cap_exc = cb / 32 + 4096; exc = static_cast<uint64_t*>(get(cap_exc * sizeof(uint64_t))); }
+        if (pack) { cap_exc = cb / 128 + 4096; exc = static_cast<uint64_t*>(get(cap_exc * sizeof(uint64_t))); }   // ~0.8 % of the bases; grows
         return bases && offsets && (!pack || exc);
     }
+    // room for one more read in the offsets (they start sized for reads of >= 256 bases and grow for shorter ones)
+    bool reserve_read() {
+        if (n_reads + 1 <= cap_reads) return true;
+        const size_t cap2 = cap_reads * 4;
+        uint64_t* o2 = static_cast<uint64_t*>(pinned ? bb_host_alloc((cap2 + 1) * sizeof(uint64_t)) : std::malloc((cap2 + 1) * sizeof(uint64_t)));
+        if (!o2) return false;
+        std::memcpy(o2, offsets, (static_cast<size_t>(n_reads) + 1) * sizeof(uint64_t));
+        if (pinned) bb_host_free(offsets); else std::free(offsets);
+        offsets = o2; cap_reads = cap2;
+        return true;
+    }
     void clear() { bytes = 0; n_reads = 0; n_exc = 0; exc_overflow = false; id_chars.clear(); id_off.assign(1, 0); if (offsets) offsets[0] = 0; }
+    bool grow_exc() {                    // N-rich input: the exception list grows (re-appending the read rewrites the same crumbs)
+        const size_t cap2 = cap_exc * 4;
+        uint64_t* e2 = static_cast<uint64_t*>(pinned ? bb_host_alloc(cap2 * sizeof(uint64_t)) : std::malloc(cap2 * sizeof(uint64_t)));
+        if (!e2) { exc_overflow = true; return false; }
+        std::memcpy(e2, exc, n_exc * sizeof(uint64_t));
+        if (pinned) bb_host_free(exc); else std::free(exc);
+        exc = e2; cap_exc = cap2;
+        return true;
+    }
+    void push_read(const char* id, size_t id_len) {
+        offsets[++n_reads] = bytes;
+        id_chars.insert(id_chars.end(), id, id + id_len);
+        id_off.push_back(static_cast<uint32_t>(id_chars.size()));
+    }
     void append(const char* id, size_t id_len, const char* seq, size_t seq_len) {
         if (packed) {
             uint64_t pos = bytes, ne = n_exc;
             while (!exc_overflow && bb_pack_crumbs_append(reinterpret_cast<const uint8_t*>(seq), seq_len, bases, &pos, exc, cap_exc, &ne) != BB_OK) {
-                // N-rich input: the exception list grows (re-appending the read rewrites the same crumbs)
-                const size_t cap2 = cap_exc * 4;
-                uint64_t* e2 = static_cast<uint64_t*>(pinned ? bb_host_alloc(cap2 * sizeof(uint64_t)) : std::malloc(cap2 * sizeof(uint64_t)));
-                if (!e2) { exc_overflow = true; break; }
-                std::memcpy(e2, exc, n_exc * sizeof(uint64_t));
-                if (pinned) bb_host_free(exc); else std::free(exc);
-                exc = e2; cap_exc = cap2; pos = bytes; ne = n_exc;
+                if (!grow_exc()) break;
+                pos = bytes; ne = n_exc;
             }
             n_exc = ne;
         } else {
             std::memcpy(bases + bytes, seq, seq_len);
         }
         bytes += seq_len;
-        offsets[++n_reads] = bytes;
-        id_chars.insert(id_chars.end(), id, id + id_len);
-        id_off.push_back(static_cast<uint32_t>(id_chars.size()));
+        push_read(id, id_len);
+    }
+    // packed form, for a reader that has not looked for the end of the sequence line yet: the line at s (avail readable bytes) is
+    // packed WHILE its end is searched -- one pass over the bases.  line_len = bases, term = bytes of its terminator (0 at the end
+    // of the input); the read is entered with push_read once the rest of the record has been checked.
+    bool append_seq_line(const char* s, size_t avail, size_t& line_len, size_t& term, const char*& what) {
+        const size_t n = std::min(avail, cap_bytes - bytes);
+        uint64_t pos = bytes, ne = n_exc, ll = 0; int found = 0;
+        while (!exc_overflow && bb_pack_crumbs_append_line(reinterpret_cast<const uint8_t*>(s), n, bases, &pos, exc, cap_exc, &ne, &ll, &found) != BB_OK) {
+            if (!grow_exc()) break;
+            pos = bytes; ne = n_exc;
+        }
+        if (!found && n < avail) { what = "read longer than the batch buffer (raise --batch-mb)"; return false; }
+        n_exc = ne; bytes += ll; line_len = ll;
+        term = found ? (s[ll] == '\r' ? 2 : 1) : 0;
+        return true;
     }
     void release() {
         auto put = [&](void* q) { if (pinned) bb_host_free(q); else std::free(q); };
@@ -224,7 +260,7 @@ class SequentialSource : public BatchSource {
             if (!more && !err.empty()) { err_ = err; filled_.push(-2); return; }
             Batch* B = &slots_[cur];
             if (more && v.seq_len > B->cap_bytes) { err_ = "read longer than the batch buffer (raise --batch-mb)"; filled_.push(-2); return; }
-            const bool full = more && (B->bytes + v.seq_len > B->cap_bytes || B->n_reads + 1 > B->cap_reads);
+            const bool full = more && (B->bytes + v.seq_len > B->cap_bytes || !B->reserve_read());
             if ((full || !more) && B->n_reads > 0) {
                 filled_.push(cur);
                 if (!more) break;
@@ -303,6 +339,8 @@ class ParallelSource : public BatchSource {
     void abort() override { { std::lock_guard<std::mutex> lk(mu_); aborted_ = true; } cv_.notify_all(); }
     void join() override { for (auto& w : workers_) if (w.joinable()) w.join(); workers_.clear(); }
     const std::string& error() const override { return err_; }
+    // seconds the parser threads spent parsing / waiting for a free batch slot, summed over the threads (after join())
+    void thread_seconds(double& parse, double& wait) const { parse = parse_secs_; wait = wait_secs_; }
 
   private:
     struct File { std::string path; int fd = -1; size_t size = 0; const char* map = nullptr; size_t first_chunk = 0; };
@@ -313,11 +351,25 @@ class ParallelSource : public BatchSource {
         size_t p = begin;
         while (p < end) {
             bb::FastqRec r; const char* what = nullptr;
+            size_t idl, doff;
+            if (B.packed) {
+                const int st = bb::fastq_record_at(m, f.size, p, r, what, [&](const char*, size_t, size_t start, size_t& e, size_t& next) {
+                    if (!B.reserve_read()) { what = "out of memory for the read offsets"; return false; }
+                    size_t ll = 0, term = 0;
+                    if (!B.append_seq_line(m + start, f.size - start, ll, term, what)) return false;
+                    e = start + ll; next = e + term;
+                    return true;
+                });
+                if (st == 1) continue;                             // blank line between records
+                if (st < 0) { err = std::string(what) + " in " + f.path; return false; }
+                bb::fastq_split_header(r.head, r.head_len, idl, doff);
+                B.push_read(r.head, idl);
+                continue;
+            }
             const int st = bb::fastq_record_at(m, f.size, p, r, what);
             if (st == 1) continue;                                 // blank line between records
             if (st < 0) { err = std::string(what) + " in " + f.path; return false; }
-            if (B.bytes + r.seq_len > B.cap_bytes || B.n_reads + 1 > B.cap_reads) { err = "read longer than the batch buffer (raise --batch-mb)"; return false; }
-            size_t idl, doff;
+            if (B.bytes + r.seq_len > B.cap_bytes || !B.reserve_read()) { err = "read longer than the batch buffer (raise --batch-mb)"; return false; }
             bb::fastq_split_header(r.head, r.head_len, idl, doff);
             B.append(r.head, idl, r.seq, r.seq_len);
         }
@@ -328,21 +380,26 @@ class ParallelSource : public BatchSource {
             const size_t i = claim_.fetch_add(1);
             if (i >= n_chunks_) return;
             const size_t slot = i % slots_.size(), need = i / slots_.size();
+            const auto tw = std::chrono::steady_clock::now();
             {
                 std::unique_lock<std::mutex> lk(mu_);
                 cv_.wait(lk, [&] { return aborted_ || round_[slot] == need; });
                 if (aborted_) return;
             }
+            const auto tp = std::chrono::steady_clock::now();
             const File* f = &files_[0];
             for (const auto& ff : files_) if (i >= ff.first_chunk) f = &ff;
             Batch& B = slots_[slot];
             B.clear();
             std::string err;
             const bool ok = parse_chunk(*f, i - f->first_chunk, B, err);
+            const auto te = std::chrono::steady_clock::now();
             {
                 std::lock_guard<std::mutex> lk(mu_);
                 if (!ok && err_.empty()) err_ = err;
                 done_[i] = ok ? 1 : 2;
+                wait_secs_ += std::chrono::duration<double>(tp - tw).count();
+                parse_secs_ += std::chrono::duration<double>(te - tp).count();
             }
             cv_.notify_all();
             if (!ok) return;
@@ -358,6 +415,7 @@ class ParallelSource : public BatchSource {
     std::condition_variable cv_;
     std::vector<std::thread> workers_;
     std::string err_;
+    double parse_secs_ = 0, wait_secs_ = 0;
     bool failed_ = false, aborted_ = false;
 };
 
@@ -441,7 +499,7 @@ class MultiFileSource : public BatchSource {
                 const size_t len = P.ends[r] - b0;
                 Batch* B = &slots_[cur];
                 if (len > B->cap_bytes) { err_ = "read longer than the batch buffer (raise --batch-mb)"; filled_.push(-2); return; }
-                if (B->bytes + len > B->cap_bytes || B->n_reads + 1 > B->cap_reads) {
+                if (B->bytes + len > B->cap_bytes || !B->reserve_read()) {
                     filled_.push(cur);
                     cur = free_.pop();
                     if (cur < 0) return;
@@ -477,22 +535,31 @@ struct Ingest {
     std::vector<Batch> slots;
     std::unique_ptr<BatchSource> source;
     bool parallel = false, multifile = false;
+    size_t input_bytes = 0, chunk_bytes = 0;                // parallel source only
     std::chrono::steady_clock::time_point t_start;          // when the parsers were started (after the slots were allocated)
-    bool open(const Args& a, int in_flight, bool pinned, std::string& err) {
-        const size_t cap_bytes = a.batch_mb << 20, cap_reads = 1u << 22;
+    // before_start (optional) runs once the plan is known (parallel, input_bytes, chunk_bytes) and the slots are allocated, right
+    // before the parser threads start
+    bool open(const Args& a, int in_flight, bool pinned, std::string& err, const std::function<bool(std::string&)>& before_start = nullptr) {
+        const size_t cap_bytes = a.batch_mb << 20;
         const int parse_threads = std::min(32, std::max(1, a.threads));
         parallel = parse_threads > 1 && !a.single_reader && ParallelSource::usable(a.input);
         size_t chunk = a.chunk_kb ? a.chunk_kb << 10 : cap_bytes, n_chunks = 0;
         if (parallel) {
-            for (const auto& p : a.input) { struct stat st; if (stat(p.c_str(), &st) == 0) n_chunks += (static_cast<size_t>(st.st_size) + chunk - 1) / chunk; }
+            for (const auto& p : a.input) { struct stat st; if (stat(p.c_str(), &st) == 0) { n_chunks += (static_cast<size_t>(st.st_size) + chunk - 1) / chunk; input_bytes += static_cast<size_t>(st.st_size); } }
+            chunk_bytes = chunk;
         }
         // sequential: in flight + one filled + the one being filled; parallel: in flight + one per parser (fewer for small inputs)
-        const size_t n_slots = parallel ? std::max<size_t>(2, std::min<size_t>(in_flight + parse_threads, n_chunks + 1)) : static_cast<size_t>(in_flight + 2);
+        // slots beyond one per parser: the batches on the GPU(s), the ones queued for the writer thread, and slack against the
+        // in-order hand-over (a parser that finishes early must not wait for the slot of a slower one)
+        const size_t slack = std::getenv("BB_SLOT_SLACK") ? static_cast<size_t>(std::atoi(std::getenv("BB_SLOT_SLACK"))) : 4;
+        const size_t n_slots = parallel ? std::max<size_t>(2, std::min<size_t>(in_flight + parse_threads + slack, n_chunks + 1)) : static_cast<size_t>(in_flight + 2);
         // a chunk holds at most chunk/2 bases plus the tail of the record that straddles its end (16 MB covers the longest reads)
         const size_t slot_bytes = parallel ? std::min(cap_bytes, chunk / 2) + (16u << 20) : cap_bytes;
         slots.resize(n_slots);
+        const size_t cap_reads = std::max<size_t>(4096, slot_bytes / 256);         // Batch::reserve_read grows it for shorter reads
         for (auto& b : slots) if (!b.alloc(slot_bytes, cap_reads, pinned, !a.no_pack)) { err = pinned ? "pinned host allocation failed" : "host allocation failed"; return false; }
         multifile = !parallel && parse_threads > 1 && !a.single_reader && MultiFileSource::usable(a.input);
+        if (before_start && !before_start(err)) return false;
         t_start = std::chrono::steady_clock::now();
         if (parallel) source.reset(new ParallelSource(a.input, slots, chunk, parse_threads));
         else if (multifile) source.reset(new MultiFileSource(a.input, slots, parse_threads));
@@ -527,6 +594,7 @@ struct RowWriter {
     void flush() { if (n && std::fwrite(buf.data(), 1, n, f) != n) failed = true; n = 0; }
     void room(size_t need) { if (n + need > buf.size()) flush(); if (need > buf.size()) buf.resize(need * 2); }
     void raw(const char* p, size_t len) { room(len); std::memcpy(buf.data() + n, p, len); n += len; }
+    void raw_nocheck(const char* p, size_t len) { std::memcpy(buf.data() + n, p, len); n += len; }   // after room()
     void str(const char* p) { raw(p, std::strlen(p)); }
     void ch(char c) { buf[n++] = c; }                      // after room()
     void num(long long v) {                                // after room(24)
@@ -587,17 +655,35 @@ int run_annotate(const Args& a, const std::string& out_path, std::thread* teardo
     RowWriter W(out);
 
     Ingest ingest;
+    double reserve_secs = 0;
     {
+        // plain files of some size: the engines allocate their buffers and load the kernels for batches of one chunk now -- all engines
+        // of all GPUs at once, and before the parser threads start (an allocation changes the address space, which waits for every
+        // page fault of 16 threads streaming through a mapped file) -- instead of one after the other on the first batches
+        auto reserve = [&](std::string& e) {
+            if (!ingest.parallel || ingest.input_bytes < (64u << 20)) return true;
+            const auto tr = std::chrono::steady_clock::now();
+            const uint64_t max_bases = std::min<uint64_t>(ingest.chunk_bytes / 2 + ingest.chunk_bytes / 32, ingest.input_bytes / 2 + (1u << 20));
+            std::vector<std::thread> th;
+            std::vector<int> rcs(n_gpus, BB_OK);
+            for (int d = 0; d < n_gpus; d++) th.emplace_back([&, d] { rcs[d] = bb_reserve(ctx[d], static_cast<uint32_t>(max_bases / 1024 + 1), max_bases); });
+            for (auto& t : th) t.join();
+            for (int d = 0; d < n_gpus; d++) if (rcs[d] != BB_OK) { e = bb_last_error(ctx[d]); return false; }
+            reserve_secs = since(tr);
+            return true;
+        };
         std::string ierr;
-        if (!ingest.open(a, 2 * n_gpus, true, ierr)) {
+        if (!ingest.open(a, BB_MAX_INFLIGHT * n_gpus, true, ierr, reserve)) {
             std::printf("Error during processing: %s\n", ierr.c_str());
             ingest.close(); std::fclose(out); for (auto* c : ctx) bb_destroy(c); bb_groups_free(gs);
             return BB_ERR_CUDA;
         }
     }
     std::vector<Batch>& slots = ingest.slots;
+    const size_t n_slots_used = slots.size();
     BatchSource* source = ingest.source.get();
     const auto t0 = ingest.t_start;                        // the stream phase starts when the parsers start
+    struct rusage ru0; getrusage(RUSAGE_SELF, &ru0);
     const double setup_secs = std::chrono::duration<double>(t0 - t_setup).count();
 
     struct Flight { int slot, dev; };
@@ -607,46 +693,75 @@ int run_annotate(const Args& a, const std::string& out_path, std::thread* teardo
     // labels are looked up once per (group, barcode), not per row
     std::vector<std::vector<const char*>> labels(n_groups);
     for (int g = 0; g < n_groups; g++) { labels[g].resize(groups[g].n_barcodes); for (int b = 0; b < groups[g].n_barcodes; b++) labels[g][b] = bb_groups_label(gs, g, b); }
-    auto collect_one = [&](bool write) -> int {
-        const Flight f = flight.front(); flight.pop_front();
-        uint64_t tag = 0, n_rows = 0; const bb_row* rows = nullptr;
-        int r = bb_collect(ctx[f.dev], &tag, &rows, &n_rows);
-        if (r != BB_OK) { if (write) std::printf("Error during processing: %s\n", bb_last_error(ctx[f.dev])); source->release(f.slot); return r; }
-        if (!write) { source->release(f.slot); return BB_OK; }
-        const Batch& B = slots[f.slot];
+    double t_collect = 0, t_format = 0, t_submit = 0, t_source = 0;    // where the main / writer thread's time goes (--verbose)
+    std::vector<std::vector<size_t>> label_len(n_groups);
+    for (int g = 0; g < n_groups; g++) for (const char* l : labels[g]) label_len[g].push_back(std::strlen(l));
+    // Rows are written by their own thread: the main thread only moves batches between the parsers and the GPU(s), and formatting
+    // overlaps the waits for the GPU.  (The rows are copied out of the engine's buffer into the batch slot, ~1 MB per batch: the
+    // engine is free for its next batch whatever the writer's backlog.)
+    struct WriteJob { int slot; const bb_row* rows; uint64_t n_rows; };
+    Channel<WriteJob> write_q;
+    // batches in flight per GPU: 2 keep it busy (measured: 4 are no faster, the parsers set the pace); BB_CLI_INFLIGHT = tuning knob
+    const int per_gpu = std::getenv("BB_CLI_INFLIGHT") ? std::max(1, std::min(BB_MAX_INFLIGHT, std::atoi(std::getenv("BB_CLI_INFLIGHT")))) : 2;
+    auto write_rows = [&](const WriteJob& j) {
+        const auto tf0 = std::chrono::steady_clock::now();
+        const Batch& B = slots[j.slot];
         uint32_t last = UINT32_MAX;
-        for (uint64_t i = 0; i < n_rows; i++) {
-            const bb_row& w = rows[i];
-            if (!header_written) {
-                W.str("read_id\tread_len\trel_dist_to_end\tread_start_bar\tread_end_bar\tread_start_flank\tread_end_flank\t"
-                      "bar_start\tbar_end\tmatch_type\tflank_cost\tbarcode_cost\tlabel\tstrand\tcuts\n");
-                header_written = true;
-            }
+        if (!header_written && j.n_rows) {
+            W.str("read_id\tread_len\trel_dist_to_end\tread_start_bar\tread_end_bar\tread_start_flank\tread_end_flank\t"
+                  "bar_start\tbar_end\tmatch_type\tflank_cost\tbarcode_cost\tlabel\tstrand\tcuts\n");
+            header_written = true;
+        }
+        for (uint64_t i = 0; i < j.n_rows; i++) {
+            const bb_row& w = j.rows[i];
             if (w.read_idx != last) { kept++; last = w.read_idx; }
             const size_t idl = B.id_off[w.read_idx + 1] - B.id_off[w.read_idx];
             const char* label = w.label_idx < 0 ? "flank" : labels[w.group_idx][w.label_idx];
-            const size_t ll = std::strlen(label);
+            const size_t ll = w.label_idx < 0 ? 5 : label_len[w.group_idx][w.label_idx];
             W.room(idl + ll + 320);
-            W.raw(B.id_chars.data() + B.id_off[w.read_idx], idl);
+            W.raw_nocheck(B.id_chars.data() + B.id_off[w.read_idx], idl);
             W.ch('\t'); W.num(w.read_len);
             W.ch('\t'); W.num(w.rel_dist_to_end);
             W.ch('\t'); W.num(w.read_start_bar); W.ch('\t'); W.num(w.read_end_bar);
             W.ch('\t'); W.num(w.read_start_flank); W.ch('\t'); W.num(w.read_end_flank);
             W.ch('\t'); W.num(w.bar_start); W.ch('\t'); W.num(w.bar_end);
-            W.ch('\t'); W.str(kTypeNames[w.match_type & 3]);
+            W.ch('\t'); W.raw_nocheck(kTypeNames[w.match_type & 3], (w.match_type & 2) ? 6 : 4);
             W.ch('\t'); W.num(w.flank_cost); W.ch('\t'); W.num(w.barcode_cost);
-            W.ch('\t'); W.raw(label, ll);
-            W.ch('\t'); W.str(w.strand ? "Rc" : "Fwd");
-            W.ch('\t'); W.ch('\n');
+            W.ch('\t'); W.raw_nocheck(label, ll);
+            if (w.strand) W.raw_nocheck("\tRc\t\n", 5); else W.raw_nocheck("\tFwd\t\n", 6);
         }
-        total_rows += n_rows;
-        source->release(f.slot);
+        total_rows += j.n_rows;
+        t_format += since(tf0);
+    };
+    std::thread writer([&] {
+        for (;;) {
+            const WriteJob j = write_q.pop();
+            if (j.slot < 0) return;
+            write_rows(j);
+            source->release(j.slot);
+        }
+    });
+    bool writer_joined = false;
+    auto join_writer = [&] { if (!writer_joined) { write_q.push({-1, nullptr, 0}); writer.join(); writer_joined = true; } };
+    auto collect_one = [&](bool write) -> int {
+        const Flight f = flight.front(); flight.pop_front();
+        uint64_t tag = 0, n_rows = 0; const bb_row* rows = nullptr;
+        const auto tc0 = std::chrono::steady_clock::now();
+        int r = bb_collect(ctx[f.dev], &tag, &rows, &n_rows);
+        t_collect += since(tc0);
+        if (r != BB_OK) { if (write) std::printf("Error during processing: %s\n", bb_last_error(ctx[f.dev])); source->release(f.slot); return r; }
+        if (!write) { source->release(f.slot); return BB_OK; }
+        Batch& B = slots[f.slot];
+        B.rows.assign(rows, rows + n_rows);
+        write_q.push({f.slot, B.rows.data(), n_rows});
         return BB_OK;
     };
 
     rc = BB_OK;
     for (;;) {
+        const auto ts0 = std::chrono::steady_clock::now();
         const int cur = source->next_filled();
+        t_source += since(ts0);
         if (cur == -1) break;
         if (cur == -2) { std::printf("Error during processing: %s\n", source->error().c_str()); rc = BB_ERR_IO; break; }
         Batch& B = slots[cur];
@@ -656,10 +771,12 @@ int run_annotate(const Args& a, const std::string& out_path, std::thread* teardo
         }
         const int dev = static_cast<int>(submitted % n_gpus);
         size_t on_dev = 0; for (const auto& f : flight) on_dev += f.dev == dev;
-        while (on_dev >= 2 && rc == BB_OK) { const int d0 = flight.front().dev; rc = collect_one(true); if (d0 == dev) on_dev--; }   // 2 in flight per GPU
+        while (on_dev >= static_cast<size_t>(per_gpu) && rc == BB_OK) { const int d0 = flight.front().dev; rc = collect_one(true); if (d0 == dev) on_dev--; }
         if (rc != BB_OK) { source->release(cur); break; }
+        const auto tb0 = std::chrono::steady_clock::now();
         rc = B.packed ? bb_submit_packed(ctx[dev], B.bases, B.bytes, B.exc, B.n_exc, B.offsets, B.n_reads, submitted)
                       : bb_submit(ctx[dev], B.bases, B.offsets, B.n_reads, submitted);
+        t_submit += since(tb0);
         if (rc != BB_OK) { std::printf("Error during processing: %s\n", bb_last_error(ctx[dev])); source->release(cur); break; }
         flight.push_back({cur, dev});
         submitted++;
@@ -670,11 +787,15 @@ int run_annotate(const Args& a, const std::string& out_path, std::thread* teardo
         source->abort();                             // unblock the producers ...
         while (!flight.empty()) collect_one(false);  // ... and wait for every batch still in flight: its buffers are being read by the workers / the DMA engine
     }
+    join_writer();
     source->join();
+    double parse_secs = 0, wait_secs = 0;
+    if (ingest.parallel) static_cast<ParallelSource*>(source)->thread_seconds(parse_secs, wait_secs);
     W.flush();
     const bool close_failed = std::fclose(out) != 0;
     if ((W.failed || close_failed) && rc == BB_OK) { std::printf("Error during processing: write to %s failed\n", out_path.c_str()); rc = BB_ERR_IO; }
     const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    struct rusage ru1; getrusage(RUSAGE_SELF, &ru1);
     if (rc == BB_OK && a.verbose)
         write_progress_log(parent_dir(out_path), "annotate", {{"Total:", total_reads}, {"Kept:", kept}, {"Dropped:", total_reads - kept}});
     if (rc == BB_OK) {
@@ -693,8 +814,15 @@ int run_annotate(const Args& a, const std::string& out_path, std::thread* teardo
         bb_groups_free(gs);
     }
     // (pinning the slots on a second thread beside the context set-up was tried: the driver serialises the two, no gain)
-    if (a.verbose) std::fprintf(stderr, "[timing] setup %.2f s (CUDA context + engine %.2f s, pinned batch slots %.2f s), stream %.2f s, teardown %.2f s%s\n",
-                                setup_secs, ctx_secs, setup_secs - ctx_secs, secs, since(t_down), teardown ? " (continues in the background)" : "");
+    if (a.verbose) {
+        auto tv = [](const timeval& x) { return static_cast<double>(x.tv_sec) + 1e-6 * static_cast<double>(x.tv_usec); };
+        std::fprintf(stderr, "[timing] setup %.2f s (CUDA context + engine %.2f s, %zu pinned batch slots + engine buffers %.2f s of which reserve %.3f s), stream %.2f s (all threads: user %.2f s, "
+                             "kernel %.2f s, %ld minor faults; parser threads: %.2f s parsing, %.2f s waiting for a slot; main thread: %.3f s waiting for a parsed "
+                             "batch, %.3f s submitting, %.3f s waiting for the GPU; writer thread: %.3f s writing rows), teardown %.2f s%s\n",
+                     setup_secs, ctx_secs, n_slots_used, setup_secs - ctx_secs, reserve_secs, secs, tv(ru1.ru_utime) - tv(ru0.ru_utime), tv(ru1.ru_stime) - tv(ru0.ru_stime),
+                     ru1.ru_minflt - ru0.ru_minflt, parse_secs, wait_secs, t_source, t_submit, t_collect, t_format, since(t_down),
+                     teardown ? " (continues in the background)" : "");
+    }
     return rc;
 }
 
@@ -731,6 +859,12 @@ int run_fastq_stats(const Args& a) {
         ingest.source->release(cur);
     }
     const char* kind = ingest.parallel ? "parallel" : ingest.multifile ? "multifile" : "sequential";
+    if (a.count_only && ingest.parallel) {
+        ingest.source->join();
+        const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - ingest.t_start).count();
+        double ps = 0, ws = 0; static_cast<ParallelSource*>(ingest.source.get())->thread_seconds(ps, ws);
+        std::fprintf(stderr, "[timing] %.3f s, %.0f reads/s; parser threads: %.2f s parsing, %.2f s waiting for a slot; %zu slots\n", secs, static_cast<double>(n) / secs, ps, ws, ingest.slots.size());
+    }
     ingest.close();
     if (rc == 0) std::printf("records=%llu bases=%llu fnv=%016llx batches=%llu reader=%s form=%s\n", static_cast<unsigned long long>(n), static_cast<unsigned long long>(bases),
                              static_cast<unsigned long long>(h), static_cast<unsigned long long>(batches), kind, a.no_pack ? "bytes" : "packed");

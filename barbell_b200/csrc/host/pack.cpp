@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
@@ -99,39 +100,106 @@ void crumbs_scalar(const uint8_t* src, size_t pos0, size_t n, uint8_t* dst, cons
     }
 }
 
-// 128 input bytes -> 32 output bytes per iteration.  A C G T (any case; U as T) are told apart arithmetically: with x = c >> 1 and
-// y = c >> 2 the two low bits of x ^ y are 0 1 2 3 for A C G T; a byte is one of those letters iff (c | 0x20) equals the letter its
-// low nibble stands for (1 a, 3 c, 4 t, 5 u, 7 g).  Everything else gets crumb 0 and an exception entry with its 4-bit base set.
-__attribute__((target("avx2"))) void crumbs_avx2(const uint8_t* src, size_t pos0, size_t n, uint8_t* dst, const uint8_t* code, ExcWriter& w) {
+// 128 input bytes -> 32 output bytes per step.  A C G T U (any case) have distinct low nibbles (1 3 7 4 5), so one pshufb gives the
+// crumb and a second one the lower-case letter that nibble stands for; a byte is a single base iff (c | 0x20) equals that letter
+// (bytes >= 0x80 look up 0 and fail).  Everything else gets crumb 0 and an exception entry with its 4-bit base set.  Four bytes of
+// crumbs are folded into one with two multiply-adds (1, 4 per byte pair; 1, 16 per word pair), 4 x 8 dwords are narrowed to 32 bytes.
+// Only blocks with a byte that is not a single base leave the straight path (one movemask per 128 bytes).
+// LINE: the input is a text line of unknown length <= n: stop in front of the first '\n' (*found), which -- not being a base -- can
+// only sit in such a block.  The block that holds the end of the input is packed from a copy (or in place when 128 bytes are
+// readable) with the crumbs past the end forced to 0: the next read ORs its first bases into the partly used last byte.
+struct CrumbConsts { __m256i L, CR, lower, mul4, mul16, perm, iota; };
+__attribute__((target("avx2"))) static inline CrumbConsts crumb_consts() {
     alignas(32) static const uint8_t kLetter[32] = {0, 'a', 0, 'c', 't', 'u', 0, 'g', 0, 0, 0, 0, 0, 0, 0, 0,
                                                     0, 'a', 0, 'c', 't', 'u', 0, 'g', 0, 0, 0, 0, 0, 0, 0, 0};
-    const __m256i L = _mm256_load_si256(reinterpret_cast<const __m256i*>(kLetter));
-    const __m256i three = _mm256_set1_epi8(3), low4 = _mm256_set1_epi8(0x0f), lower = _mm256_set1_epi8(0x20);
-    const __m256i mul4 = _mm256_set1_epi16(0x0401), mul16 = _mm256_set1_epi16(0x1001);
-    const bool aligned = (reinterpret_cast<uintptr_t>(dst) & 31) == 0;
+    alignas(32) static const uint8_t kCrumb[32] = {0, 0, 0, 1, 3, 3, 0, 2, 0, 0, 0, 0, 0, 0, 0, 0,
+                                                   0, 0, 0, 1, 3, 3, 0, 2, 0, 0, 0, 0, 0, 0, 0, 0};
+    alignas(32) static const uint8_t kIota[32] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 31};
+    CrumbConsts k;
+    k.L = _mm256_load_si256(reinterpret_cast<const __m256i*>(kLetter));
+    k.CR = _mm256_load_si256(reinterpret_cast<const __m256i*>(kCrumb));
+    k.iota = _mm256_load_si256(reinterpret_cast<const __m256i*>(kIota));
+    k.lower = _mm256_set1_epi8(0x20);
+    k.mul4 = _mm256_set1_epi16(0x0401);
+    k.mul16 = _mm256_set1_epi32(0x00100001);
+    k.perm = _mm256_setr_epi32(0, 4, 1, 5, 2, 6, 3, 7);
+    return k;
+}
+// the 32 output bytes of four vectors of masked crumbs
+__attribute__((target("avx2"))) static inline __m256i crumbs_fold(const __m256i c[4], const CrumbConsts& k) {
+    __m256i d[4];
+    for (int q = 0; q < 4; q++) d[q] = _mm256_madd_epi16(_mm256_maddubs_epi16(c[q], k.mul4), k.mul16);      // 8 dwords, each one output byte
+    const __m256i pk = _mm256_packus_epi16(_mm256_packus_epi32(d[0], d[1]), _mm256_packus_epi32(d[2], d[3]));
+    return _mm256_permutevar8x32_epi32(pk, k.perm);                                                           // undo the per-lane interleave
+}
+// one block of `len` <= 128 valid bytes at s (128 readable): exceptions + 32 output bytes (crumbs at >= len are 0)
+__attribute__((target("avx2"))) static inline void crumbs_block_masked(const uint8_t* s, size_t len, size_t pos, uint8_t* out, const uint8_t* code,
+                                                                       ExcWriter& w, const CrumbConsts& k) {
+    __m256i c[4];
+    for (int q = 0; q < 4; q++) {
+        const __m256i v = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(s + 32 * q));
+        const int left = static_cast<int>(len) - 32 * q;
+        const __m256i in = _mm256_cmpgt_epi8(_mm256_set1_epi8(static_cast<char>(std::max(0, std::min(127, left)))), k.iota);
+        const __m256i ok = _mm256_cmpeq_epi8(_mm256_or_si256(v, k.lower), _mm256_shuffle_epi8(k.L, v));
+        uint32_t m = ~static_cast<uint32_t>(_mm256_movemask_epi8(ok)) & static_cast<uint32_t>(_mm256_movemask_epi8(in));
+        while (m) {
+            const int t = __builtin_ctz(m); m &= m - 1;
+            w.push(static_cast<uint64_t>(pos + 32 * q + t) << 4 | code[s[32 * q + t]]);
+        }
+        c[q] = _mm256_and_si256(_mm256_shuffle_epi8(k.CR, v), _mm256_and_si256(ok, in));
+    }
+    _mm256_storeu_si256(reinterpret_cast<__m256i*>(out), crumbs_fold(c, k));
+}
+template <bool LINE>
+__attribute__((target("avx2"))) size_t crumbs_avx2_t(const uint8_t* src, size_t pos0, size_t n, uint8_t* dst, const uint8_t* code, ExcWriter& w, bool* found) {
+    const CrumbConsts k = crumb_consts();
+    const bool aligned = !LINE && (reinterpret_cast<uintptr_t>(dst) & 31) == 0;
+    static const size_t kAhead = [] { const char* e = std::getenv("BB_PACK_AHEAD"); return e ? static_cast<size_t>(std::atoi(e)) : size_t(1024); }();
     size_t i = 0;
     for (; i + 128 <= n; i += 128) {
-        __m256i c[4];
+        __m256i c[4], all = _mm256_set1_epi8(-1);
+        _mm_prefetch(reinterpret_cast<const char*>(src + i + kAhead), _MM_HINT_T0);
+        _mm_prefetch(reinterpret_cast<const char*>(src + i + kAhead + 64), _MM_HINT_T0);
         for (int q = 0; q < 4; q++) {
             const __m256i v = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + i + 32 * q));
-            const __m256i ok = _mm256_cmpeq_epi8(_mm256_or_si256(v, lower), _mm256_shuffle_epi8(L, _mm256_and_si256(v, low4)));
-            uint32_t m = ~static_cast<uint32_t>(_mm256_movemask_epi8(ok));
-            while (m) {                                                     // rare: bytes that are not a single base
-                const int t = __builtin_ctz(m); m &= m - 1;
-                const size_t at = i + 32 * q + t;
-                w.push(static_cast<uint64_t>(pos0 + at) << 4 | code[src[at]]);
-            }
-            const __m256i x = _mm256_xor_si256(_mm256_srli_epi16(v, 1), _mm256_srli_epi16(v, 2));   // (bits shifted in from the neighbour byte land above bit 1)
-            c[q] = _mm256_and_si256(_mm256_and_si256(x, three), ok);
+            const __m256i ok = _mm256_cmpeq_epi8(_mm256_or_si256(v, k.lower), _mm256_shuffle_epi8(k.L, v));
+            c[q] = _mm256_and_si256(_mm256_shuffle_epi8(k.CR, v), ok);
+            all = _mm256_and_si256(all, ok);
         }
-        const __m256i n01 = _mm256_permute4x64_epi64(_mm256_packus_epi16(_mm256_maddubs_epi16(c[0], mul4), _mm256_maddubs_epi16(c[1], mul4)), 0xD8);
-        const __m256i n23 = _mm256_permute4x64_epi64(_mm256_packus_epi16(_mm256_maddubs_epi16(c[2], mul4), _mm256_maddubs_epi16(c[3], mul4)), 0xD8);
-        const __m256i pk = _mm256_permute4x64_epi64(_mm256_packus_epi16(_mm256_maddubs_epi16(n01, mul16), _mm256_maddubs_epi16(n23, mul16)), 0xD8);
-        if (aligned) _mm256_stream_si256(reinterpret_cast<__m256i*>(dst + (i >> 2)), pk);
+        if (__builtin_expect(_mm256_movemask_epi8(all) != -1, 0)) {           // rare: a byte that is not a single base (or the end of the line)
+            size_t len = 128;
+            if (LINE) {
+                const void* nl = std::memchr(src + i, '\n', 128);
+                if (nl) len = static_cast<size_t>(static_cast<const uint8_t*>(nl) - (src + i));
+            }
+            crumbs_block_masked(src + i, len, pos0 + i, dst + (i >> 2), code, w, k);
+            if (len < 128) { *found = true; return i + len; }
+            continue;
+        }
+        const __m256i pk = crumbs_fold(c, k);
+        if (aligned) _mm256_stream_si256(reinterpret_cast<__m256i*>(dst + (i >> 2)), pk);   // no read-for-ownership of the output
         else _mm256_storeu_si256(reinterpret_cast<__m256i*>(dst + (i >> 2)), pk);
     }
     if (aligned) _mm_sfence();
-    crumbs_scalar(src + i, pos0 + i, n - i, dst + (i >> 2), code, w);
+    if (i < n) {                                                              // fewer than 128 readable bytes: pack a padded copy
+        alignas(32) uint8_t tmp[128];
+        size_t len = n - i;
+        std::memcpy(tmp, src + i, len);
+        std::memset(tmp + len, 0, 128 - len);
+        if (LINE) {
+            const void* nl = std::memchr(tmp, '\n', len);
+            if (nl) { len = static_cast<size_t>(static_cast<const uint8_t*>(nl) - tmp); *found = true; }
+        }
+        alignas(32) uint8_t out[32];
+        crumbs_block_masked(tmp, len, pos0 + i, out, code, w, k);
+        std::memcpy(dst + (i >> 2), out, (len + 3) >> 2);
+        i += len;
+    }
+    return i;
+}
+void crumbs_avx2(const uint8_t* src, size_t pos0, size_t n, uint8_t* dst, const uint8_t* code, ExcWriter& w) {
+    bool f = false;
+    crumbs_avx2_t<false>(src, pos0, n, dst, code, w, &f);
 }
 
 class Pool {
@@ -203,25 +271,50 @@ Pool& pool(int threads) {
 }
 }  // namespace
 
-bool crumbs_append(const uint8_t* src, size_t n, uint8_t* dst, uint64_t* pos, uint64_t* exc, size_t exc_cap, size_t* n_exc, const uint8_t* code) {
+// shared body of crumbs_append / crumbs_append_line
+template <bool LINE>
+static bool append_impl(const uint8_t* src, size_t n, uint8_t* dst, uint64_t* pos, uint64_t* exc, size_t exc_cap, size_t* n_exc, const uint8_t* code,
+                        size_t* line_len, bool* found) {
     static const bool avx2 = __builtin_cpu_supports("avx2");
     std::atomic<bool> over{false};
     ExcWriter w{exc, exc_cap, nullptr, &over};
     w.cur = *n_exc; w.end = exc_cap;
     size_t p = static_cast<size_t>(*pos), i = 0;
+    bool nl = false;
     // head: fill up the byte the previous read left partly used (its missing crumbs are still zero)
     for (; i < n && (p & 3); i++, p++) {
+        if (LINE && src[i] == '\n') { nl = true; break; }
         const uint8_t v = code[src[i]], cr = kCrumbOfSet[v];
         if (cr & 0x80) w.push(static_cast<uint64_t>(p) << 4 | v);
         else dst[p >> 2] = static_cast<uint8_t>(dst[p >> 2] | cr << (2 * (p & 3)));
     }
     // body: from here on the stream is byte aligned; the tail of this read leaves the last byte partly used (upper crumbs zero)
-    if (i < n) {
-        if (avx2) crumbs_avx2(src + i, p, n - i, dst + (p >> 2), code, w); else crumbs_scalar(src + i, p, n - i, dst + (p >> 2), code, w);
-        p += n - i;
+    if (i < n && !nl) {
+        size_t took;
+        if (avx2) {
+            took = crumbs_avx2_t<LINE>(src + i, p, n - i, dst + (p >> 2), code, w, &nl);
+        } else {
+            took = n - i;
+            if (LINE) { const void* e = std::memchr(src + i, '\n', n - i); if (e) { took = static_cast<size_t>(static_cast<const uint8_t*>(e) - (src + i)); nl = true; } }
+            crumbs_scalar(src + i, p, took, dst + (p >> 2), code, w);
+        }
+        p += took; i += took;
+    }
+    if (LINE) {
+        if (nl && i > 0 && src[i - 1] == '\r' && !w.dead) {     // CRLF: the '\r' went in as an exception (crumb 0, base set 0) -- take it back
+            p--; i--; w.cur--;
+        }
+        *line_len = i; *found = nl;
     }
     *pos = p; *n_exc = w.cur;
     return !w.dead;
+}
+bool crumbs_append(const uint8_t* src, size_t n, uint8_t* dst, uint64_t* pos, uint64_t* exc, size_t exc_cap, size_t* n_exc, const uint8_t* code) {
+    return append_impl<false>(src, n, dst, pos, exc, exc_cap, n_exc, code, nullptr, nullptr);
+}
+bool crumbs_append_line(const uint8_t* src, size_t n, uint8_t* dst, uint64_t* pos, uint64_t* exc, size_t exc_cap, size_t* n_exc, const uint8_t* code,
+                        size_t* line_len, bool* found) {
+    return append_impl<true>(src, n, dst, pos, exc, exc_cap, n_exc, code, line_len, found);
 }
 
 int pack_default_threads() {

@@ -17,5 +17,9 @@ double pack_crumbs(const uint8_t* src, size_t n, uint8_t* dst, uint64_t* exc, si
 // exceptions are appended at exc[*n_exc ...) with their position IN THE STREAM.  One writer per stream; false = exception list full.
 // (For producers that pack while they parse: the bytes of a read are touched once, while they are still in the cache.)
 bool crumbs_append(const uint8_t* src, size_t n, uint8_t* dst, uint64_t* pos, uint64_t* exc, size_t exc_cap, size_t* n_exc, const uint8_t* code);
+// The same for a text line of unknown length: packs src[0, e) where e = index of the first '\n' in src[0, n) (*found) or n; a '\r' in front
+// of the '\n' is not part of the line.  *line_len = e.  One pass over the bytes instead of memchr + pack.
+bool crumbs_append_line(const uint8_t* src, size_t n, uint8_t* dst, uint64_t* pos, uint64_t* exc, size_t exc_cap, size_t* n_exc, const uint8_t* code,
+                        size_t* line_len, bool* found);
 int pack_default_threads();
 }  // namespace bb

@@ -145,8 +145,14 @@ int  bb_fetch_rows(bb_ctx *ctx, bb_row *rows, uint64_t rows_cap, uint64_t *n_row
    CUDA streams (each with its own worker thread and device buffers) so that the host-side packing, the host->device copy
    and the kernels of different batches overlap.  The caller owns `bases` and
    `offsets` until bb_collect has returned that batch_tag (they are read by the DMA engine in place: use pinned memory
-   for full PCIe speed).  `rows` returned by bb_collect stay valid until the next bb_submit / bb_collect on the ctx. */
+   for full PCIe speed).  `rows` returned by bb_collect live in the result buffer of the engine
+   that ran the batch (batch number i of a ctx runs on engine i % BB_MAX_INFLIGHT): they stay valid until BB_MAX_INFLIGHT further
+   batches have been submitted on the ctx, so a host may hand them to a writer thread and go on submitting. */
 #define BB_MAX_INFLIGHT 4
+/* optional, before the first bb_submit: sizes the device buffers of every engine for batches of up to max_reads reads / max_bases
+   bases and loads the kernels, by running an all-'A' batch of that shape through each engine (all engines at once).  Without it
+   the first BB_MAX_INFLIGHT batches pay for the allocations (tens of ms each); results are the same either way. */
+int  bb_reserve(bb_ctx *ctx, uint32_t max_reads, uint64_t max_bases);
 int  bb_submit(bb_ctx *ctx, const uint8_t *bases, const uint64_t *offsets, uint32_t n_reads, uint64_t batch_tag);
 int  bb_collect(bb_ctx *ctx, uint64_t *batch_tag, const bb_row **rows, uint64_t *n_rows);
 /* bb_submit for a host that packs while it parses (the FASTQ reader of `barbell annotate` does: src/io/io.rs:27-32 -> pinned ring):
@@ -183,6 +189,11 @@ int  bb_pack_crumbs(const uint8_t *src, uint64_t n, uint8_t *dst, uint64_t *exc,
    2 * (i & 3); dst bytes past the stream must be zero or unwritten), advances *pos, appends exception entries (stream position << 4 |
    set()) at exc[*n_exc ...) and advances *n_exc.  One writer per stream.  BB_ERR_OVERFLOW when exc_cap entries do not suffice. */
 int  bb_pack_crumbs_append(const uint8_t *src, uint64_t n, uint8_t *dst, uint64_t *pos, uint64_t *exc, uint64_t exc_cap, uint64_t *n_exc);
+/* the same for a text line whose length is not known yet (the sequence line of a FASTQ record, read in ONE pass): appends src[0, e),
+   e = index of the first '\n' in src[0, n) (*found = 1) or n (*found = 0); a '\r' in front of the '\n' is not part of the line;
+   *line_len = e without that '\r'.  dst needs 32 bytes of slack past the end of the stream (they are written as zero). */
+int  bb_pack_crumbs_append_line(const uint8_t *src, uint64_t n, uint8_t *dst, uint64_t *pos, uint64_t *exc, uint64_t exc_cap, uint64_t *n_exc,
+                                uint64_t *line_len, int *found);
 
 /* ---- the stages that consume annotation.tsv (host side, no GPU): filter, inspect, trim -- so that `barbell kit` runs the
  *      reference's whole pipeline, src/kits/use_kit.rs:11-109 ---- */

@@ -153,3 +153,49 @@ def test_pack_crumbs_append_builds_the_same_stream_read_by_read():
     r = np.frombuffer(b"ACGNNNNT", np.uint8).copy()
     pos, ne = C.c_uint64(0), C.c_uint64(0)
     assert bb.lib().bb_pack_crumbs_append(r.ctypes.data, 8, dst.ctypes.data, C.byref(pos), exc.ctypes.data, 2, C.byref(ne)) == -3
+
+
+def test_pack_crumbs_append_line_equals_append_of_the_line():
+    """bb_pack_crumbs_append_line (one pass: find the end of the line while packing it) against memchr + bb_pack_crumbs_append, for
+    lines whose end falls everywhere relative to the 128-base step and the 4-base byte, LF and CRLF, without a terminator, with
+    text behind the line (a quality string of the same length, as in a FASTQ record) and with a short readable window."""
+    import ctypes as C
+    import numpy as np
+    rnd = np.random.default_rng(13)
+    L = bb.lib()
+    lens = list(range(0, 12)) + [31, 32, 33, 63, 64, 65, 125, 126, 127, 128, 129, 130, 131, 132, 255, 256, 257, 383, 384, 385, 1000, 4099]
+    for start in (0, 1, 2, 3, 4, 130):
+        for term in (b"\n", b"\r\n", b""):
+            for n in lens:
+                seq = rnd.choice(np.frombuffer(b"ACGTacgtU", np.uint8), n)
+                odd = rnd.random(n) < 0.03
+                seq[odd] = rnd.choice(np.frombuffer(b"NnRY-x*\r", np.uint8), int(odd.sum()))
+                if n and seq[-1] == 13:
+                    seq[-1] = ord("A")                            # (a '\r' in front of the terminator would belong to it)
+                behind = b"" if not term else (b"+\n" + b"I" * n + b"\n@next\nACGT\n")
+                buf = np.frombuffer(seq.tobytes() + term + behind, np.uint8).copy()
+                for window in (len(buf), n + len(term), max(0, n - 5)):
+                    window = min(window, len(buf))
+                    want_len = min(n, window) if window < n + len(term) or not term else n
+                    want_found = 1 if (term and window >= n + len(term)) else 0
+                    if term == b"\r\n" and window == n + 1:
+                        want_len, want_found = n + 1, 0          # the '\r' alone is a (non-base) byte of the window
+                    if b"\n" in buf[:want_len].tobytes():
+                        continue
+                    cap = 4096
+                    da = np.zeros(2048, np.uint8); ea = np.zeros(cap, np.uint64); pa, na = C.c_uint64(start), C.c_uint64(0)
+                    db = np.zeros(2048, np.uint8); eb = np.zeros(cap, np.uint64); pb, nb = C.c_uint64(start), C.c_uint64(0)
+                    assert L.bb_pack_crumbs_append(buf.ctypes.data, want_len, da.ctypes.data, C.byref(pa), ea.ctypes.data, cap, C.byref(na)) == 0
+                    ll, found = C.c_uint64(99), C.c_int(9)
+                    assert L.bb_pack_crumbs_append_line(buf.ctypes.data, window, db.ctypes.data, C.byref(pb), eb.ctypes.data, cap, C.byref(nb),
+                                                        C.byref(ll), C.byref(found)) == 0
+                    key = (start, term, n, window)
+                    assert (ll.value, found.value) == (want_len, want_found), key
+                    assert pb.value == pa.value == start + want_len and nb.value == na.value, key
+                    assert (eb[:nb.value] == ea[:na.value]).all(), key
+                    assert (db == da).all(), key                  # ... including zeros behind the end of the stream
+    # a full exception list is reported
+    buf = np.frombuffer(b"NNNNNNNNNN\n", np.uint8).copy()
+    d = np.zeros(64, np.uint8); e = np.zeros(4, np.uint64); p, ne = C.c_uint64(0), C.c_uint64(0)
+    ll, found = C.c_uint64(0), C.c_int(0)
+    assert L.bb_pack_crumbs_append_line(buf.ctypes.data, len(buf), d.ctypes.data, C.byref(p), e.ctypes.data, 4, C.byref(ne), C.byref(ll), C.byref(found)) == -3

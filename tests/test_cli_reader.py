@@ -113,3 +113,16 @@ def test_parallel_chunked_reader_equals_sequential(tmp_path):
     assert r.returncode != 0 and ("quality length" in r.stdout or "malformed" in r.stdout), r.stdout
     empty = tmp_path / "empty.fastq"; empty.write_text("")
     assert stats([empty, pa], "--chunk-kb", "4")[0] == 70
+
+
+def test_many_tiny_reads_grow_the_offset_arrays(tmp_path):
+    """The read-offset arrays of a batch slot start sized for reads of >= 256 bases and grow: a chunk (parallel reader) / a batch
+    (sequential reader) with several hundred thousand 0..2-base reads must come through unchanged."""
+    import random
+    rnd = random.Random(5)
+    recs = [(b"r%d" % i, bytes(rnd.choice(b"ACGTN") for _ in range(i % 3))) for i in range(400_000)]
+    p = tmp_path / "tiny.fastq"
+    p.write_bytes(b"".join(b"@%s\n%s\n+\n%s\n" % (rid, seq, b"I" * len(seq)) for rid, seq in recs))
+    want = (len(recs), sum(len(s) for _, s in recs), fnv(recs))
+    assert stats([p], "--chunk-kb", "8192", "-t", "2", want_reader="parallel") == want
+    assert stats([p], "--single-reader", "--batch-mb", "1", want_reader="sequential") == want

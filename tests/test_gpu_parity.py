@@ -593,3 +593,28 @@ def test_barcodes_with_ambiguity_codes_in_the_patterns():
     b, o, _ = synth.make_reads(gs.as_dicts(), 800, (200, 2500), seed=124)
     rows = _check(gs, b, o)
     assert (rows["match_type"] < 2).sum() > 200
+
+
+@pytest.mark.gpu
+def test_reserve_changes_nothing_but_the_first_batch_cost():
+    """bb_reserve (every engine sized and warmed by an all-'A' batch of the given shape) before the first submit: rows and counters
+    of the batches that follow are those of a context that was not reserved; it is refused while batches are in flight."""
+    import torch
+    gs = bb.GroupSet.from_kit("SQK-NBD114-96")
+    b, o, _ = synth.make_reads(gs.as_dicts(), 3000, 3000, seed=77)
+    want = O.demux_batch(gs.as_dicts(), b, o)
+    hb = torch.from_numpy(b).pin_memory(); ho = torch.from_numpy(o.astype(np.uint64).view(np.int64)).pin_memory()
+    a0 = bb.Annotator(gs); a1 = bb.Annotator(gs)
+    a1.reserve(4000, 4000 * 3000)
+    assert a1.kernel_launches() == 0 and a1.counters() == dict(total=0, kept=0, dropped=0)
+    for an in (a0, a1):
+        for rep in range(5):                                      # past BB_MAX_INFLIGHT: every engine runs at least once
+            an.submit(hb.data_ptr(), ho.data_ptr(), len(o) - 1, tag=rep)
+            tag, rows = an.collect()
+            assert tag == rep and rows.tobytes() == want.tobytes()
+    assert a1.kernel_launches() <= a0.kernel_launches() and a0.counters() == a1.counters()
+    a1.submit(hb.data_ptr(), ho.data_ptr(), len(o) - 1, tag=9)
+    with pytest.raises(bb.BarbellError, match="in flight"):
+        a1.reserve(10, 1000)
+    a1.collect()
+    a0.close(); a1.close()

@@ -1,37 +1,28 @@
 #!/bin/bash
-# FASTQ -> annotation.tsv wall time of the CLI on synthetic 10 kb reads (configs[1] shape), sequential vs chunk-parallel reader.
-# usage: bash tools/cli_throughput.sh [n_reads] ; writes gpurun_out/cli/throughput.txt
+# CLI FASTQ -> annotation.tsv throughput on the GPU box (under gpurun): thread sweep, copy forms, parser alone, kit pipeline wall.
 set -u
-N=${1:-100000}
-OUT=gpurun_out/cli; mkdir -p $OUT; TMP=$(mktemp -d)
-python tools/make_fastq.py $TMP/reads.fastq $N > /dev/null
-ls -la $TMP/reads.fastq | awk '{print "fastq bytes", $5}' | tee $OUT/throughput.txt
-for mode in "--single-reader" "-t 4" "-t 8" "-t 8"; do
-  s=$(date +%s%N)
-  barbell_b200/barbell annotate --kit SQK-NBD114-96 -i $TMP/reads.fastq -o $TMP/out.tsv $mode | tail -1 | tee -a $OUT/throughput.txt
-  e=$(date +%s%N)
-  echo "| mode=[$mode] wall_ms=$(( (e - s) / 1000000 )) reads=$N" | tee -a $OUT/throughput.txt
-  md5sum $TMP/out.tsv | tee -a $OUT/throughput.txt
-done
-# the usual shape of a run: many small gzip files (one zlib stream each): one reader thread vs one file per worker
-python - "$TMP" <<'PY'
-import gzip, sys
-tmp = sys.argv[1]
-lines = open(tmp + "/reads.fastq", "rb").read(16 * 20000 * 4 * 5200).split(b"\n")   # first ~16k reads
-recs = [b"\n".join(lines[i:i + 4]) + b"\n" for i in range(0, len(lines) - 4, 4)]
-per = 1000
-for k in range(len(recs) // per):
-    with gzip.open(f"{tmp}/part{k:03d}.fastq.gz", "wb", compresslevel=4) as f:
-        f.write(b"".join(recs[k * per:(k + 1) * per]))
-print("gz parts:", len(recs) // per, "reads:", (len(recs) // per) * per)
-PY
-for mode in "--single-reader" "-t 8"; do
-  s=$(date +%s%N)
-  barbell_b200/barbell annotate --kit SQK-NBD114-96 -i $TMP/part*.fastq.gz -o $TMP/outz.tsv $mode | tail -2 | tr '\n' ' '
-  e=$(date +%s%N)
-  echo "| gzip parts mode=[$mode] wall_ms=$(( (e - s) / 1000000 ))" | tee -a $OUT/throughput.txt
-  md5sum $TMP/outz.tsv | tee -a $OUT/throughput.txt
-done
-s=$(date +%s%N); barbell_b200/barbell kit -k SQK-NBD114-96 -i $TMP/reads.fastq -o $TMP/kit -t 8 | tail -3 | tr '\n' ' '; e=$(date +%s%N)
-echo "| kit pipeline wall_ms=$(( (e - s) / 1000000 ))" | tee -a $OUT/throughput.txt
-rm -rf $TMP
+O=gpurun_out/cli; mkdir -p $O
+python tools/make_fastq.py /dev/shm/r.fastq 100000 > /dev/null
+F=/dev/shm/r.fastq
+{
+  lscpu | grep -i "model name\|^CPU(s)\|Thread(s) per core\|Socket" | tr -s ' '
+  ls -la $F | awk '{print "fastq bytes", $5, "(100000 reads of 10 kb); the file is named 10 times on the command line = 1 M reads, 20 GB of FASTQ text from the page cache"}'
+  for t in 4 8 12 16 24; do
+    echo "== -t $t"; barbell_b200/barbell annotate --kit SQK-NBD114-96 -i $F $F $F $F $F $F $F $F $F $F -o /dev/shm/x.tsv -t $t --verbose 2>&1 | grep -v "complete\|Auto"
+  done
+  for t in 8 16; do
+    echo "== -t $t --count-only (parsers alone)"; barbell_b200/barbell annotate --kit SQK-NBD114-96 -i $F $F $F $F $F $F $F $F $F $F -o /dev/shm/c.tsv -t $t --count-only --verbose 2>&1 | grep -v "complete\|Auto"
+  done
+  echo "== -t 16 --no-pack"; barbell_b200/barbell annotate --kit SQK-NBD114-96 -i $F $F $F $F $F $F $F $F $F $F -o /dev/shm/y.tsv -t 16 --no-pack --verbose 2>&1 | grep -v "complete\|Auto"
+  md5sum /dev/shm/x.tsv /dev/shm/y.tsv
+  barbell_b200/barbell annotate --kit SQK-NBD114-96 -i $F -o /dev/shm/one.tsv -t 16 | tail -2 | head -1; md5sum /dev/shm/one.tsv
+  s=$(date +%s%N); barbell_b200/barbell kit -k SQK-NBD114-96 -i $F -o /dev/shm/kit -t 16 | tail -3 | tr '\n' ' '; e=$(date +%s%N); echo "| kit pipeline wall_ms=$(( (e - s) / 1000000 ))"
+  s=$(date +%s%N); barbell_b200/barbell annotate --kit SQK-NBD114-96 -i $F -o /dev/shm/one.tsv -t 16 > /dev/null; e=$(date +%s%N); echo "| annotate alone wall_ms=$(( (e - s) / 1000000 ))"
+} > $O/cli_throughput.txt 2>&1
+cat $O/cli_throughput.txt
+python bench.py --steps 10 --warmup 3 --no-cpu-baseline --e2e-modes > $O/bench_nbd.json 2> $O/bench_nbd.err
+python - <<'P'
+import json
+j = json.loads(open('gpurun_out/cli/bench_nbd.json').read().strip().splitlines()[-1])
+print('value', j['value'], 'e2e', j['e2e'], 'packed', j.get('e2e_packed', {}).get('value'), 'fastq', j.get('e2e_fastq', {}).get('value'))
+P
