@@ -104,7 +104,8 @@ void crumbs_scalar(const uint8_t* src, size_t pos0, size_t n, uint8_t* dst, cons
 // crumb and a second one the lower-case letter that nibble stands for; a byte is a single base iff (c | 0x20) equals that letter
 // (bytes >= 0x80 look up 0 and fail).  Everything else gets crumb 0 and an exception entry with its 4-bit base set.  Four bytes of
 // crumbs are folded into one with two multiply-adds (1, 4 per byte pair; 1, 16 per word pair), 4 x 8 dwords are narrowed to 32 bytes.
-// Only blocks with a byte that is not a single base leave the straight path (one movemask per 128 bytes).
+// Only blocks with a byte that is not a single base leave the straight path (one movemask per 128 bytes) -- for its exception entries;
+// the crumbs are already right (such a byte has crumb 0).
 // LINE: the input is a text line of unknown length <= n: stop in front of the first '\n' (*found), which -- not being a base -- can
 // only sit in such a block.  The block that holds the end of the input is packed from a copy (or in place when 128 bytes are
 // readable) with the crumbs past the end forced to 0: the next read ORs its first bases into the partly used last byte.
@@ -166,15 +167,28 @@ __attribute__((target("avx2"))) size_t crumbs_avx2_t(const uint8_t* src, size_t 
             c[q] = _mm256_and_si256(_mm256_shuffle_epi8(k.CR, v), ok);
             all = _mm256_and_si256(all, ok);
         }
-        if (__builtin_expect(_mm256_movemask_epi8(all) != -1, 0)) {           // rare: a byte that is not a single base (or the end of the line)
+        if (__builtin_expect(_mm256_movemask_epi8(all) != -1, 0)) {           // a byte that is not a single base (or the end of the line)
             size_t len = 128;
-            if (LINE) {
-                const void* nl = std::memchr(src + i, '\n', 128);
-                if (nl) len = static_cast<size_t>(static_cast<const uint8_t*>(nl) - (src + i));
+            for (int q = 0; q < 4 && len == 128; q++) {
+                const __m256i v = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + i + 32 * q));   // (not kept live: the straight path needs the registers)
+                const __m256i ok = _mm256_cmpeq_epi8(_mm256_or_si256(v, k.lower), _mm256_shuffle_epi8(k.L, v));
+                uint32_t m = ~static_cast<uint32_t>(_mm256_movemask_epi8(ok));
+                while (m) {
+                    const int t = __builtin_ctz(m); m &= m - 1;
+                    const size_t at = static_cast<size_t>(32 * q + t);
+                    if (LINE && src[i + at] == '\n') { len = at; break; }
+                    w.push(static_cast<uint64_t>(pos0 + i + at) << 4 | code[src[i + at]]);
+                }
             }
-            crumbs_block_masked(src + i, len, pos0 + i, dst + (i >> 2), code, w, k);
-            if (len < 128) { *found = true; return i + len; }
-            continue;
+            if (LINE && len < 128) {                                          // the line ends in this block: crumbs past its end are 0
+                for (int q = 0; q < 4; q++) {
+                    const int left = static_cast<int>(len) - 32 * q;
+                    c[q] = _mm256_and_si256(c[q], _mm256_cmpgt_epi8(_mm256_set1_epi8(static_cast<char>(std::max(0, std::min(127, left)))), k.iota));
+                }
+                _mm256_storeu_si256(reinterpret_cast<__m256i*>(dst + (i >> 2)), crumbs_fold(c, k));
+                *found = true;
+                return i + len;
+            }
         }
         const __m256i pk = crumbs_fold(c, k);
         if (aligned) _mm256_stream_si256(reinterpret_cast<__m256i*>(dst + (i >> 2)), pk);   // no read-for-ownership of the output
