@@ -9,6 +9,7 @@
 #include <sys/mman.h>
 #include <sys/resource.h>
 #include <sys/stat.h>
+#include <sys/syscall.h>
 #include <unistd.h>
 #include <zlib.h>
 
@@ -376,6 +377,9 @@ class ParallelSource : public BatchSource {
         return true;
     }
     void work() {
+        // the parsers take every core they get; the few threads that feed the GPU and write the rows (short bursts, latency bound)
+        // must not queue behind them: parsers run at a lower priority (a thread may always lower its own)
+        if (!std::getenv("BB_PARSER_NICE_OFF")) setpriority(PRIO_PROCESS, static_cast<id_t>(syscall(SYS_gettid)), 10);
         for (;;) {
             const size_t i = claim_.fetch_add(1);
             if (i >= n_chunks_) return;

@@ -293,10 +293,15 @@ def main():
         except (AttributeError, OSError):
             os.environ.setdefault("BB_PACK_THREADS", str(max(1, (os.cpu_count() or 1) // local_world)))
 
-    sampler = ClockSampler(local)
-    sampler.start()                                         # early: nvidia-smi takes a few hundred ms to deliver its first line
     gs = product_groups(cfg)
     G = gs.as_dicts()
+    # the CLI leg first, while this process holds no CUDA context, pinned memory or helper threads: it is its own process and
+    # should see the machine the way a user's `barbell annotate` does
+    e2e_fastq = None
+    if world == 1 and not args.no_e2e_fastq:
+        e2e_fastq = fastq_leg(cfg, G, args.fastq_reads, args.fastq_passes, min(16, os.cpu_count() or 1))
+    sampler = ClockSampler(local)
+    sampler.start()                                         # early: nvidia-smi takes a few hundred ms to deliver its first line
     an = bb.Annotator(gs, device=local)
     n_reads = args.reads or cfg["reads"]
     bases, offsets, _ = make_batch(G, n_reads, synth.SEED0 + 2 + 1000 * rank)
@@ -492,8 +497,8 @@ def main():
                    e2e=e2e, e2e_packed=e2e_packed, gpu_launches=int(launches), clocks=clocks, rows_per_step=int(n_rows), counters=summed,
                    label_counts=dict(labels_seen=int((hist[1:] > 0).sum()), rows=int(hist.sum()), flank_only_rows=int(hist[0]),
                                      note="rows per barcode of the last step, all ranks (all_reduce of %d int64)" % len(hist)))
-        if world == 1 and not args.no_e2e_fastq:
-            out["e2e_fastq"] = fastq_leg(cfg, G, args.fastq_reads, args.fastq_passes, min(16, os.cpu_count() or 1))
+        if e2e_fastq is not None:
+            out["e2e_fastq"] = e2e_fastq
         if world == 1 and not args.no_cpu_baseline:       # (rank 0 at N = 1 only)
             import oracle_lib as O
             Go = oracle_groups(cfg)

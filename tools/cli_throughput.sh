@@ -11,8 +11,9 @@ F=/dev/shm/r.fastq
     echo "== -t $t"; barbell_b200/barbell annotate --kit SQK-NBD114-96 -i $F $F $F $F $F $F $F $F $F $F -o /dev/shm/x.tsv -t $t --verbose 2>&1 | grep -v "complete\|Auto"
   done
   for t in 8 16; do
-    echo "== -t $t --count-only (parsers alone)"; barbell_b200/barbell annotate --kit SQK-NBD114-96 -i $F $F $F $F $F $F $F $F $F $F -o /dev/shm/c.tsv -t $t --count-only --verbose 2>&1 | grep -v "complete\|Auto"
+    echo "== fastq-stats --count-only -t $t (the parsers alone, no GPU)"; barbell_b200/barbell fastq-stats -i $F $F $F $F $F $F $F $F $F $F -t $t --count-only 2>&1 | grep timing
   done
+  echo "== -t 16 --batch-mb 256"; barbell_b200/barbell annotate --kit SQK-NBD114-96 -i $F $F $F $F $F $F $F $F $F $F -o /dev/shm/x.tsv -t 16 --batch-mb 256 --verbose 2>&1 | grep -v "complete\|Auto"
   echo "== -t 16 --no-pack"; barbell_b200/barbell annotate --kit SQK-NBD114-96 -i $F $F $F $F $F $F $F $F $F $F -o /dev/shm/y.tsv -t 16 --no-pack --verbose 2>&1 | grep -v "complete\|Auto"
   md5sum /dev/shm/x.tsv /dev/shm/y.tsv
   barbell_b200/barbell annotate --kit SQK-NBD114-96 -i $F -o /dev/shm/one.tsv -t 16 | tail -2 | head -1; md5sum /dev/shm/one.tsv
@@ -20,9 +21,9 @@ F=/dev/shm/r.fastq
   s=$(date +%s%N); barbell_b200/barbell annotate --kit SQK-NBD114-96 -i $F -o /dev/shm/one.tsv -t 16 > /dev/null; e=$(date +%s%N); echo "| annotate alone wall_ms=$(( (e - s) / 1000000 ))"
 } > $O/cli_throughput.txt 2>&1
 cat $O/cli_throughput.txt
-python bench.py --steps 10 --warmup 3 --no-cpu-baseline --e2e-modes > $O/bench_nbd.json 2> $O/bench_nbd.err
+python bench.py --steps 10 --warmup 3 --no-cpu-baseline --e2e-modes > $O/bench_nbd_e2e_modes.json 2> $O/bench_nbd.err
 python - <<'P'
 import json
-j = json.loads(open('gpurun_out/cli/bench_nbd.json').read().strip().splitlines()[-1])
+j = json.loads(open('gpurun_out/cli/bench_nbd_e2e_modes.json').read().strip().splitlines()[-1])
 print('value', j['value'], 'e2e', j['e2e'], 'packed', j.get('e2e_packed', {}).get('value'), 'fastq', j.get('e2e_fastq', {}).get('value'))
 P
