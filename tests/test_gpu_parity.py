@@ -618,3 +618,37 @@ def test_reserve_changes_nothing_but_the_first_batch_cost():
         a1.reserve(10, 1000)
     a1.collect()
     a0.close(); a1.close()
+
+
+@pytest.mark.gpu
+def test_cli_error_paths_end_cleanly(tmp_path):
+    """`barbell annotate` with its parser threads, GPU workers and writer thread: an unwritable output and a malformed record in
+    the middle of the stream must end the run with the reference's message and without "Annotation complete!" (the exit code stays
+    0 like the reference's, bin/main.rs:301-304), not with a hang or a truncated-but-successful file."""
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(bb.lib_path()), "barbell")
+    gs, bases, offsets, rows, _ = cases.load_case("nbd_1k")
+    n = len(offsets) - 1
+    def rec(i):
+        s = bases[int(offsets[i]):int(offsets[i + 1])].tobytes().decode()
+        return f"@read_{i}\n{s}\n+\n{'I' * len(s)}\n"
+    good = "".join(rec(i) for i in range(n))
+    fq = tmp_path / "good.fastq"; fq.write_text(good * 3)
+    if os.path.exists("/dev/full"):
+        r = subprocess.run([exe, "annotate", "--kit", "SQK-NBD114-96", "-i", str(fq), "-o", "/dev/full", "-t", "4", "--chunk-kb", "256"],
+                           capture_output=True, text=True, timeout=120)
+        assert "Error during processing: write to /dev/full failed" in r.stdout and "Annotation complete!" not in r.stdout, r.stdout + r.stderr
+    bad = tmp_path / "bad.fastq"; bad.write_text(good * 2 + "@broken\nACGT\n+\nII\n" + good)
+    for extra in (["-t", "4", "--chunk-kb", "256"], ["--single-reader"]):
+        out = tmp_path / "bad.tsv"
+        r = subprocess.run([exe, "annotate", "--kit", "SQK-NBD114-96", "-i", str(bad), "-o", str(out)] + extra, capture_output=True, text=True, timeout=120)
+        assert "Error during processing" in r.stdout and ("quality length" in r.stdout or "malformed" in r.stdout), r.stdout + r.stderr
+        assert "Annotation complete!" not in r.stdout
+    # and the good file through the same small chunks gives the golden rows three times over
+    out = tmp_path / "good.tsv"
+    r = subprocess.run([exe, "annotate", "--kit", "SQK-NBD114-96", "-i", str(fq), "-o", str(out), "-t", "6", "--chunk-kb", "256"],
+                       capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "Annotation complete!" in r.stdout, r.stdout + r.stderr
+    want = open(cases.GOLD + "/nbd_1k.annotation.tsv").read().splitlines(keepends=True)
+    assert open(out).read() == want[0] + "".join(want[1:]) * 3
