@@ -44,3 +44,13 @@ clean, oclean, _ = synth.make_reads(gs.as_dicts(), 600, (2000, 5000), seed=36, n
 an = bb.Annotator(gs, pack_h2d="crumbs")
 print("NBD crumb copy, 0.1 % N:", len(an.annotate(clean, oclean)), "rows")
 an.close()
+# bb_reserve (all-'A' batch through every engine) followed by a real batch through the pipelined form
+import torch
+an = bb.Annotator(gs)
+an.reserve(1000, 1000 * 3000)
+hb = torch.from_numpy(clean).pin_memory(); ho = torch.from_numpy(oclean.astype(np.uint64).view(np.int64)).pin_memory()
+for rep in range(5):
+    an.submit(hb.data_ptr(), ho.data_ptr(), len(oclean) - 1, tag=rep)
+    tag, rows = an.collect()
+print("reserve + 5 pipelined batches:", len(rows), "rows each")
+an.close()
