@@ -134,6 +134,11 @@ struct Engine {
         BB_CUDA(d_counters.ensure(64));
         for (auto& e : ev) BB_CUDA(cudaEventCreate(&e));
         for (auto& e : ev_copy) BB_CUDA(cudaEventCreate(&e));
+#if BB_K3_LUT_GLOBAL
+        uint32_t lut[256];
+        for (int q = 0; q < 256; q++) lut[q] = scan_lut_entry(q);
+        BB_CUDA(cudaMemcpyToSymbol(g_k3_scan_lut, lut, sizeof lut));
+#endif
         return BB_OK;
     }
     void destroy() {

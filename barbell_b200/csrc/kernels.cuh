@@ -1017,7 +1017,7 @@ struct BarArgs {
 
 constexpr int kMaxBarRounds = 16;   // up to 512 barcodes per group
 #ifndef BB_K3_MIN_CTAS
-#define BB_K3_MIN_CTAS 16            // resident warps (= CTAs) per SM the register allocation of k_barcode_rows aims at
+#define BB_K3_MIN_CTAS 18            // resident warps (= CTAs) per SM the register allocation of k_barcode_rows aims at
 #endif
 
 __device__ __forceinline__ int64_t rel_dist_to_end(int64_t pos, int64_t read_len) {   // searcher.rs:183-199
@@ -1048,10 +1048,19 @@ struct TopTwo {
 
 // Shared memory of one k_barcode_rows CTA (= one warp): the scan table, the 16 text masks, the records of the shared leading rows,
 // one traceback record byte per row and lane, and the lanes' own-row records.
+#ifndef BB_K3_LUT_GLOBAL
+#define BB_K3_LUT_GLOBAL 1
+#endif
+#if BB_K3_LUT_GLOBAL
+__device__ uint32_t g_k3_scan_lut[256];      // scan_lut_entry(), filled by Engine::init (read through L1: frees 1 KB of every CTA's shared memory)
+constexpr size_t kK3LutBytes = 0;
+#else
+constexpr size_t kK3LutBytes = 1024;
+#endif
 template <int NWT, bool PACKED, bool MITM>
 __host__ __device__ inline size_t barcode_rows_smem(int sh_rows, int own_rows) {
-    return 1024 + 16 * NWT * 8 + ((static_cast<size_t>(sh_rows) * 3 * NWT * 8 + 15) & ~static_cast<size_t>(15)) + 64 + static_cast<size_t>(sh_rows) * 32 + 64 * kOffStride +
-           row_hist_bytes<NWT, PACKED>(resident_rows(own_rows, MITM)) + 16;
+    return kK3LutBytes + 16 * NWT * 8 + ((static_cast<size_t>(sh_rows) * 3 * NWT * 8 + 15) & ~static_cast<size_t>(15)) + 64 + static_cast<size_t>(sh_rows) * 32 +
+           static_cast<size_t>(sh_rows) * kOffStride + row_hist_bytes<NWT, PACKED>(resident_rows(own_rows, MITM)) + 16;
 }
 
 // One warp (= one CTA) per flank match; lane = barcode pattern (rounds of 32).  The region's text masks and the pattern rows
@@ -1066,14 +1075,18 @@ template <int NWT, bool PACKED, bool S2PAT, bool MITM>
 __global__ void __launch_bounds__(32, NWT == 1 ? BB_K3_MIN_CTAS : 1) k_barcode_rows(const BarArgs A) {
     extern __shared__ __align__(16) unsigned char bar_smem[];
     const int lane = threadIdx.x;
-    uint32_t* lut = reinterpret_cast<uint32_t*>(bar_smem);                                 // [256] bottom-row scan table
-    uint64_t* tm = reinterpret_cast<uint64_t*>(bar_smem + 1024);                           // [16][NWT]
+#if BB_K3_LUT_GLOBAL
+    const uint32_t* lut = g_k3_scan_lut;                                                   // [256] bottom-row scan table
+#else
+    uint32_t* lut = reinterpret_cast<uint32_t*>(bar_smem);
+    for (int q = threadIdx.x; q < 256; q += 32) lut[q] = scan_lut_entry(q);
+#endif
+    uint64_t* tm = reinterpret_cast<uint64_t*>(bar_smem + kK3LutBytes);                    // [16][NWT]
     uint64_t* sh = tm + 16 * NWT;                                                          // [sh_rows][3][NWT]
     uint8_t* s_shoff = reinterpret_cast<uint8_t*>(sh) + ((static_cast<size_t>(A.sh_rows) * 3 * NWT * 8 + 15) & ~static_cast<size_t>(15));   // [64] codes of the shared rows
     uint8_t* rec = s_shoff + 64;                                                           // [sh_rows][32]
-    uint8_t* s_off = rec + static_cast<size_t>(A.sh_rows) * 32;                            // [64 rows][32 lanes] pattern codes of the round
-    const RowHist<NWT, PACKED> hist{reinterpret_cast<uint32_t*>(s_off + 64 * kOffStride), lane};
-    for (int q = lane; q < 256; q += 32) lut[q] = scan_lut_entry(q);
+    uint8_t* s_off = rec + static_cast<size_t>(A.sh_rows) * 32;                            // [sh_rows][32 lanes] pattern codes of the round
+    const RowHist<NWT, PACKED> hist{reinterpret_cast<uint32_t*>(s_off + static_cast<size_t>(A.sh_rows) * kOffStride), lane};
     const uint32_t n_hits = __ldg(A.n_hits);
     for (uint32_t h = blockIdx.x; h < n_hits; h += gridDim.x) {
         const Hit H = A.hits[h];
