@@ -39,6 +39,13 @@ constexpr int kPolMask = 63;
 // [strand][round of 32 barcodes][row][lane], so a round's codes are one contiguous block that the warp copies into shared
 // memory with a few 16-byte loads, and a warp's read of one row is 32 consecutive bytes (conflict-free).
 constexpr int kOffStride = 32;
+#ifndef BB_K3_UNROLL_F
+#define BB_K3_UNROLL_F 4             // rows per iteration of the forward loop / of the traceback over a lane's own rows
+#endif
+#ifndef BB_K3_UNROLL_T
+#define BB_K3_UNROLL_T 2
+#endif
+constexpr int kK3UnrollF = BB_K3_UNROLL_F, kK3UnrollT = BB_K3_UNROLL_T;
 BB_HD uint32_t ld_code(const uint8_t* p) { return *p; }
 
 BB_HD int bb_clz64(uint64_t x) {
@@ -264,7 +271,7 @@ BB_HD void rows_lane(const uint64_t* tm, const uint8_t* offs, int rn, int L, int
         RowHist<NWT, PACKED> hp = hist;
         hp.w += slot0 * kRowWords;
         const uint8_t* cp = offs + r0 * kOffStride;
-#pragma unroll 2
+#pragma unroll kK3UnrollF
         for (int r = r0; r < r1; r++, cp += kOffStride) {
             const uint64_t* e = row_mask<NWT>(tm, ld_code(cp));
             uint64_t ev[NWT], diag[NWT], stop[NWT];
@@ -394,7 +401,7 @@ BB_HD void rows_lane(const uint64_t* tm, const uint8_t* offs, int rn, int L, int
         if (MITM && i > H && lo <= H) lo = H + 1;
         if (i > P) {
             if (lo <= P) lo = P + 1;
-#pragma unroll 2
+#pragma unroll kK3UnrollT
             for (; i >= lo; i--, cp -= kOffStride, hp.w -= kRowWords) {
                 uint64_t diag[NWT], stop[NWT];
                 hp.load(0, diag, stop);
