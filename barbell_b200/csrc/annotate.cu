@@ -789,7 +789,7 @@ int bb_set_groups(bb_ctx* c, const bb_group* groups, int32_t n_groups) {
         const int m = S.flank_len;
         if (m < 1 || m > 64 * kMaxFlankWords) return bad("flank length must be 1..128");
         if (S.bar_len < 1 || S.bar_len > kMaxBarLen) return bad("padded barcode length must be 1..64");
-        if (S.n_barcodes < 1 || S.n_barcodes > 32 * kMaxBarRounds) return bad("1..512 barcodes per group");
+        if (S.n_barcodes < 1 || S.n_barcodes > 32 * kMaxBarRounds) return bad("1..4096 barcodes per group");
         if (S.k_flank < 0 || S.k_flank > 120) return bad("flank threshold must be 0..120");
         const int ov_m = over_cost(m);
         if (S.bar1 - S.bar0 + 1 + S.k_flank + 2 * kPadding > kRegionMax) return bad("barcode region (mask + k + 20) exceeds 160 characters");

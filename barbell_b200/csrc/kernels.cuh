@@ -1015,7 +1015,7 @@ struct BarArgs {
     int pol;                  // kPolS1Left | kPolS5Last (S2 is a template parameter)
 };
 
-constexpr int kMaxBarRounds = 16;   // up to 512 barcodes per group
+constexpr int kMaxBarRounds = 128;  // up to 4096 barcodes per group (a bound on the pattern table, 256 KB per strand at that size; the kernels loop over rounds)
 #ifndef BB_K3_MIN_CTAS
 #define BB_K3_MIN_CTAS 18            // resident warps (= CTAs) per SM the register allocation of k_barcode_rows aims at
 #endif

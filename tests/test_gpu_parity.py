@@ -652,3 +652,28 @@ def test_cli_error_paths_end_cleanly(tmp_path):
     assert r.returncode == 0 and "Annotation complete!" in r.stdout, r.stdout + r.stderr
     want = open(cases.GOLD + "/nbd_1k.annotation.tsv").read().splitlines(keepends=True)
     assert open(out).read() == want[0] + "".join(want[1:]) * 3
+
+
+@pytest.mark.gpu
+def test_large_barcode_panel_1200_patterns():
+    """A group may hold up to 4096 barcodes (the reference has no limit, barcodes.rs:106-197): 1200 patterns = 38 rounds of 32
+    lanes with a partly filled last round, through the barcode stage's fallback rule and top-two reduction; a group beyond the
+    limit is refused with a message."""
+    rnd = np.random.default_rng(321)
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    pre, suf = b"GGTCTAGACCATGCTAGGAT", b"TTGACCGATTCAGGCATCAA"
+    def panel(n):
+        seqs = []
+        for i in range(n):
+            core = bytearray(bytes(rnd.choice(acgt, 24)))
+            core[0] = b"ACGT"[i % 4]; core[-1] = b"ACGT"[(i // 4) % 4]
+            seqs.append(pre + bytes(core) + suf)
+        return seqs
+    gs = bb.GroupSet.from_seqs([(panel(1200), [f"P{i}" for i in range(1200)], 0)])
+    b, o, _ = synth.make_reads(gs.as_dicts(), 600, (200, 2500), seed=322)
+    rows = _check(gs, b, o)
+    tags = rows[rows["match_type"] < 2]
+    assert len(tags) > 150 and tags["label_idx"].max() >= 1024 and len(np.unique(tags["label_idx"])) > 100
+    big = bb.GroupSet.from_seqs([(panel(4100), [f"Q{i}" for i in range(4100)], 0)])
+    with pytest.raises(bb.BarbellError, match="barcodes per group"):
+        bb.Annotator(big)
